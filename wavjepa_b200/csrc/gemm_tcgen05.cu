@@ -1,0 +1,580 @@
+// tcgen05 / TMEM / TMA GEMM core for the WavJEPA hot path (sm_100a only).
+//
+// One persistent, warp-specialised kernel serves every GEMM-shaped op of the path:
+//   * Linear layers fwd / dgrad            (reference: torch.nn.Linear inside nn.TransformerEncoderLayer,
+//                                            wavjepa/jepa.py:126-132; MHA in/out-proj, MLP, the three mappers)
+//   * Conv1d 512->512 (k3 s2, k2 s2) fwd / dgrad as implicit GEMM over channels-last activations
+//                                           (reference: nn.Conv1d, wavjepa/extractors/audio_feature_extractor.py:70)
+//   * weight gradients (WGRAD mode: both operands MN-major, split over the token dimension, fp32 reduce-add)
+//
+// Layout of a CTA (384 threads, 1 CTA / SM, grid = min(#tiles, #SMs), static round-robin tile schedule):
+//   warp 0      : TMA producer (one elected lane)   global -> 128B-swizzled smem ring (STAGES deep)
+//   warp 1      : MMA issuer   (one elected lane)   tcgen05.mma.cta_group::1.kind::f16, D in TMEM (2 accumulators)
+//   warp 2      : TMEM allocator / deallocator
+//   warp 3      : idle
+//   warps 4..11 : epilogue: tcgen05.ld -> registers -> fused bias / GELU / GELU' / residual -> global
+//
+// Operand addressing is "virtual column" based so that the same kernel covers implicit-GEMM convolutions: the
+// reduction (normal mode) or output-column (WGRAD mode) index vc is split into segments of `seg.width` columns;
+// segment s reads the 4-D tensor map at (vc % width, seg.q[s], row + seg.p[s], batch).  A plain matrix is the
+// single-segment case.
+#include "ptx.cuh"
+#include "common.cuh"
+
+#include <stdio.h>
+#include <string.h>
+
+namespace wj {
+
+struct SegInfo {
+  int width;
+  int q[4];
+  int p[4];
+};
+
+struct GemmParams {
+  int L;             // rows per batch entry (normal: output rows; wgrad: reduction rows)
+  int batch;
+  int N;             // normal: output columns.  wgrad: output columns (= virtual columns of operand B)
+  int K;             // normal: reduction length (virtual columns of A).  wgrad: unused
+  int M;             // wgrad: output rows (columns of operand A)
+  int mb_per_batch;  // normal: ceil(L / 128)
+  int m_blocks;      // normal: batch * mb_per_batch; wgrad: M / 128
+  int n_blocks;
+  int total_tiles;
+  int splits;        // wgrad: split of the reduction
+  int kb_per_batch;  // wgrad: ceil(L / 64)
+  SegInfo seg;       // normal: segments of A's K;  wgrad: segments of B's N
+  // epilogue
+  void* out;
+  long long ld_out;
+  int out_f32;
+  int accumulate;    // out (fp32) += result with red.global.add
+  bf16* out2;        // optional second output (pre-activation, bf16)
+  long long ld_out2;
+  const float* bias;
+  const void* resid;
+  int resid_f32;
+  long long ld_resid;
+  int resid_mod;     // residual row = row % resid_mod when > 0 (positional table broadcast)
+  const bf16* aux;   // pre-activation for act == 2
+  long long ld_aux;
+  int act;           // 0 none; 1: h = bf16(acc + bias), out2 = h, v = gelu(h); 2: v = acc * gelu'(aux)
+  const int* out_rows;  // optional row indirection for the output / residual / aux rows (scatter), -1 = skip
+};
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int kThreads = 384;
+constexpr int kEpiWarp0 = 4;
+constexpr int kEpiWarps = 8;
+
+template <int BN>
+struct Cfg {
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN == 256) ? 4 : ((BN == 128) ? 6 : 8);
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+__device__ __forceinline__ void seg_coords(const SegInfo& s, int vc, int& c0, int& q, int& p) {
+  if (s.width > 0) {
+    const int si = vc / s.width;
+    c0 = vc - si * s.width;
+    q = s.q[si];
+    p = s.p[si];
+  } else {
+    c0 = vc;
+    q = 0;
+    p = 0;
+  }
+}
+
+template <int BN, bool WGRAD>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+  using C = Cfg<BN>;
+  constexpr int STAGES = C::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * C::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], kEpiWarps);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // ------------------------------------------------------------------------------------------ tile decode helpers
+  // normal: tile -> (m_blk, n_blk), n fastest (CTAs running together share the A rows through L2)
+  // wgrad : tile -> (split, m_blk, n_blk)
+  auto num_kb = [&](int tile) -> int {
+    if constexpr (!WGRAD) {
+      return p.K / BK;
+    } else {
+      const int split = tile / (p.m_blocks * p.n_blocks);
+      const int kb_total = p.batch * p.kb_per_batch;
+      const int per = (kb_total + p.splits - 1) / p.splits;
+      const int lo = split * per;
+      int hi = lo + per;
+      if (hi > kb_total) hi = kb_total;
+      return hi > lo ? hi - lo : 0;
+    }
+  };
+
+  if (warp == 0) {
+    // ======================================================================================= TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        if constexpr (!WGRAD) {
+          const int m_blk = tile / p.n_blocks;
+          const int n_blk = tile - m_blk * p.n_blocks;
+          const int b = m_blk / p.mb_per_batch;
+          const int row0 = (m_blk - b * p.mb_per_batch) * BM;
+          const int nkb = p.K / BK;
+          for (int kb = 0; kb < nkb; ++kb) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* sa = smem + stage * C::STAGE_BYTES;
+            uint8_t* sb = sa + C::A_BYTES;
+            int c0, q, po;
+            seg_coords(p.seg, kb * BK, c0, q, po);
+            mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+            tma_load_4d(sa, &tmA, &full_bar[stage], c0, q, row0 + po, b);
+            tma_load_2d(sb, &tmB, &full_bar[stage], kb * BK, n_blk * BN);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        } else {
+          const int mn = p.m_blocks * p.n_blocks;
+          const int split = tile / mn;
+          const int rem = tile - split * mn;
+          const int m_blk = rem / p.n_blocks;
+          const int n_blk = rem - m_blk * p.n_blocks;
+          const int kb_total = p.batch * p.kb_per_batch;
+          const int per = (kb_total + p.splits - 1) / p.splits;
+          const int lo = split * per;
+          const int hi = min(lo + per, kb_total);
+          for (int kb = lo; kb < hi; ++kb) {
+            const int b = kb / p.kb_per_batch;
+            const int row0 = (kb - b * p.kb_per_batch) * BK;
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* sa = smem + stage * C::STAGE_BYTES;
+            uint8_t* sb = sa + C::A_BYTES;
+            mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+            // A operand: dY[b, row, m] (m contiguous): two 64-wide MN atoms of 64 reduction rows each
+#pragma unroll
+            for (int a = 0; a < BM / 64; ++a)
+              tma_load_4d(sa + a * (BK * 128), &tmA, &full_bar[stage], m_blk * BM + a * 64, 0, row0, b);
+            // B operand: X[b, row + p, (q), n] : BN/64 atoms, each may live in a different segment
+#pragma unroll
+            for (int a = 0; a < BN / 64; ++a) {
+              int c0, q, po;
+              seg_coords(p.seg, n_blk * BN + a * 64, c0, q, po);
+              tma_load_4d(sb + a * (BK * 128), &tmB, &full_bar[stage], c0, q, row0 + po, b);
+            }
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ======================================================================================= MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, WGRAD, WGRAD);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        const int nkb = num_kb(tile);
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
+          const uint32_t sb = sa + C::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            uint64_t da, db;
+            if constexpr (!WGRAD) {
+              // K-major, 128B swizzle: rows of 128 B, 8-row groups 1024 B apart; advance 16 elements = 32 B
+              da = umma_smem_desc_sw128(sa + k * 32, 0, 1024);
+              db = umma_smem_desc_sw128(sb + k * 32, 0, 1024);
+            } else {
+              // MN-major, 128B swizzle: atom = 64 (MN) x 8 (K) = 1024 B; K groups 1024 B apart (SBO),
+              // MN atoms BK*128 B apart (LBO); advance 16 reduction rows = 2048 B
+              da = umma_smem_desc_sw128(sa + k * 2048, BK * 128, 1024);
+              db = umma_smem_desc_sw128(sb + k * 2048, BK * 128, 1024);
+            }
+            umma_bf16(d_tmem, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+      }
+    }
+  } else if (warp >= kEpiWarp0) {
+    // ======================================================================================= epilogue
+    const int ew = warp - kEpiWarp0;
+    const int lane_grp = warp & 3;            // TMEM lanes [32*lane_grp, +32) are accessible to this warp
+    const int col_half = ew >> 2;             // which half of the BN columns this warp handles
+    constexpr int CHUNKS = BN / 32 / 2;       // 32-column chunks per warp
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      int m_blk, n_blk, b = 0, row_in_batch0 = 0;
+      bool have_k = true;
+      if constexpr (!WGRAD) {
+        m_blk = tile / p.n_blocks;
+        n_blk = tile - m_blk * p.n_blocks;
+        b = m_blk / p.mb_per_batch;
+        row_in_batch0 = (m_blk - b * p.mb_per_batch) * BM;
+      } else {
+        const int mn = p.m_blocks * p.n_blocks;
+        const int rem = tile % mn;
+        m_blk = rem / p.n_blocks;
+        n_blk = rem - m_blk * p.n_blocks;
+        have_k = num_kb(tile) > 0;
+      }
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+
+      const int r_local = lane_grp * 32 + lane;
+      long long row;     // logical output row
+      bool row_ok;
+      if constexpr (!WGRAD) {
+        const int rib = row_in_batch0 + r_local;
+        row_ok = rib < p.L;
+        row = static_cast<long long>(b) * p.L + rib;
+      } else {
+        row = static_cast<long long>(m_blk) * BM + r_local;
+        row_ok = row < p.M;
+      }
+      long long orow = row;
+      if (p.out_rows != nullptr && row_ok) {
+        const int r = p.out_rows[row];
+        row_ok = r >= 0;
+        orow = r;
+      }
+
+#pragma unroll 1
+      for (int ch = 0; ch < CHUNKS; ++ch) {
+        const int col_local = (col_half * CHUNKS + ch) * 32;
+        const int n0 = n_blk * BN + col_local;
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16) + acc * BN + col_local, v);
+        tmem_ld_wait();
+        if (row_ok && n0 < p.N && have_k) {
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+        // columns valid in this chunk (N is a multiple of 8)
+        const int ncols = min(32, p.N - n0);
+        if (p.bias != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            if (j < ncols) {
+              const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
+              f[j] += bb.x; f[j + 1] += bb.y; f[j + 2] += bb.z; f[j + 3] += bb.w;
+            }
+          }
+        }
+        if (p.act == 1) {
+          // reference autocast semantics: linear/conv output is bf16, GELU evaluated on that bf16 value
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = bf16_round(f[j]);
+          if (p.out2 != nullptr) {
+            bf16* o2 = p.out2 + orow * p.ld_out2 + n0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              if (j < ncols) {
+                uint4 w;
+                w.x = pack_bf16x2(f[j], f[j + 1]); w.y = pack_bf16x2(f[j + 2], f[j + 3]);
+                w.z = pack_bf16x2(f[j + 4], f[j + 5]); w.w = pack_bf16x2(f[j + 6], f[j + 7]);
+                *reinterpret_cast<uint4*>(o2 + j) = w;
+              }
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
+        } else if (p.act == 2) {
+          const bf16* ax = p.aux + orow * p.ld_aux + n0;
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            if (j < ncols) {
+              const uint4 w = *reinterpret_cast<const uint4*>(ax + j);
+              const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&w);
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                const float2 hh = __bfloat1622float2(h2[t]);
+                f[j + 2 * t] *= gelu_erf_grad(hh.x);
+                f[j + 2 * t + 1] *= gelu_erf_grad(hh.y);
+              }
+            }
+          }
+        }
+        if (p.resid != nullptr) {
+          const long long rrow = p.resid_mod > 0 ? (orow % p.resid_mod) : orow;
+          if (p.resid_f32) {
+            const float* rp = reinterpret_cast<const float*>(p.resid) + rrow * p.ld_resid + n0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              if (j < ncols) {
+                const float4 rr = *reinterpret_cast<const float4*>(rp + j);
+                f[j] += rr.x; f[j + 1] += rr.y; f[j + 2] += rr.z; f[j + 3] += rr.w;
+              }
+            }
+          } else {
+            const bf16* rp = reinterpret_cast<const bf16*>(p.resid) + rrow * p.ld_resid + n0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              if (j < ncols) {
+                const uint4 w = *reinterpret_cast<const uint4*>(rp + j);
+                const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&w);
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                  const float2 hh = __bfloat1622float2(h2[t]);
+                  f[j + 2 * t] += hh.x;
+                  f[j + 2 * t + 1] += hh.y;
+                }
+              }
+            }
+          }
+        }
+        if (p.out_f32) {
+          float* op = reinterpret_cast<float*>(p.out) + orow * p.ld_out + n0;
+          if (p.accumulate) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              if (j < ncols) red_add_v4(op + j, f[j], f[j + 1], f[j + 2], f[j + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              if (j < ncols) *reinterpret_cast<float4*>(op + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+            }
+          }
+        } else {
+          bf16* op = reinterpret_cast<bf16*>(p.out) + orow * p.ld_out + n0;
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            if (j < ncols) {
+              uint4 w;
+              w.x = pack_bf16x2(f[j], f[j + 1]); w.y = pack_bf16x2(f[j + 2], f[j + 3]);
+              w.z = pack_bf16x2(f[j + 4], f[j + 5]); w.w = pack_bf16x2(f[j + 6], f[j + 7]);
+              *reinterpret_cast<uint4*>(op + j) = w;
+            }
+          }
+        }
+        }  // row_ok
+        __syncwarp();
+      }
+      // all TMEM reads of this accumulator are complete (tcgen05.wait::ld above) -> hand it back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// =================================================================================================== host side
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  if (fn == nullptr) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+      return nullptr;
+    fn = reinterpret_cast<PFN_encodeTiled>(sym);
+  }
+  return fn;
+}
+
+
+static int encode_map(CUtensorMap* tm, const wj_operand_t* op, const uint32_t box[4]) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)"); return WJ_ERR_RUNTIME; }
+  cuuint64_t dims[4];
+  cuuint64_t strides[3];
+  cuuint32_t bx[4], es[4] = {1, 1, 1, 1};
+  for (int i = 0; i < 4; ++i) { dims[i] = static_cast<cuuint64_t>(op->dim[i]); bx[i] = box[i]; }
+  for (int i = 0; i < 3; ++i) strides[i] = static_cast<cuuint64_t>(op->stride_bytes[i]);
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(op->ptr), dims, strides, bx, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed: %d (dims %llu %llu %llu %llu strides %llu %llu %llu box %u %u %u %u)",
+              (int)r, dims[0], dims[1], dims[2], dims[3], strides[0], strides[1], strides[2], bx[0], bx[1], bx[2],
+              bx[3]);
+    return WJ_ERR_RUNTIME;
+  }
+  return WJ_OK;
+}
+
+static int encode_map_2d(CUtensorMap* tm, const void* ptr, uint64_t inner, uint64_t outer, uint64_t stride_bytes,
+                         uint32_t box_inner, uint32_t box_outer) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)"); return WJ_ERR_RUNTIME; }
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {stride_bytes};
+  cuuint32_t bx[2] = {box_inner, box_outer}, es[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, bx, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(2d) failed: %d (dims %llu %llu stride %llu box %u %u)", (int)r, dims[0], dims[1],
+              strides[0], bx[0], bx[1]);
+    return WJ_ERR_RUNTIME;
+  }
+  return WJ_OK;
+}
+
+static int num_sms() { return sm_count(); }
+
+template <int BN, bool WGRAD>
+static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int grid, cudaStream_t st) {
+  static bool attr_set = false;
+  auto kern = gemm_kernel<BN, WGRAD>;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM_BYTES);
+    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return WJ_ERR_RUNTIME; }
+    attr_set = true;
+  }
+  kern<<<grid, kThreads, Cfg<BN>::SMEM_BYTES, st>>>(tmA, tmB, p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { set_error("gemm launch: %s", cudaGetErrorString(e)); return WJ_ERR_RUNTIME; }
+  return WJ_OK;
+}
+
+static void fill_seg(SegInfo& s, const wj_operand_t* op) {
+  s.width = op->seg_width;
+  for (int i = 0; i < 4; ++i) { s.q[i] = op->seg_q[i]; s.p[i] = op->seg_p[i]; }
+}
+
+static void fill_epilogue(GemmParams& p, const wj_epilogue_t* e) {
+  p.out = e->out; p.ld_out = e->ld_out; p.out_f32 = e->out_f32; p.accumulate = e->accumulate;
+  p.out2 = reinterpret_cast<bf16*>(e->out2); p.ld_out2 = e->ld_out2;
+  p.bias = e->bias; p.resid = e->resid; p.resid_f32 = e->resid_f32; p.ld_resid = e->ld_resid;
+  p.resid_mod = e->resid_mod; p.aux = reinterpret_cast<const bf16*>(e->aux); p.ld_aux = e->ld_aux;
+  p.act = e->act; p.out_rows = e->out_rows;
+}
+
+}  // namespace wj
+
+using namespace wj;
+
+// out[b*L + t, n] = epilogue( sum_vc A(vc; t, b) * W[n, vc] )        W is [N, K] row-major (K contiguous), bf16.
+extern "C" int wj_gemm_bf16(const wj_operand_t* A, const void* W, int64_t ldw, int L, int batch, int N, int K,
+                            const wj_epilogue_t* epi, int block_n, void* stream) {
+  if (L <= 0 || batch <= 0) return WJ_OK;
+  if (K % BK != 0 || N % 8 != 0) { set_error("wj_gemm_bf16: K must be a multiple of 64 and N of 8 (K=%d N=%d)", K, N); return WJ_ERR_ARG; }
+  if (A->seg_width > 0 && (A->seg_width % BK != 0 || K > 4 * A->seg_width)) { set_error("wj_gemm_bf16: bad segment width"); return WJ_ERR_ARG; }
+  if (block_n == 0) block_n = (N % 256 == 0 || N > 1024) ? 256 : 128;
+  if (block_n != 128 && block_n != 256) { set_error("wj_gemm_bf16: block_n must be 128 or 256"); return WJ_ERR_ARG; }
+  CUtensorMap tmA, tmB;
+  const uint32_t boxA[4] = {BK, 1, BM, 1};
+  int rc = encode_map(&tmA, A, boxA);
+  if (rc) return rc;
+  rc = encode_map_2d(&tmB, W, (uint64_t)K, (uint64_t)N, (uint64_t)ldw * 2, BK, (uint32_t)block_n);
+  if (rc) return rc;
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.L = L; p.batch = batch; p.N = N; p.K = K;
+  p.mb_per_batch = (L + BM - 1) / BM;
+  p.m_blocks = batch * p.mb_per_batch;
+  p.n_blocks = (N + block_n - 1) / block_n;
+  p.total_tiles = p.m_blocks * p.n_blocks;
+  fill_seg(p.seg, A);
+  fill_epilogue(p, epi);
+  const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (block_n == 256) return launch<256, false>(tmA, tmB, p, grid, st);
+  return launch<128, false>(tmA, tmB, p, grid, st);
+}
+
+// dW[m, vc] (+)= sum_{b, t} dY(b, t; m) * X(vc; t, b)      fp32 output, reduce-add when splits > 1 or accumulate.
+extern "C" int wj_gemm_wgrad_bf16(const wj_operand_t* dY, const wj_operand_t* X, int L, int batch, int M, int N,
+                                  float* out, int64_t ld_out, int accumulate, int splits, void* stream) {
+  if (L <= 0 || batch <= 0) return WJ_OK;
+  if (M % BM != 0 || N % 64 != 0) { set_error("wj_gemm_wgrad_bf16: M must be a multiple of 128 and N of 64 (M=%d N=%d)", M, N); return WJ_ERR_ARG; }
+  const int block_n = (N % 256 == 0) ? 256 : ((N % 128 == 0) ? 128 : 0);
+  if (block_n == 0) { set_error("wj_gemm_wgrad_bf16: N must be a multiple of 128"); return WJ_ERR_ARG; }
+  if (X->seg_width > 0 && X->seg_width % 64 != 0) { set_error("wj_gemm_wgrad_bf16: bad segment width"); return WJ_ERR_ARG; }
+  CUtensorMap tmA, tmB;
+  const uint32_t box[4] = {64, 1, BK, 1};
+  int rc = encode_map(&tmA, dY, box);
+  if (rc) return rc;
+  rc = encode_map(&tmB, X, box);
+  if (rc) return rc;
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.L = L; p.batch = batch; p.N = N; p.M = M;
+  p.m_blocks = M / BM;
+  p.n_blocks = N / block_n;
+  p.kb_per_batch = (L + BK - 1) / BK;
+  const int kb_total = batch * p.kb_per_batch;
+  if (splits <= 0) {
+    const int mn = p.m_blocks * p.n_blocks;
+    splits = (2 * num_sms() + mn - 1) / mn;
+    if (splits > kb_total) splits = kb_total;
+    if (splits < 1) splits = 1;
+  }
+  // make every split non-empty
+  const int per = (kb_total + splits - 1) / splits;
+  splits = (kb_total + per - 1) / per;
+  p.splits = splits;
+  p.total_tiles = p.m_blocks * p.n_blocks * splits;
+  fill_seg(p.seg, X);
+  p.out = out; p.ld_out = ld_out; p.out_f32 = 1;
+  p.accumulate = (accumulate || splits > 1) ? 1 : 0;
+  if (splits > 1 && !accumulate) {
+    // caller asked for overwrite semantics but we reduce with atomics: clear the destination first
+    cudaError_t e = cudaMemset2DAsync(out, ld_out * sizeof(float), 0, (size_t)N * sizeof(float), (size_t)M,
+                                      reinterpret_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) { set_error("memset2d: %s", cudaGetErrorString(e)); return WJ_ERR_RUNTIME; }
+  }
+  const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (block_n == 256) return launch<256, true>(tmA, tmB, p, grid, st);
+  return launch<128, true>(tmA, tmB, p, grid, st);
+}
