@@ -51,6 +51,7 @@ typedef struct wj_operand {
  *   v = acc + bias[n]
  *   act == 1 : h = bf16(v); out2[row, n] = h (if out2); v = GELU_erf(h)          (nn.GELU, types/wavjepa_configs.py:37)
  *   act == 2 : v = v * GELU_erf'(aux[row, n])                                    (backward of the above)
+ *   act == 3 : v = bf16(v)                         (autocast: the Linear output is bf16 before the fp32 residual add)
  *   v += resid[row % resid_mod or row, n]                                        (residual / positional table)
  *   out[row, n] = v  (bf16, or fp32 when out_f32; fp32 reduce-add when accumulate)
  * out_rows (optional, int32 per logical row): physical row used for out/out2/resid/aux, <0 skips the row.
@@ -81,11 +82,124 @@ typedef struct wj_epilogue {
 int wj_gemm_bf16(const wj_operand_t* A, const void* W, int64_t ldw, int L, int batch, int N, int K,
                  const wj_epilogue_t* epi, int block_n, void* stream);
 
+/* out[b*L + t, n] = epilogue( sum_{s,r} A(s*seg_width + r; t, b) * W[r, seg_col_off[s] + n] ): the reduction runs over the
+ * ROWS of the row-major bf16 matrix W [w_rows, w_cols] (read MN-major), i.e. dX = dY W for y = x W^T with no
+ * transposed weight copy; with segments it is the data gradient of the stride-2 Conv1d layers. */
+int wj_gemm_dgrad_bf16(const wj_operand_t* A, const void* W, int64_t ldw, int w_rows, int w_cols,
+                       const int32_t* seg_col_off, int L, int batch, int N, int K, const wj_epilogue_t* epi,
+                       int block_n, void* stream);
+
 /* dW[m, vc] (+)= sum_{b,t} dY[b, t, m] * X(vc; t, b)   fp32 out [M, N] (leading dim ld_out); both operands are read
  * MN-major straight from the row-major activations; the token reduction is split over `splits` CTAs (0 = auto) and
  * reduced with red.global.add.  Replaces autograd's weight gradients of the Linear / Conv1d layers above. */
 int wj_gemm_wgrad_bf16(const wj_operand_t* dY, const wj_operand_t* X, int L, int batch, int M, int N, float* out,
                        int64_t ld_out, int accumulate, int splits, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Mask generation, bit-exact with the reference maskers for the same seed (integer kernels, one warp per row).
+ * kind 0 = TimeInverseBlockMasker.forward (wavjepa/masking.py:66-128), kind 1 = SpeechMasker.forward (:167-207),
+ * both on top of compute_mask_indices (wavjepa/audio_masking.py:5-194) and numpy's SeedSequence/PCG64/choice chain.
+ * Seed contract: call c (0 = context, 1..G = targets) of attempt a of global row r = row0 + i draws from
+ * numpy.random.default_rng([base_seed, r, a*8 + c]).
+ * Outputs are torch.bool-compatible bytes: ctx_hidden [batch, T_out] (True = masked context), tgt [batch, G, T_out]
+ * (True = predict), vis_hidden [batch, G, T_out] (True = hidden from the predictor); T_out = n_times when
+ * channel_based ("(S C)" interleave, masking.py:120-126) else n_times / in_channels.  attempts (optional) receives the
+ * number of rejection-loop attempts per row; *err_flag is set to 1 if a row could not be generated. */
+int wj_masks_generate(int kind, int batch, int n_times, int in_channels, int channel_based, int n_targets,
+                      double ctx_prob, int ctx_len, double tgt_prob, int tgt_len, float cutoff, int min_context_len,
+                      uint32_t base_seed, uint32_t row0, uint8_t* ctx_hidden, uint8_t* tgt, uint8_t* vis_hidden,
+                      int* attempts, int* err_flag, void* stream);
+
+/* Packed token index lists for the variable-length kernels (replaces the boolean gathers / scatters of
+ * wavjepa/jepa.py:399 and :425-435).  For B instances, G target groups, T tokens:
+ *   n_c[B], cu_c[B+1]      visible context tokens per instance;  ctx_rows[Nc] = b*T + t
+ *   n_v[B*G], cu_v[B*G+1]  predictor tokens per (b, g) (visible = !vis_hidden); vis_src[Nv] = packed context index
+ *                          or -1 (mask token), vis_pos[Nv] = t
+ *   n_t[B*G], cu_t[B*G+1]  target tokens per (b, g); tgt_vrow[Nt] = row in the packed predictor array,
+ *                          tgt_trow[Nt] = b*T + t (row of the teacher targets)
+ *   totals[8] = {Nc, Nv, Nt, #targets hidden from the predictor (unsupported, must be 0), max n_c, max n_v, 0, 0} */
+int wj_mask_indices(const uint8_t* ctx_hidden, const uint8_t* tgt, const uint8_t* vis_hidden, int B, int G, int T,
+                    int* n_c, int* n_v, int* n_t, int* cu_c, int* cu_v, int* cu_t, int* totals, int* ctx_rows,
+                    int* vis_src, int* vis_pos, int* tgt_vrow, int* tgt_trow, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Waveform encoder block 0: Conv1d(Cin->C, k=10, s=5, no bias) + GroupNorm(C, C, eps) + exact GELU, fused, output
+ * channels-last bf16 [B, L_out, C].  x is [B, Cin, L] bf16, w the fp32 master weight [C, Cin, 10] (rounded to bf16 on
+ * load, as autocast does).  stats [B, C, 2] fp64 (sum, sum of squares of the bf16 conv output) is written by the
+ * forward and consumed by the backward.  Reference: wavjepa/extractors/audio_feature_extractor.py:70,94,95. */
+int wj_conv0_gn_gelu_fwd(const void* x_bf16, const float* w, const float* gamma, const float* beta, int B, int Cin,
+                         int L, int C, int k, int stride, float eps, double* stats, void* out_bf16, void* stream);
+/* Backward of the block above given dY (bf16 [B, L_out, C]); accumulates into dw [C, Cin, 10], dgamma, dbeta (fp32).
+ * red_scratch: [B, C, 2] fp64 workspace. */
+int wj_conv0_gn_gelu_bwd(const void* x_bf16, const float* w, const float* gamma, const float* beta, int B, int Cin,
+                         int L, int C, int k, int stride, float eps, const double* stats, const void* dy_bf16,
+                         double* red_scratch, float* dw, float* dgamma, float* dbeta, void* stream);
+
+/* LayerNorm over the last dim (D in {128,256,384,512,768,1024}), biased variance, one warp per row.
+ * Writes any of: out_f32, out_bf16, stats [M,2] = (mean, rstd), rowsum [M,2] = (sum, sum of squares of the OUTPUT row).
+ * Reference: nn.LayerNorm in nn.TransformerEncoderLayer (eps 1e-6, wavjepa/types/wavjepa_configs.py:38) and
+ * feature_norms / encoder.norm / decoder.norm (eps 1e-5, wavjepa/jepa.py:109,127,130). */
+int wj_layernorm_fwd(const void* x, int x_is_bf16, const float* gamma, const float* beta, float eps, int M, int D,
+                     float* out_f32, void* out_bf16, float* stats, float* rowsum, void* stream);
+/* dx (fp32 and/or bf16) from dy (fp32), the saved input x and stats; dgamma/dbeta (+=), colsum (+= sum_rows dx). */
+int wj_layernorm_bwd(const float* dy, const void* x, int x_is_bf16, const float* stats, const float* gamma, int M,
+                     int D, float* dx_f32, void* dx_bf16, float* dgamma, float* dbeta, float* colsum, void* stream);
+
+/* out[i] = (audio[clip, :, start_i : start_i+crop_len] - mean) / (std_unbiased + 1e-5), statistics over (C, crop_len)
+ * jointly; i = clip*crops_per_clip + j; samples past clip_len read as zero.  JEPA.on_after_batch_transfer
+ * (wavjepa/jepa.py:291-311) and hear_api/runtime.py:12-16 (normalize). */
+int wj_crop_norm(const float* audio, const int* starts, int n_clips, int channels, int64_t clip_len,
+                 int crops_per_clip, int crop_len, void* out_bf16, float* out_f32, void* stream);
+
+/* targets (=|+=) scale * instance_norm(x) with statistics over all T*D values of each instance (biased var, eps);
+ * rowsum [B*T, 2] comes from wj_layernorm_fwd.  JEPA._make_targets (wavjepa/jepa.py:230-253). */
+int wj_target_accum(const float* x, const float* rowsum, int B, int T, int D, float eps, float scale, int first,
+                    float* inst_stats, float* targets, void* stream);
+
+/* Variable-length multi-head attention over packed tokens: qkv bf16 [tokens, 3*D] (q|k|v), sequences given by
+ * cu_seqlens [n_seqs+1], softmax(q k^T / sqrt(D/H)) v, head dim 32 or 64.  out bf16 [tokens, D];
+ * lse2 fp32 [tokens, H] = log2-sum-exp2 of the scaled logits (saved for the backward; may be NULL).
+ * Reference: F.scaled_dot_product_attention with key_padding_mask inside nn.MultiheadAttention. */
+int wj_attn_varlen_fwd(const void* qkv_bf16, const int* cu_seqlens, int n_seqs, int max_len, int D, int H,
+                       void* out_bf16, float* lse2, void* stream);
+int wj_attn_varlen_bwd(const void* qkv_bf16, const void* out_bf16, const void* dout_bf16, const float* lse2,
+                       const int* cu_seqlens, int n_seqs, int max_len, int D, int H, void* dqkv_bf16, void* stream);
+
+/* Row gather: out[i, :] = src[idx[i], :] (idx NULL = identity, i.e. a cast); fp32 and/or bf16 outputs.
+ * contextual_features[~ctx_masks] (wavjepa/jepa.py:399). */
+int wj_gather_rows(const void* src, int src_is_bf16, const int* idx, int N, int D, float* out_f32, void* out_bf16,
+                   void* stream);
+/* out_bf16[idx[i], :] = src[i, :] * GELU'(h[idx[i], :]) (h may be NULL); rows not listed are left untouched. */
+int wj_scatter_dgelu(const float* src, const int* idx, const void* h_bf16, int N, int D, void* out_bf16, void* stream);
+
+/* Predictor input: x0[r] = (vis_src[r] >= 0 ? ctx[vis_src[r]] : bf16(mask_token)) + pos[vis_pos[r]]
+ * (JEPA.decoder_forward, wavjepa/jepa.py:425-435) and its backward (d_ctx fp32 [Nc, D] +=, d_mask_token [D] +=). */
+int wj_predictor_assemble(const void* ctx_bf16, const float* mask_token, const float* pos, const int* vis_src,
+                          const int* vis_pos, int N, int D, float* out_f32, void* out_bf16, void* stream);
+int wj_predictor_assemble_bwd(const float* dx0, const int* vis_src, int N, int D, float* d_ctx, float* d_mask_token,
+                              void* stream);
+
+/* *loss += sum_i mean_d (pred[i,d] - targets[tgt_rows[i], d])^2 / (Nt + 1e-8); dpred (optional, bf16) = d loss / d pred.
+ * JEPA.masked_loss (wavjepa/jepa.py:335-362) restricted to the target rows (all other rows have zero weight). */
+int wj_masked_mse(const void* pred_bf16, const float* targets, const int* tgt_rows, int Nt, int D, float* loss,
+                  void* dpred_bf16, void* stream);
+
+/* teacher = teacher * decay + (1 - decay) * student, fp32, rounding exactly like
+ * teacher.mul_(r).add_((1 - r) * student) (JEPA._step_teacher, wavjepa/jepa.py:193-198). */
+int wj_ema_update(float* teacher, const float* student, int64_t n, double decay, void* stream);
+
+/* *out (fp64) += sum (scale * x[i])^2 -- global gradient norm for clip_grad_norm_ (train.py:177-178). */
+int wj_sumsq(const float* x, int64_t n, float scale, double* out, void* stream);
+/* One fused multi-tensor AdamW step over a flat parameter buffer (torch.optim.AdamW semantics, wavjepa/jepa.py:215-222)
+ * with the gradient scale (1/world_size) and clip coefficient min(1, max_norm / (sqrt(*grad_sumsq) + 1e-6)) folded in;
+ * optionally refreshes the bf16 working copy of the weights. step is 1-based. */
+int wj_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+                  float eps, float weight_decay, int step, float grad_scale, float max_norm, const double* grad_sumsq,
+                  void* p_bf16, void* stream);
+int wj_cast_bf16(const float* x, void* y_bf16, int64_t n, void* stream);
+/* out[n] += sum_m x[m, n] (bias gradients). */
+int wj_colsum(const void* x, int x_is_bf16, int64_t M, int N, int64_t ld, float* out, void* stream);
+int wj_scale_bf16(void* x_bf16, const float* scale_dev, int64_t n, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,365 @@
+// HBM-bound elementwise / gather / reduction kernels of the WavJEPA step.
+//
+//   gather_rows / scatter_dgelu : contextual_features[~ctx_masks] (wavjepa/jepa.py:399) and its backward
+//   predictor_assemble fwd/bwd  : JEPA.decoder_forward input assembly (wavjepa/jepa.py:425-435)
+//   masked_mse                  : JEPA.masked_loss (wavjepa/jepa.py:335-362), forward and d(loss)/d(pred) in one pass
+//   ema_update                  : JEPA._step_teacher (wavjepa/jepa.py:193-198)
+//   adamw_step / sumsq          : torch.optim.AdamW + clip_grad_norm_(5.0) (wavjepa/jepa.py:215-222, train.py:177-178)
+//   cast / colsum               : bf16 working copies of the fp32 master weights; bias gradients
+#include "common.cuh"
+
+namespace wj {
+
+__device__ __forceinline__ float4 load4(const void* p, bool is_bf16, size_t idx) {
+  if (is_bf16) {
+    const uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const bf16*>(p) + idx);
+    const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+    const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+  }
+  return *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p) + idx);
+}
+__device__ __forceinline__ void store4(float* of, bf16* ob, size_t idx, float4 v) {
+  if (of != nullptr) *reinterpret_cast<float4*>(of + idx) = v;
+  if (ob != nullptr) {
+    uint2 u;
+    u.x = pack_bf16x2(v.x, v.y);
+    u.y = pack_bf16x2(v.z, v.w);
+    *reinterpret_cast<uint2*>(ob + idx) = u;
+  }
+}
+
+__global__ void __launch_bounds__(256) gather_rows_kernel(const void* __restrict__ src, int src_bf16,
+                                                          const int* __restrict__ idx, long long n4, int D4,
+                                                          float* __restrict__ out_f32, bf16* __restrict__ out_bf16) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = i / D4;
+    const int c = static_cast<int>(i - r * D4);
+    const long long sr = idx ? idx[r] : r;
+    const float4 v = load4(src, src_bf16, static_cast<size_t>(sr) * D4 * 4 + c * 4);
+    store4(out_f32, out_bf16, static_cast<size_t>(i) * 4, v);
+  }
+}
+
+// out_bf16[idx[r], :] = src_f32[r, :] * gelu'(h[idx[r], :])   (rows not listed stay as the caller zeroed them)
+__global__ void __launch_bounds__(256) scatter_dgelu_kernel(const float* __restrict__ src, const int* __restrict__ idx,
+                                                            const bf16* __restrict__ h, long long n4, int D4,
+                                                            bf16* __restrict__ out) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = i / D4;
+    const int c = static_cast<int>(i - r * D4);
+    const size_t o = static_cast<size_t>(idx[r]) * D4 * 4 + c * 4;
+    float4 v = reinterpret_cast<const float4*>(src)[i];
+    if (h != nullptr) {
+      const float4 hv = load4(h, true, o);
+      v.x *= gelu_erf_grad(hv.x); v.y *= gelu_erf_grad(hv.y); v.z *= gelu_erf_grad(hv.z); v.w *= gelu_erf_grad(hv.w);
+    }
+    store4(nullptr, out, o, v);
+  }
+}
+
+// x0[r, :] = (src[r] >= 0 ? ctx[src[r], :] : bf16(mask_token)) + pos[pos_idx[r], :]
+__global__ void __launch_bounds__(256) predictor_assemble_kernel(const bf16* __restrict__ ctx,
+                                                                 const float* __restrict__ mask_token,
+                                                                 const float* __restrict__ pos,
+                                                                 const int* __restrict__ vis_src,
+                                                                 const int* __restrict__ vis_pos, long long n4, int D4,
+                                                                 float* __restrict__ out_f32,
+                                                                 bf16* __restrict__ out_bf16) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = i / D4;
+    const int c = static_cast<int>(i - r * D4) * 4;
+    const int s = vis_src[r];
+    float4 v;
+    if (s >= 0) {
+      v = load4(ctx, true, static_cast<size_t>(s) * D4 * 4 + c);
+    } else {
+      const float4 m = *reinterpret_cast<const float4*>(mask_token + c);
+      v = make_float4(bf16_round(m.x), bf16_round(m.y), bf16_round(m.z), bf16_round(m.w));  // .type_as(bf16)
+    }
+    const float4 p = *reinterpret_cast<const float4*>(pos + static_cast<size_t>(vis_pos[r]) * D4 * 4 + c);
+    v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w;
+    store4(out_f32, out_bf16, static_cast<size_t>(i) * 4, v);
+  }
+}
+
+// d_ctx[src[r], :] += dx0[r, :] (src >= 0);  d_mask_token += sum over rows with src < 0
+__global__ void __launch_bounds__(256) predictor_assemble_bwd_kernel(const float* __restrict__ dx0,
+                                                                     const int* __restrict__ vis_src, int N, int D,
+                                                                     int rows_per_block, float* __restrict__ d_ctx,
+                                                                     float* __restrict__ d_mask) {
+  // thread t owns columns t, t+256, ... ; the block walks rows_per_block rows
+  const int r0 = blockIdx.x * rows_per_block;
+  const int r1 = min(N, r0 + rows_per_block);
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    float acc = 0.f;
+    for (int r = r0; r < r1; ++r) {
+      const int s = vis_src[r];
+      const float v = dx0[static_cast<size_t>(r) * D + c];
+      if (s >= 0) atomicAdd(d_ctx + static_cast<size_t>(s) * D + c, v);
+      else acc += v;
+    }
+    atomicAdd(d_mask + c, acc);
+  }
+}
+
+// loss += sum_i mean_d (pred[i,d] - tgt[trow[i],d])^2 / (Nt + 1e-8);  dpred = 2 (pred - tgt) / (D (Nt + 1e-8))
+__global__ void __launch_bounds__(256) masked_mse_kernel(const bf16* __restrict__ pred, const float* __restrict__ tgt,
+                                                         const int* __restrict__ trow, int Nt, int D,
+                                                         float* __restrict__ loss, bf16* __restrict__ dpred) {
+  __shared__ float s_part[8];
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float denom = static_cast<float>(Nt) + 1e-8f;
+  const float inv = 1.0f / (static_cast<float>(D) * denom);
+  float acc = 0.f;
+  for (int i = blockIdx.x * 8 + wib; i < Nt; i += gridDim.x * 8) {
+    const size_t pb = static_cast<size_t>(i) * D, tb = static_cast<size_t>(trow[i]) * D;
+    for (int c = lane * 4; c < D; c += 128) {
+      const float4 p = load4(pred, true, pb + c);
+      const float4 t = *reinterpret_cast<const float4*>(tgt + tb + c);
+      const float4 d = make_float4(p.x - t.x, p.y - t.y, p.z - t.z, p.w - t.w);
+      acc += d.x * d.x + d.y * d.y + d.z * d.z + d.w * d.w;
+      if (dpred != nullptr) {
+        const float k = 2.0f * inv;
+        store4(nullptr, dpred, pb + c, make_float4(d.x * k, d.y * k, d.z * k, d.w * k));
+      }
+    }
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) s_part[wib] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += s_part[w];
+    atomicAdd(loss, t * inv);
+  }
+}
+
+// teacher = fl(fl(teacher * r) + fl(student * q)) -- exactly teacher.mul_(r).add_((1 - r) * student) in fp32
+__global__ void __launch_bounds__(256) ema_kernel(float* __restrict__ teacher, const float* __restrict__ student, float r,
+                                                  float q, long long n4, long long n) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float4 t = reinterpret_cast<float4*>(teacher)[i];
+    const float4 s = reinterpret_cast<const float4*>(student)[i];
+    t.x = __fadd_rn(__fmul_rn(t.x, r), __fmul_rn(s.x, q));
+    t.y = __fadd_rn(__fmul_rn(t.y, r), __fmul_rn(s.y, q));
+    t.z = __fadd_rn(__fmul_rn(t.z, r), __fmul_rn(s.z, q));
+    t.w = __fadd_rn(__fmul_rn(t.w, r), __fmul_rn(s.w, q));
+    reinterpret_cast<float4*>(teacher)[i] = t;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    for (long long i = n4 * 4; i < n; ++i) teacher[i] = __fadd_rn(__fmul_rn(teacher[i], r), __fmul_rn(student[i], q));
+}
+
+__global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ x, long long n, float scale,
+                                                    double* __restrict__ out) {
+  __shared__ double s_part[8];
+  double acc = 0.0;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float v = x[i] * scale;
+    acc += static_cast<double>(v) * v;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += s_part[w];
+    atomicAdd(out, t);
+  }
+}
+
+// torch.optim.AdamW (non-amsgrad, decoupled decay) with the clip_grad_norm_ coefficient folded in:
+//   g *= grad_scale * min(1, max_norm / (sqrt(sumsq) + 1e-6));  p *= 1 - lr*wd;  m,v updates;  p -= lr/bc1 * m / (sqrt(v)/sqrt(bc2) + eps)
+__global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                                    float* __restrict__ m, float* __restrict__ v, long long n, float lr,
+                                                    float beta1, float beta2, float eps, float wd, float bc1,
+                                                    float bc2_sqrt, float grad_scale, float max_norm,
+                                                    const double* __restrict__ sumsq, bf16* __restrict__ p_bf16) {
+  float coef = grad_scale;
+  if (sumsq != nullptr && max_norm > 0.f) {
+    const float total = static_cast<float>(sqrt(*sumsq));
+    const float c = max_norm / (total + 1e-6f);
+    coef *= fminf(c, 1.0f);
+  }
+  const float step = lr / bc1;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float gr = g[i] * coef;
+    float pv = p[i] * (1.0f - lr * wd);
+    const float mv = beta1 * m[i] + (1.0f - beta1) * gr;
+    const float vv = beta2 * v[i] + (1.0f - beta2) * gr * gr;
+    m[i] = mv;
+    v[i] = vv;
+    const float denom = sqrtf(vv) / bc2_sqrt + eps;
+    pv -= step * (mv / denom);
+    p[i] = pv;
+    if (p_bf16 != nullptr) p_bf16[i] = __float2bfloat16_rn(pv);
+  }
+}
+
+__global__ void __launch_bounds__(256) cast_kernel(const float* __restrict__ x, bf16* __restrict__ y, long long n) {
+  const long long n4 = n / 4;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(x)[i];
+    store4(nullptr, y, static_cast<size_t>(i) * 4, v);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    for (long long i = n4 * 4; i < n; ++i) y[i] = __float2bfloat16_rn(x[i]);
+}
+
+// out[n] += sum_m x[m, n]  (x bf16 or fp32, row-major with leading dimension ld)
+__global__ void __launch_bounds__(256) colsum_kernel(const void* __restrict__ x, int is_bf16, long long M, int N,
+                                                     long long ld, int rows_per_block, float* __restrict__ out) {
+  const long long r0 = static_cast<long long>(blockIdx.y) * rows_per_block;
+  const long long r1 = min(M, r0 + rows_per_block);
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 2;
+  if (c >= N) return;
+  float a0 = 0.f, a1 = 0.f;
+  if (is_bf16) {
+    const bf16* p = reinterpret_cast<const bf16*>(x);
+    for (long long r = r0; r < r1; ++r) {
+      const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p + r * ld + c));
+      a0 += v.x; a1 += v.y;
+    }
+  } else {
+    const float* p = reinterpret_cast<const float*>(x);
+    for (long long r = r0; r < r1; ++r) {
+      const float2 v = *reinterpret_cast<const float2*>(p + r * ld + c);
+      a0 += v.x; a1 += v.y;
+    }
+  }
+  atomicAdd(out + c, a0);
+  atomicAdd(out + c + 1, a1);
+}
+
+__global__ void __launch_bounds__(256) scale_kernel(bf16* __restrict__ x, const float* __restrict__ s, long long n) {
+  const float k = *s;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    x[i] = __float2bfloat16_rn(__bfloat162float(x[i]) * k);
+}
+
+static int grid_for(long long work_items, int threads = 256, int waves = 16) {
+  long long blocks = (work_items + threads - 1) / threads;
+  const long long cap = static_cast<long long>(sm_count()) * waves;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return static_cast<int>(blocks);
+}
+
+}  // namespace wj
+
+using namespace wj;
+
+extern "C" int wj_gather_rows(const void* src, int src_is_bf16, const int* idx, int N, int D, float* out_f32,
+                              void* out_bf16, void* stream) {
+  if (N <= 0) return WJ_OK;
+  if (D % 4) { set_error("wj_gather_rows: D %% 4 != 0"); return WJ_ERR_ARG; }
+  const long long n4 = static_cast<long long>(N) * (D / 4);
+  gather_rows_kernel<<<grid_for(n4), 256, 0, WJ_STREAM(stream)>>>(src, src_is_bf16, idx, n4, D / 4, out_f32,
+                                                                 reinterpret_cast<bf16*>(out_bf16));
+  return check_launch("gather_rows");
+}
+
+extern "C" int wj_scatter_dgelu(const float* src, const int* idx, const void* h_bf16, int N, int D, void* out_bf16,
+                                void* stream) {
+  if (N <= 0) return WJ_OK;
+  if (D % 4) { set_error("wj_scatter_dgelu: D %% 4 != 0"); return WJ_ERR_ARG; }
+  const long long n4 = static_cast<long long>(N) * (D / 4);
+  scatter_dgelu_kernel<<<grid_for(n4), 256, 0, WJ_STREAM(stream)>>>(src, idx, reinterpret_cast<const bf16*>(h_bf16), n4,
+                                                                   D / 4, reinterpret_cast<bf16*>(out_bf16));
+  return check_launch("scatter_dgelu");
+}
+
+extern "C" int wj_predictor_assemble(const void* ctx_bf16, const float* mask_token, const float* pos,
+                                     const int* vis_src, const int* vis_pos, int N, int D, float* out_f32,
+                                     void* out_bf16, void* stream) {
+  if (N <= 0) return WJ_OK;
+  if (D % 4) { set_error("wj_predictor_assemble: D %% 4 != 0"); return WJ_ERR_ARG; }
+  const long long n4 = static_cast<long long>(N) * (D / 4);
+  predictor_assemble_kernel<<<grid_for(n4), 256, 0, WJ_STREAM(stream)>>>(
+      reinterpret_cast<const bf16*>(ctx_bf16), mask_token, pos, vis_src, vis_pos, n4, D / 4, out_f32,
+      reinterpret_cast<bf16*>(out_bf16));
+  return check_launch("predictor_assemble");
+}
+
+extern "C" int wj_predictor_assemble_bwd(const float* dx0, const int* vis_src, int N, int D, float* d_ctx,
+                                         float* d_mask_token, void* stream) {
+  if (N <= 0) return WJ_OK;
+  int rows_per_block = (N + sm_count() * 8 - 1) / (sm_count() * 8);
+  if (rows_per_block < 1) rows_per_block = 1;
+  const int blocks = (N + rows_per_block - 1) / rows_per_block;
+  predictor_assemble_bwd_kernel<<<blocks, 256, 0, WJ_STREAM(stream)>>>(dx0, vis_src, N, D, rows_per_block, d_ctx,
+                                                                      d_mask_token);
+  return check_launch("predictor_assemble_bwd");
+}
+
+extern "C" int wj_masked_mse(const void* pred_bf16, const float* targets, const int* tgt_rows, int Nt, int D,
+                             float* loss, void* dpred_bf16, void* stream) {
+  if (Nt <= 0) return WJ_OK;
+  if (D % 4) { set_error("wj_masked_mse: D %% 4 != 0"); return WJ_ERR_ARG; }
+  int blocks = (Nt + 7) / 8;
+  const int cap = sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  masked_mse_kernel<<<blocks, 256, 0, WJ_STREAM(stream)>>>(reinterpret_cast<const bf16*>(pred_bf16), targets, tgt_rows,
+                                                          Nt, D, loss, reinterpret_cast<bf16*>(dpred_bf16));
+  return check_launch("masked_mse");
+}
+
+extern "C" int wj_ema_update(float* teacher, const float* student, int64_t n, double decay, void* stream) {
+  if (n <= 0) return WJ_OK;
+  const float r = static_cast<float>(decay), q = static_cast<float>(1.0 - decay);
+  ema_kernel<<<grid_for(n / 4 + 1), 256, 0, WJ_STREAM(stream)>>>(teacher, student, r, q, n / 4, n);
+  return check_launch("ema_update");
+}
+
+extern "C" int wj_sumsq(const float* x, int64_t n, float scale, double* out, void* stream) {
+  if (n <= 0) return WJ_OK;
+  sumsq_kernel<<<grid_for(n, 256, 8), 256, 0, WJ_STREAM(stream)>>>(x, n, scale, out);
+  return check_launch("sumsq");
+}
+
+extern "C" int wj_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
+                             float beta2, float eps, float weight_decay, int step, float grad_scale, float max_norm,
+                             const double* grad_sumsq, void* p_bf16, void* stream) {
+  if (n <= 0) return WJ_OK;
+  const double bc1 = 1.0 - pow(static_cast<double>(beta1), step);
+  const double bc2 = 1.0 - pow(static_cast<double>(beta2), step);
+  adamw_kernel<<<grid_for(n), 256, 0, WJ_STREAM(stream)>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay,
+                                                          static_cast<float>(bc1), static_cast<float>(sqrt(bc2)),
+                                                          grad_scale, max_norm, grad_sumsq,
+                                                          reinterpret_cast<bf16*>(p_bf16));
+  return check_launch("adamw_step");
+}
+
+extern "C" int wj_cast_bf16(const float* x, void* y_bf16, int64_t n, void* stream) {
+  if (n <= 0) return WJ_OK;
+  cast_kernel<<<grid_for(n / 4 + 1), 256, 0, WJ_STREAM(stream)>>>(x, reinterpret_cast<bf16*>(y_bf16), n);
+  return check_launch("cast_bf16");
+}
+
+extern "C" int wj_colsum(const void* x, int x_is_bf16, int64_t M, int N, int64_t ld, float* out, void* stream) {
+  if (M <= 0) return WJ_OK;
+  if (N % 2) { set_error("wj_colsum: N must be even"); return WJ_ERR_ARG; }
+  const int bx = (N / 2 + 255) / 256;
+  int by = (2 * sm_count() + bx - 1) / bx;
+  if (by > M) by = static_cast<int>(M);
+  const int rows_per_block = static_cast<int>((M + by - 1) / by);
+  by = static_cast<int>((M + rows_per_block - 1) / rows_per_block);
+  colsum_kernel<<<dim3(bx, by), 256, 0, WJ_STREAM(stream)>>>(x, x_is_bf16, M, N, ld, rows_per_block, out);
+  return check_launch("colsum");
+}
+
+extern "C" int wj_scale_bf16(void* x_bf16, const float* scale_dev, int64_t n, void* stream) {
+  if (n <= 0) return WJ_OK;
+  scale_kernel<<<grid_for(n), 256, 0, WJ_STREAM(stream)>>>(reinterpret_cast<bf16*>(x_bf16), scale_dev, n);
+  return check_launch("scale_bf16");
+}

@@ -44,7 +44,8 @@ struct GemmParams {
   int total_tiles;
   int splits;        // wgrad: split of the reduction
   int kb_per_batch;  // wgrad: ceil(L / 64)
-  SegInfo seg;       // normal: segments of A's K;  wgrad: segments of B's N
+  SegInfo seg;       // normal/dgrad: segments of A's K;  wgrad: segments of B's N
+  int segB_col[4];   // dgrad: column offset into W for each reduction segment
   // epilogue
   void* out;
   long long ld_out;
@@ -59,7 +60,7 @@ struct GemmParams {
   int resid_mod;     // residual row = row % resid_mod when > 0 (positional table broadcast)
   const bf16* aux;   // pre-activation for act == 2
   long long ld_aux;
-  int act;           // 0 none; 1: h = bf16(acc + bias), out2 = h, v = gelu(h); 2: v = acc * gelu'(aux)
+  int act;           // 0 none; 1: h = bf16(acc + bias), out2 = h, v = gelu(h); 2: v = acc * gelu'(aux); 3: v = bf16(v)
   const int* out_rows;  // optional row indirection for the output / residual / aux rows (scatter), -1 = skip
 };
 
@@ -91,10 +92,13 @@ __device__ __forceinline__ void seg_coords(const SegInfo& s, int vc, int& c0, in
   }
 }
 
-template <int BN, bool WGRAD>
+// MODE 0: A K-major, B K-major (fwd)   MODE 1: A, B MN-major (wgrad)   MODE 2: A K-major, B MN-major (dgrad)
+template <int BN, int MODE>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
   using C = Cfg<BN>;
+  constexpr bool WGRAD = (MODE == 1);
+  constexpr bool B_MN = (MODE != 0);
   constexpr int STAGES = C::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -165,7 +169,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             seg_coords(p.seg, kb * BK, c0, q, po);
             mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
             tma_load_4d(sa, &tmA, &full_bar[stage], c0, q, row0 + po, b);
-            tma_load_2d(sb, &tmB, &full_bar[stage], kb * BK, n_blk * BN);
+            if constexpr (!B_MN) {
+              tma_load_2d(sb, &tmB, &full_bar[stage], kb * BK, n_blk * BN);
+            } else {
+              // dgrad: W is [reduction rows, output cols] row-major -> BN/64 MN-major atoms of 64 reduction rows
+              const int si = p.seg.width > 0 ? (kb * BK) / p.seg.width : 0;
+              const int r0 = kb * BK - si * (p.seg.width > 0 ? p.seg.width : 0);
+#pragma unroll
+              for (int a = 0; a < BN / 64; ++a)
+                tma_load_2d(sb + a * (BK * 128), &tmB, &full_bar[stage], p.segB_col[si] + n_blk * BN + a * 64, r0);
+            }
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         } else {
@@ -204,7 +217,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   } else if (warp == 1) {
     // ======================================================================================= MMA issuer
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, WGRAD, WGRAD);
+      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, WGRAD, B_MN);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -223,16 +236,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             uint64_t da, db;
-            if constexpr (!WGRAD) {
-              // K-major, 128B swizzle: rows of 128 B, 8-row groups 1024 B apart; advance 16 elements = 32 B
-              da = umma_smem_desc_sw128(sa + k * 32, 0, 1024);
-              db = umma_smem_desc_sw128(sb + k * 32, 0, 1024);
-            } else {
-              // MN-major, 128B swizzle: atom = 64 (MN) x 8 (K) = 1024 B; K groups 1024 B apart (SBO),
-              // MN atoms BK*128 B apart (LBO); advance 16 reduction rows = 2048 B
-              da = umma_smem_desc_sw128(sa + k * 2048, BK * 128, 1024);
-              db = umma_smem_desc_sw128(sb + k * 2048, BK * 128, 1024);
-            }
+            // K-major, 128B swizzle: rows of 128 B, 8-row groups 1024 B apart; advance 16 elements = 32 B
+            // MN-major, 128B swizzle: atom = 64 (MN) x 8 (K) = 1024 B; K groups 1024 B apart (SBO),
+            // MN atoms BK*128 B apart (LBO); advance 16 reduction rows = 2048 B
+            if constexpr (!WGRAD) da = umma_smem_desc_sw128(sa + k * 32, 0, 1024);
+            else da = umma_smem_desc_sw128(sa + k * 2048, BK * 128, 1024);
+            if constexpr (!B_MN) db = umma_smem_desc_sw128(sb + k * 32, 0, 1024);
+            else db = umma_smem_desc_sw128(sb + k * 2048, BK * 128, 1024);
             umma_bf16(d_tmem, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
@@ -308,7 +318,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             }
           }
         }
-        if (p.act == 1) {
+        if (p.act == 3) {
+          // linear output is bf16 under autocast before it meets the fp32 residual / positional table
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = bf16_round(f[j]);
+        } else if (p.act == 1) {
           // reference autocast semantics: linear/conv output is bf16, GELU evaluated on that bf16 value
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = bf16_round(f[j]);
@@ -471,10 +485,10 @@ static int encode_map_2d(CUtensorMap* tm, const void* ptr, uint64_t inner, uint6
 
 static int num_sms() { return sm_count(); }
 
-template <int BN, bool WGRAD>
+template <int BN, int MODE>
 static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int grid, cudaStream_t st) {
   static bool attr_set = false;
-  auto kern = gemm_kernel<BN, WGRAD>;
+  auto kern = gemm_kernel<BN, MODE>;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM_BYTES);
     if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return WJ_ERR_RUNTIME; }
@@ -528,8 +542,8 @@ extern "C" int wj_gemm_bf16(const wj_operand_t* A, const void* W, int64_t ldw, i
   fill_epilogue(p, epi);
   const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (block_n == 256) return launch<256, false>(tmA, tmB, p, grid, st);
-  return launch<128, false>(tmA, tmB, p, grid, st);
+  if (block_n == 256) return launch<256, 0>(tmA, tmB, p, grid, st);
+  return launch<128, 0>(tmA, tmB, p, grid, st);
 }
 
 // dW[m, vc] (+)= sum_{b, t} dY(b, t; m) * X(vc; t, b)      fp32 output, reduce-add when splits > 1 or accumulate.
@@ -575,6 +589,38 @@ extern "C" int wj_gemm_wgrad_bf16(const wj_operand_t* dY, const wj_operand_t* X,
   }
   const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (block_n == 256) return launch<256, true>(tmA, tmB, p, grid, st);
-  return launch<128, true>(tmA, tmB, p, grid, st);
+  if (block_n == 256) return launch<256, 1>(tmA, tmB, p, grid, st);
+  return launch<128, 1>(tmA, tmB, p, grid, st);
+}
+
+// out[b*L + t, n] = epilogue( sum_{s, r} A(s*width + r; t, b) * W[r, col_off[s] + n] ),  W bf16 row-major [R, ldw]:
+// the reduction runs over ROWS of W (B operand read MN-major), i.e. dX = dY * W for y = x W^T without a transposed copy.
+extern "C" int wj_gemm_dgrad_bf16(const wj_operand_t* A, const void* W, int64_t ldw, int w_rows, int w_cols,
+                                  const int32_t* seg_col_off, int L, int batch, int N, int K, const wj_epilogue_t* epi,
+                                  int block_n, void* stream) {
+  if (L <= 0 || batch <= 0) return WJ_OK;
+  if (K % BK != 0 || N % 64 != 0) { set_error("wj_gemm_dgrad_bf16: K must be a multiple of 64 and N of 64 (K=%d N=%d)", K, N); return WJ_ERR_ARG; }
+  if (A->seg_width > 0 && (A->seg_width % BK != 0 || K > 4 * A->seg_width)) { set_error("wj_gemm_dgrad_bf16: bad segment width"); return WJ_ERR_ARG; }
+  if (block_n == 0) block_n = (N % 256 == 0 || N > 1024) ? 256 : 128;
+  if (block_n != 128 && block_n != 256) { set_error("wj_gemm_dgrad_bf16: block_n must be 128 or 256"); return WJ_ERR_ARG; }
+  CUtensorMap tmA, tmB;
+  const uint32_t boxA[4] = {BK, 1, BM, 1};
+  int rc = encode_map(&tmA, A, boxA);
+  if (rc) return rc;
+  rc = encode_map_2d(&tmB, W, (uint64_t)w_cols, (uint64_t)w_rows, (uint64_t)ldw * 2, 64, 64);
+  if (rc) return rc;
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.L = L; p.batch = batch; p.N = N; p.K = K;
+  p.mb_per_batch = (L + BM - 1) / BM;
+  p.m_blocks = batch * p.mb_per_batch;
+  p.n_blocks = (N + block_n - 1) / block_n;
+  p.total_tiles = p.m_blocks * p.n_blocks;
+  fill_seg(p.seg, A);
+  for (int i = 0; i < 4; ++i) p.segB_col[i] = seg_col_off ? seg_col_off[i] : 0;
+  fill_epilogue(p, epi);
+  const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (block_n == 256) return launch<256, 2>(tmA, tmB, p, grid, st);
+  return launch<128, 2>(tmA, tmB, p, grid, st);
 }

@@ -109,3 +109,238 @@ def gemm_wgrad(dy: Operand, x: Operand, L: int, batch: int, out: torch.Tensor, *
     lib = _lib.load()
     check(lib.wj_gemm_wgrad_bf16(C.byref(dy), C.byref(x), L, batch, M, N, C.c_void_p(_ptr(out) + out_offset * 4),
                                  C.c_int64(ld), 1 if accumulate else 0, splits, _stream()))
+
+
+def gemm_dgrad(a: Operand, w: torch.Tensor, L: int, batch: int, out: torch.Tensor, *, K: int, N: int,
+               w_col_offset: int = 0, w_cols: Optional[int] = None, seg_col_off: Sequence[int] = (),
+               ld_out: Optional[int] = None, out_offset: int = 0, act: int = ACT_NONE,
+               aux: Optional[torch.Tensor] = None, ld_aux: Optional[int] = None, aux_offset: int = 0,
+               resid: Optional[torch.Tensor] = None, ld_resid: Optional[int] = None, resid_offset: int = 0,
+               accumulate: bool = False, out_rows: Optional[torch.Tensor] = None, block_n: int = 0) -> None:
+    """out[b*L+t, n] = epilogue(sum_r A(r; t, b) * w[r, w_col_offset + seg_col_off[s] + n]); w bf16 [R, cols] row-major."""
+    assert w.dtype == torch.bfloat16 and w.dim() == 2 and w.stride(1) == 1
+    e = Epilogue()
+    esz = out.element_size()
+    e.out = _ptr(out) + out_offset * esz
+    e.ld_out = out.stride(-2) if ld_out is None else ld_out
+    e.out_f32 = 1 if out.dtype == torch.float32 else 0
+    e.accumulate = 1 if accumulate else 0
+    if resid is not None:
+        e.resid = _ptr(resid) + resid_offset * resid.element_size()
+        e.resid_f32 = 1 if resid.dtype == torch.float32 else 0
+        e.ld_resid = resid.stride(-2) if ld_resid is None else ld_resid
+    if aux is not None:
+        assert aux.dtype == torch.bfloat16
+        e.aux = _ptr(aux) + aux_offset * 2
+        e.ld_aux = aux.stride(-2) if ld_aux is None else ld_aux
+    e.act = act
+    if out_rows is not None:
+        e.out_rows = _ptr(out_rows)
+    seg = (C.c_int32 * 4)(*([int(v) for v in seg_col_off] + [0] * (4 - len(seg_col_off))))
+    w_cols = (w.shape[1] - w_col_offset) if w_cols is None else w_cols
+    lib = _lib.load()
+    check(lib.wj_gemm_dgrad_bf16(C.byref(a), C.c_void_p(_ptr(w) + w_col_offset * 2), C.c_int64(w.stride(0)),
+                                 w.shape[0], w_cols, seg, L, batch, N, K, C.byref(e), block_n, _stream()))
+
+
+# ----------------------------------------------------------------------------------------------------- masks
+def masks_generate(kind: int, batch: int, n_times: int, in_channels: int, channel_based: bool, n_targets: int,
+                   ctx_prob: float, ctx_len: int, tgt_prob: float, tgt_len: int, cutoff: float, min_context_len: int,
+                   base_seed: int, row0: int, device):
+    T = n_times // in_channels
+    t_out = n_times if channel_based else T
+    ctx = torch.empty(batch, t_out, dtype=torch.bool, device=device)
+    tgt = torch.empty(batch, n_targets, t_out, dtype=torch.bool, device=device)
+    vis = torch.empty(batch, n_targets, t_out, dtype=torch.bool, device=device)
+    attempts = torch.zeros(batch, dtype=torch.int32, device=device)
+    err = torch.zeros(1, dtype=torch.int32, device=device)
+    lib = _lib.load()
+    check(lib.wj_masks_generate(kind, batch, n_times, in_channels, 1 if channel_based else 0, n_targets,
+                                C.c_double(ctx_prob), ctx_len, C.c_double(tgt_prob), tgt_len, C.c_float(cutoff),
+                                min_context_len, C.c_uint32(base_seed & 0xFFFFFFFF), C.c_uint32(row0 & 0xFFFFFFFF),
+                                C.c_void_p(_ptr(ctx)), C.c_void_p(_ptr(tgt)), C.c_void_p(_ptr(vis)),
+                                C.c_void_p(_ptr(attempts)), C.c_void_p(_ptr(err)), _stream()))
+    return ctx, tgt, vis, attempts, err
+
+
+class MaskIndex:
+    """Packed index lists built by wj_mask_indices (all int32, on device) + host-side totals."""
+    __slots__ = ("B", "G", "T", "n_c", "n_v", "n_t", "cu_c", "cu_v", "cu_t", "totals", "ctx_rows", "vis_src",
+                 "vis_pos", "tgt_vrow", "tgt_trow", "Nc", "Nv", "Nt", "max_nc", "max_nv")
+
+
+def mask_indices(ctx_hidden: torch.Tensor, tgt: torch.Tensor, vis_hidden: torch.Tensor) -> MaskIndex:
+    """ctx_hidden [B,T] bool, tgt [B,G,T] bool, vis_hidden [B,G,T] bool.  One small D2H copy (the totals)."""
+    assert ctx_hidden.dtype == torch.bool and tgt.dtype == torch.bool and vis_hidden.dtype == torch.bool
+    ctx_hidden, tgt, vis_hidden = ctx_hidden.contiguous(), tgt.contiguous(), vis_hidden.contiguous()
+    B, T = ctx_hidden.shape
+    G = tgt.shape[1]
+    dev = ctx_hidden.device
+    mi = MaskIndex()
+    mi.B, mi.G, mi.T = B, G, T
+    i32 = dict(dtype=torch.int32, device=dev)
+    mi.n_c = torch.empty(B, **i32); mi.n_v = torch.empty(B * G, **i32); mi.n_t = torch.empty(B * G, **i32)
+    mi.cu_c = torch.empty(B + 1, **i32); mi.cu_v = torch.empty(B * G + 1, **i32); mi.cu_t = torch.empty(B * G + 1, **i32)
+    mi.totals = torch.empty(8, **i32)
+    mi.ctx_rows = torch.empty(B * T, **i32)
+    mi.vis_src = torch.empty(B * G * T, **i32); mi.vis_pos = torch.empty(B * G * T, **i32)
+    mi.tgt_vrow = torch.empty(B * G * T, **i32); mi.tgt_trow = torch.empty(B * G * T, **i32)
+    lib = _lib.load()
+    p = lambda t: C.c_void_p(_ptr(t))
+    check(lib.wj_mask_indices(p(ctx_hidden), p(tgt), p(vis_hidden), B, G, T, p(mi.n_c), p(mi.n_v), p(mi.n_t),
+                              p(mi.cu_c), p(mi.cu_v), p(mi.cu_t), p(mi.totals), p(mi.ctx_rows), p(mi.vis_src),
+                              p(mi.vis_pos), p(mi.tgt_vrow), p(mi.tgt_trow), _stream()))
+    tot = mi.totals.tolist()  # the one host sync of the step: grid sizes of the varlen kernels
+    mi.Nc, mi.Nv, mi.Nt, viol, mi.max_nc, mi.max_nv = tot[0], tot[1], tot[2], tot[3], tot[4], tot[5]
+    if viol:
+        raise _lib.WavJepaLibError(f"{viol} target positions are hidden from the predictor (ctx_and_target_masks); "
+                                   "unsupported by the packed path")
+    return mi
+
+
+# ----------------------------------------------------------------------------------------------------- conv0
+def conv0_fwd(x: torch.Tensor, w: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, out: torch.Tensor,
+              stats: torch.Tensor, k: int = 10, stride: int = 5, eps: float = 1e-5) -> None:
+    B, Cin, L = x.shape
+    assert x.dtype == torch.bfloat16 and x.is_contiguous() and w.dtype == torch.float32
+    lib = _lib.load()
+    check(lib.wj_conv0_gn_gelu_fwd(C.c_void_p(_ptr(x)), C.c_void_p(_ptr(w)), C.c_void_p(_ptr(gamma)),
+                                   C.c_void_p(_ptr(beta)), B, Cin, L, w.shape[0], k, stride, C.c_float(eps),
+                                   C.c_void_p(_ptr(stats)), C.c_void_p(_ptr(out)), _stream()))
+
+
+def conv0_bwd(x, w, gamma, beta, stats, dy, red_scratch, dw, dgamma, dbeta, k: int = 10, stride: int = 5,
+              eps: float = 1e-5) -> None:
+    B, Cin, L = x.shape
+    lib = _lib.load()
+    p = lambda t: C.c_void_p(_ptr(t))
+    check(lib.wj_conv0_gn_gelu_bwd(p(x), p(w), p(gamma), p(beta), B, Cin, L, w.shape[0], k, stride, C.c_float(eps),
+                                   p(stats), p(dy), p(red_scratch), p(dw), p(dgamma), p(dbeta), _stream()))
+
+
+# ----------------------------------------------------------------------------------------------------- norms
+def layernorm_fwd(x: torch.Tensor, gamma, beta, eps: float, out_f32=None, out_bf16=None, stats=None, rowsum=None):
+    M, D = x.shape
+    assert x.is_contiguous()
+    lib = _lib.load()
+    p = lambda t: C.c_void_p(_ptr(t))
+    check(lib.wj_layernorm_fwd(p(x), 1 if x.dtype == torch.bfloat16 else 0, p(gamma), p(beta), C.c_float(eps), M, D,
+                               p(out_f32), p(out_bf16), p(stats), p(rowsum), _stream()))
+
+
+def layernorm_bwd(dy: torch.Tensor, x: torch.Tensor, stats, gamma, dx_f32=None, dx_bf16=None, dgamma=None, dbeta=None,
+                  colsum=None):
+    M, D = x.shape
+    assert dy.dtype == torch.float32 and dy.is_contiguous() and x.is_contiguous()
+    lib = _lib.load()
+    p = lambda t: C.c_void_p(_ptr(t))
+    check(lib.wj_layernorm_bwd(p(dy), p(x), 1 if x.dtype == torch.bfloat16 else 0, p(stats), p(gamma), M, D, p(dx_f32),
+                               p(dx_bf16), p(dgamma), p(dbeta), p(colsum), _stream()))
+
+
+def crop_norm(audio: torch.Tensor, starts: Optional[torch.Tensor], crops_per_clip: int, crop_len: int,
+              out_bf16=None, out_f32=None):
+    n_clips, ch, clip_len = audio.shape
+    assert audio.dtype == torch.float32 and audio.is_contiguous()
+    lib = _lib.load()
+    p = lambda t: C.c_void_p(_ptr(t))
+    check(lib.wj_crop_norm(p(audio), p(starts), n_clips, ch, C.c_int64(clip_len), crops_per_clip, crop_len,
+                           p(out_bf16), p(out_f32), _stream()))
+
+
+def target_accum(x: torch.Tensor, rowsum, B: int, T: int, D: int, scale: float, first: bool, inst_stats, targets,
+                 eps: float = 1e-5):
+    lib = _lib.load()
+    p = lambda t: C.c_void_p(_ptr(t))
+    check(lib.wj_target_accum(p(x), p(rowsum), B, T, D, C.c_float(eps), C.c_float(scale), 1 if first else 0,
+                              p(inst_stats), p(targets), _stream()))
+
+
+# ----------------------------------------------------------------------------------------------------- attention
+def attn_fwd(qkv: torch.Tensor, cu: torch.Tensor, n_seqs: int, max_len: int, D: int, H: int, out: torch.Tensor,
+             lse2=None):
+    lib = _lib.load()
+    p = lambda t: C.c_void_p(_ptr(t))
+    check(lib.wj_attn_varlen_fwd(p(qkv), p(cu), n_seqs, max_len, D, H, p(out), p(lse2), _stream()))
+
+
+def attn_bwd(qkv, out, dout, lse2, cu, n_seqs: int, max_len: int, D: int, H: int, dqkv):
+    lib = _lib.load()
+    p = lambda t: C.c_void_p(_ptr(t))
+    check(lib.wj_attn_varlen_bwd(p(qkv), p(out), p(dout), p(lse2), p(cu), n_seqs, max_len, D, H, p(dqkv), _stream()))
+
+
+# ----------------------------------------------------------------------------------------------------- misc
+def gather_rows(src: torch.Tensor, idx: Optional[torch.Tensor], N: int, out_f32=None, out_bf16=None):
+    D = src.shape[-1]
+    lib = _lib.load()
+    p = lambda t: C.c_void_p(_ptr(t))
+    check(lib.wj_gather_rows(p(src), 1 if src.dtype == torch.bfloat16 else 0, p(idx), N, D, p(out_f32), p(out_bf16),
+                             _stream()))
+
+
+def scatter_dgelu(src: torch.Tensor, idx: torch.Tensor, h: Optional[torch.Tensor], N: int, out_bf16: torch.Tensor):
+    lib = _lib.load()
+    p = lambda t: C.c_void_p(_ptr(t))
+    check(lib.wj_scatter_dgelu(p(src), p(idx), p(h), N, src.shape[-1], p(out_bf16), _stream()))
+
+
+def predictor_assemble(ctx_bf16, mask_token, pos, vis_src, vis_pos, N: int, D: int, out_f32, out_bf16):
+    lib = _lib.load()
+    p = lambda t: C.c_void_p(_ptr(t))
+    check(lib.wj_predictor_assemble(p(ctx_bf16), p(mask_token), p(pos), p(vis_src), p(vis_pos), N, D, p(out_f32),
+                                    p(out_bf16), _stream()))
+
+
+def predictor_assemble_bwd(dx0, vis_src, N: int, D: int, d_ctx, d_mask_token):
+    lib = _lib.load()
+    p = lambda t: C.c_void_p(_ptr(t))
+    check(lib.wj_predictor_assemble_bwd(p(dx0), p(vis_src), N, D, p(d_ctx), p(d_mask_token), _stream()))
+
+
+def masked_mse(pred_bf16, targets, tgt_rows, Nt: int, D: int, loss, dpred_bf16=None):
+    lib = _lib.load()
+    p = lambda t: C.c_void_p(_ptr(t))
+    check(lib.wj_masked_mse(p(pred_bf16), p(targets), p(tgt_rows), Nt, D, p(loss), p(dpred_bf16), _stream()))
+
+
+def ema_update(teacher_flat: torch.Tensor, student_flat: torch.Tensor, decay: float):
+    assert teacher_flat.numel() == student_flat.numel()
+    lib = _lib.load()
+    p = lambda t: C.c_void_p(_ptr(t))
+    check(lib.wj_ema_update(p(teacher_flat), p(student_flat), C.c_int64(teacher_flat.numel()), C.c_double(decay),
+                            _stream()))
+
+
+def sumsq(x: torch.Tensor, scale: float, out_f64: torch.Tensor):
+    lib = _lib.load()
+    p = lambda t: C.c_void_p(_ptr(t))
+    check(lib.wj_sumsq(p(x), C.c_int64(x.numel()), C.c_float(scale), p(out_f64), _stream()))
+
+
+def adamw_step(p_, g, m, v, lr, beta1, beta2, eps, wd, step, grad_scale=1.0, max_norm=0.0, grad_sumsq=None, p_bf16=None):
+    lib = _lib.load()
+    p = lambda t: C.c_void_p(_ptr(t))
+    check(lib.wj_adamw_step(p(p_), p(g), p(m), p(v), C.c_int64(p_.numel()), C.c_float(lr), C.c_float(beta1),
+                            C.c_float(beta2), C.c_float(eps), C.c_float(wd), int(step), C.c_float(grad_scale),
+                            C.c_float(max_norm), p(grad_sumsq), p(p_bf16), _stream()))
+
+
+def cast_bf16(x: torch.Tensor, y: torch.Tensor):
+    lib = _lib.load()
+    p = lambda t: C.c_void_p(_ptr(t))
+    check(lib.wj_cast_bf16(p(x), p(y), C.c_int64(x.numel()), _stream()))
+
+
+def colsum(x: torch.Tensor, out: torch.Tensor, M: Optional[int] = None):
+    M = x.shape[0] if M is None else M
+    lib = _lib.load()
+    p = lambda t: C.c_void_p(_ptr(t))
+    check(lib.wj_colsum(p(x), 1 if x.dtype == torch.bfloat16 else 0, C.c_int64(M), x.shape[1], C.c_int64(x.stride(0)),
+                        p(out), _stream()))
+
+
+def scale_bf16(x: torch.Tensor, scale_dev: torch.Tensor):
+    lib = _lib.load()
+    p = lambda t: C.c_void_p(_ptr(t))
+    check(lib.wj_scale_bf16(p(x), p(scale_dev), C.c_int64(x.numel()), _stream()))
