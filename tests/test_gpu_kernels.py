@@ -1,0 +1,445 @@
+"""Kernel-level parity on the B200: every C-ABI entry point against a plain PyTorch fp32 restatement of the same op
+(float kernels, tolerance stated per test) or against the numpy oracle (integer mask kernels, bit-exact)."""
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from wavjepa_b200 import _lib, ops  # noqa: E402
+
+DEV = "cuda"
+BF16_TOL = 4e-3   # rel-L2 of a bf16-rounded result against fp32 (bf16 eps = 3.9e-3, rel-L2 of rounding ~1.7e-3)
+
+
+def rel(a, b):
+    a = a.float()
+    b = b.float()
+    return ((a - b).norm() / (b.norm() + 1e-30)).item()
+
+
+@pytest.fixture(autouse=True, scope="module")
+def _device():
+    _lib.require_device()
+    torch.manual_seed(0)
+
+
+# ------------------------------------------------------------------------------------------------------- GEMM
+@pytest.mark.parametrize("M,N,K,bn", [(128, 256, 64, 256), (128, 128, 64, 128), (300, 768, 512, 0), (300, 384, 768, 256),
+                                      (20000, 2304, 768, 256), (20000, 1152, 384, 128), (77, 3072, 768, 0)])
+def test_gemm_plain(M, N, K, bn):
+    a = torch.randn(M, K, device=DEV).bfloat16()
+    w = (torch.randn(N, K, device=DEV) * 0.05).bfloat16()
+    out = torch.full((M, N), float("nan"), device=DEV, dtype=torch.bfloat16)
+    ops.gemm(ops.plain_operand(a), w, M, 1, out, block_n=bn)
+    assert rel(out, a.float() @ w.float().t()) < BF16_TOL
+
+
+def test_gemm_f32_out():
+    M, N, K = 5000, 768, 3072
+    a = torch.randn(M, K, device=DEV).bfloat16()
+    w = (torch.randn(N, K, device=DEV) * 0.05).bfloat16()
+    out = torch.empty(M, N, device=DEV)
+    ops.gemm(ops.plain_operand(a), w, M, 1, out)
+    assert rel(out, a.float() @ w.float().t()) < 2e-5
+
+
+def test_gemm_epilogues():
+    M, N, K = 1000, 1536, 384
+    a = torch.randn(M, K, device=DEV).bfloat16()
+    w = (torch.randn(N, K, device=DEV) * 0.05).bfloat16()
+    bias = torch.randn(N, device=DEV)
+    base = a.float() @ w.float().t()
+    out = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+    out2 = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+    ops.gemm(ops.plain_operand(a), w, M, 1, out, bias=bias, act=ops.ACT_GELU, out2=out2)
+    h = (base + bias).bfloat16()
+    assert rel(out2, h) < 1e-4
+    assert rel(out, F.gelu(h.float())) < BF16_TOL
+    res = torch.randn(M, N, device=DEV)
+    o3 = torch.empty(M, N, device=DEV)
+    ops.gemm(ops.plain_operand(a), w, M, 1, o3, bias=bias, resid=res)
+    assert rel(o3, base + bias + res) < 2e-5
+    # act 3: the Linear output is rounded to bf16 before the fp32 residual
+    ops.gemm(ops.plain_operand(a), w, M, 1, o3, bias=bias, resid=res, act=ops.ACT_BF16)
+    assert rel(o3, (base + bias).bfloat16().float() + res) < 1e-4
+    aux = torch.randn(M, N, device=DEV).bfloat16()
+    o4 = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+    ops.gemm(ops.plain_operand(a), w, M, 1, o4, act=ops.ACT_DGELU, aux=aux)
+    x = aux.float().requires_grad_(True)
+    F.gelu(x).sum().backward()
+    assert rel(o4, base * x.grad) < BF16_TOL
+    pos = torch.randn(200, N, device=DEV)
+    o5 = torch.empty(M, N, device=DEV)
+    ops.gemm(ops.plain_operand(a), w, M, 1, o5, resid=pos, resid_mod=200)
+    assert rel(o5, base + pos[torch.arange(M, device=DEV) % 200]) < 2e-5
+    perm = torch.randperm(M, device=DEV).int()
+    o6 = torch.zeros(M, N, device=DEV)
+    ops.gemm(ops.plain_operand(a), w, M, 1, o6, out_rows=perm)
+    ref6 = torch.zeros(M, N, device=DEV)
+    ref6[perm.long()] = base
+    assert rel(o6, ref6) < 2e-5
+
+
+def _conv_operand(x, L_in, k):
+    Bn, _, Cc = x.shape
+    return ops.make_operand(x, Cc, L_in // 2, Bn, nq=2, q_stride=Cc, row_stride=2 * Cc, batch_stride=L_in * Cc,
+                            seg_width=Cc, seg_q=(0, 1, 0)[:k], seg_p=(0, 0, 1)[:k])
+
+
+@pytest.mark.parametrize("Bn,L_in,k", [(3, 402, 3), (3, 400, 2), (2, 6430, 3)])
+def test_conv_implicit_gemm(Bn, L_in, k):
+    Cc = 512
+    x = torch.randn(Bn, L_in, Cc, device=DEV).bfloat16()
+    w = (torch.randn(Cc, Cc, k, device=DEV) * 0.03).bfloat16()
+    L_out = (L_in - k) // 2 + 1
+    wk = w.permute(0, 2, 1).reshape(Cc, k * Cc).contiguous()
+    out = torch.full((Bn, L_out, Cc), float("nan"), device=DEV, dtype=torch.bfloat16)
+    ops.gemm(_conv_operand(x, L_in, k), wk, L_out, Bn, out.view(-1, Cc))
+    ref = F.conv1d(x.float().transpose(1, 2), w.float(), stride=2).transpose(1, 2)
+    assert rel(out, ref) < BF16_TOL
+    # overlapping-row view (row pitch 2C < row length kC)
+    a = ops.make_operand(x, k * Cc, L_out, Bn, row_stride=2 * Cc, batch_stride=L_in * Cc)
+    out.fill_(float("nan"))
+    ops.gemm(a, wk, L_out, Bn, out.view(-1, Cc))
+    assert rel(out, ref) < BF16_TOL
+
+
+@pytest.mark.parametrize("M,Nw,Kw,splits", [(1000, 256, 384, 0), (64, 128, 128, 1), (50000, 768, 3072, 0), (333, 1152, 384, 0)])
+def test_wgrad(M, Nw, Kw, splits):
+    dy = torch.randn(M, Nw, device=DEV).bfloat16()
+    x = torch.randn(M, Kw, device=DEV).bfloat16()
+    out = torch.full((Nw, Kw), float("nan"), device=DEV)
+    ops.gemm_wgrad(ops.plain_operand(dy), ops.plain_operand(x), M, 1, out, splits=splits)
+    assert rel(out, dy.float().t() @ x.float()) < 5e-5
+
+
+@pytest.mark.parametrize("L_in,k", [(402, 3), (400, 2)])
+def test_conv_wgrad_dgrad(L_in, k):
+    Bn, Cc = 3, 512
+    x = torch.randn(Bn, L_in, Cc, device=DEV).bfloat16()
+    w = (torch.randn(Cc, Cc, k, device=DEV) * 0.03).bfloat16()
+    L_out = (L_in - k) // 2 + 1
+    dy = torch.randn(Bn, L_out, Cc, device=DEV).bfloat16()
+    xf = x.float().transpose(1, 2).requires_grad_(True)
+    wf = w.float().requires_grad_(True)
+    F.conv1d(xf, wf, stride=2).backward(dy.float().transpose(1, 2))
+    # wgrad
+    out = torch.zeros(Cc, k * Cc, device=DEV)
+    ops.gemm_wgrad(ops.make_operand(dy, Cc, L_out, Bn), _conv_operand(x, L_in, k), L_out, Bn, out)
+    assert rel(out, wf.grad.permute(0, 2, 1).reshape(Cc, k * Cc)) < 5e-5
+    # dgrad: even / odd input positions are two GEMMs over shifted views of dY
+    wk = w.permute(0, 2, 1).reshape(Cc, k * Cc).contiguous()
+    dx = torch.full((Bn, L_in, Cc), float("nan"), device=DEV, dtype=torch.bfloat16)
+    ops.conv_dgrad(dy, wk, dx, k)
+    assert rel(dx, xf.grad.transpose(1, 2)) < BF16_TOL
+
+
+@pytest.mark.parametrize("M,N,K", [(1000, 768, 2304), (515, 384, 1536), (4000, 3072, 768)])
+def test_dgrad(M, N, K):
+    dy = torch.randn(M, K, device=DEV).bfloat16()
+    w = (torch.randn(K, N, device=DEV) * 0.05).bfloat16()   # y = x W^T, W [K(out), N(in)]
+    res = torch.randn(M, N, device=DEV)
+    out = torch.empty(M, N, device=DEV)
+    ops.gemm_dgrad(ops.plain_operand(dy), w, M, 1, out, K=K, N=N, resid=res)
+    assert rel(out, dy.float() @ w.float() + res) < 2e-5
+    aux = torch.randn(M, N, device=DEV).bfloat16()
+    o2 = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+    ops.gemm_dgrad(ops.plain_operand(dy), w, M, 1, o2, K=K, N=N, act=ops.ACT_DGELU, aux=aux)
+    x = aux.float().requires_grad_(True)
+    F.gelu(x).sum().backward()
+    assert rel(o2, (dy.float() @ w.float()) * x.grad) < BF16_TOL
+
+
+# ------------------------------------------------------------------------------------------------------- masks
+def test_masks_time_inverse_bit_exact():
+    from oracle import masks_oracle as mo
+
+    B, T = 512, 200
+    ctx, tgt, vis, att, err = ops.masks_generate(0, B, T, 1, False, 4, 0.65, 10, 0.25, 10, 0.1, 0, 1234, 7, DEV)
+    assert err.item() == 0
+    rc, rt, rv, ra = mo.time_inverse_masks(1234, 7, B, T)
+    assert np.array_equal(ctx.cpu().numpy(), rc)
+    assert np.array_equal(tgt.cpu().numpy(), rt)
+    assert np.array_equal(vis.cpu().numpy(), rv)
+    assert np.array_equal(att.cpu().numpy(), ra)
+
+
+def test_masks_speech_and_binaural_bit_exact():
+    from oracle import masks_oracle as mo
+
+    B, T = 256, 200
+    ctx, tgt, vis, att, err = ops.masks_generate(1, B, T, 1, False, 4, 0.0, 1, 0.1, 10, 0.5, 5, 99, 0, DEV)
+    assert err.item() == 0
+    rc, rt, rv, ra = mo.speech_masks(99, 0, B, T, tgt_prob=0.1, tgt_len=10, cutoff=0.5, min_context_len=5)
+    assert np.array_equal(ctx.cpu().numpy(), rc) and np.array_equal(tgt.cpu().numpy(), rt)
+    assert np.array_equal(vis.cpu().numpy(), rv) and np.array_equal(att.cpu().numpy(), ra)
+    # WavJEPA-Nat: n_times = 400 over 2 channels, "(S C)" interleave
+    ctx, tgt, vis, att, err = ops.masks_generate(0, 64, 400, 2, True, 4, 0.65, 10, 0.25, 10, 0.1, 0, 5, 1000, DEV)
+    rc, rt, rv, ra = mo.time_inverse_masks(5, 1000, 64, 400, in_channels=2, channel_based=True)
+    assert ctx.shape == (64, 400)
+    assert np.array_equal(ctx.cpu().numpy(), rc) and np.array_equal(tgt.cpu().numpy(), rt)
+    assert np.array_equal(vis.cpu().numpy(), rv)
+
+
+def test_mask_indices():
+    B, G, T = 37, 4, 200
+    ctx, tgt, vis, _, _ = ops.masks_generate(0, B, T, 1, False, G, 0.65, 10, 0.25, 10, 0.1, 0, 3, 0, DEV)
+    mi = ops.mask_indices(ctx, tgt, vis)
+    c, t, v = ctx.cpu(), tgt.cpu(), vis.cpu()
+    ctx_rows = torch.nonzero(~c.reshape(-1)).squeeze(1)
+    assert mi.Nc == ctx_rows.numel() and torch.equal(mi.ctx_rows[:mi.Nc].cpu().long(), ctx_rows)
+    assert torch.equal(mi.n_c.cpu().long(), (~c).sum(1))
+    assert torch.equal(mi.cu_c.cpu().long(), F.pad((~c).sum(1).cumsum(0), (1, 0)))
+    visible = ~v.reshape(B * G, T)
+    assert mi.Nv == int(visible.sum()) and mi.Nt == int(t.sum())
+    assert torch.equal(mi.cu_v.cpu().long(), F.pad(visible.sum(1).cumsum(0), (1, 0)))
+    # packed predictor rows: position and source
+    pos = torch.nonzero(visible)[:, 1]
+    assert torch.equal(mi.vis_pos[:mi.Nv].cpu().long(), pos)
+    packed_ctx_index = torch.full((B * T,), -1, dtype=torch.long)
+    packed_ctx_index[ctx_rows] = torch.arange(mi.Nc)
+    bg = torch.nonzero(visible)[:, 0]
+    src = packed_ctx_index[(bg // G) * T + pos]
+    assert torch.equal(mi.vis_src[:mi.Nv].cpu().long(), src)
+    # target rows
+    tg = t.reshape(B * G, T)
+    vrow_of = torch.full((B * G, T), -1, dtype=torch.long)
+    vrow_of[visible] = torch.arange(mi.Nv)
+    nz = torch.nonzero(tg)
+    assert torch.equal(mi.tgt_vrow[:mi.Nt].cpu().long(), vrow_of[nz[:, 0], nz[:, 1]])
+    assert torch.equal(mi.tgt_trow[:mi.Nt].cpu().long(), (nz[:, 0] // G) * T + nz[:, 1])
+    assert mi.max_nc == int((~c).sum(1).max()) and mi.max_nv == int(visible.sum(1).max())
+
+
+# ------------------------------------------------------------------------------------------------------- conv0
+@pytest.mark.parametrize("Cin,L", [(1, 32159), (2, 4000)])
+def test_conv0_gn_gelu_fwd_bwd(Cin, L):
+    B, C = 3, 512
+    x = torch.randn(B, Cin, L, device=DEV).bfloat16()
+    w = torch.randn(C, Cin, 10, device=DEV) * math.sqrt(2.0 / (Cin * 10))
+    gamma = 1.0 + 0.1 * torch.randn(C, device=DEV)
+    beta = 0.1 * torch.randn(C, device=DEV)
+    L_out = (L - 10) // 5 + 1
+    out = torch.empty(B, L_out, C, device=DEV, dtype=torch.bfloat16)
+    stats = torch.empty(B, C, 2, device=DEV, dtype=torch.float64)
+    ops.conv0_fwd(x, w, gamma, beta, out, stats)
+    wr = w.bfloat16().float().requires_grad_(True)
+    gr = gamma.clone().requires_grad_(True)
+    br = beta.clone().requires_grad_(True)
+    h = F.conv1d(x.float(), wr, stride=5)
+    hq = h + (h.bfloat16().float() - h).detach()       # bf16-rounded conv output (autocast), straight-through
+    y = F.gelu(F.group_norm(hq, C, gr, br, 1e-5))
+    assert rel(out, y.transpose(1, 2)) < BF16_TOL
+    dy = torch.randn(B, L_out, C, device=DEV).bfloat16()
+    y.backward(dy.float().transpose(1, 2))
+    dw = torch.zeros_like(w)
+    dg = torch.zeros(C, device=DEV)
+    db = torch.zeros(C, device=DEV)
+    red = torch.empty(B, C, 2, device=DEV, dtype=torch.float64)
+    ops.conv0_bwd(x, w, gamma, beta, stats, dy, red, dw, dg, db)
+    assert rel(dw, wr.grad) < 2e-3
+    assert rel(dg, gr.grad) < 2e-3
+    assert rel(db, br.grad) < 2e-3
+
+
+# ------------------------------------------------------------------------------------------------------- norms
+@pytest.mark.parametrize("D,dtype", [(768, torch.float32), (384, torch.float32), (512, torch.bfloat16)])
+def test_layernorm_fwd_bwd(D, dtype):
+    M = 1237
+    x = (torch.randn(M, D, device=DEV) * 2 + 0.5).to(dtype)
+    g = 1 + 0.1 * torch.randn(D, device=DEV)
+    b = 0.1 * torch.randn(D, device=DEV)
+    of = torch.empty(M, D, device=DEV)
+    ob = torch.empty(M, D, device=DEV, dtype=torch.bfloat16)
+    st = torch.empty(M, 2, device=DEV)
+    rs = torch.empty(M, 2, device=DEV)
+    ops.layernorm_fwd(x, g, b, 1e-6, of, ob, st, rs)
+    xr = x.float().requires_grad_(True)
+    gr = g.clone().requires_grad_(True)
+    br = b.clone().requires_grad_(True)
+    y = F.layer_norm(xr, (D,), gr, br, 1e-6)
+    assert rel(of, y) < 1e-5 and rel(ob, y) < BF16_TOL
+    assert rel(rs[:, 0], y.sum(1)) < 1e-3 and rel(rs[:, 1], (y * y).sum(1)) < 1e-5
+    dy = torch.randn(M, D, device=DEV)
+    y.backward(dy)
+    dxf = torch.empty(M, D, device=DEV)
+    dxb = torch.empty(M, D, device=DEV, dtype=torch.bfloat16)
+    dg = torch.zeros(D, device=DEV)
+    db = torch.zeros(D, device=DEV)
+    cs = torch.zeros(D, device=DEV)
+    ops.layernorm_bwd(dy, x, st, g, dxf, dxb, dg, db, cs)
+    assert rel(dxf, xr.grad) < 1e-4 and rel(dxb, xr.grad) < BF16_TOL
+    assert rel(dg, gr.grad) < 1e-4 and rel(db, br.grad) < 1e-4
+    assert (cs - xr.grad.sum(0)).abs().max().item() < 1e-2
+
+
+def test_crop_norm():
+    n_clips, S, Lc, Lfull = 4, 8, 32159, 160000
+    audio = torch.randn(n_clips, 1, Lfull, device=DEV) * 0.3 + 0.01
+    starts = torch.randint(0, Lfull - Lc + 1, (n_clips * S,), device=DEV, dtype=torch.int32)
+    ob = torch.empty(n_clips * S, 1, Lc, device=DEV, dtype=torch.bfloat16)
+    of = torch.empty(n_clips * S, 1, Lc, device=DEV)
+    ops.crop_norm(audio, starts, S, Lc, ob, of)
+    idx = starts.long().view(n_clips, S, 1) + torch.arange(Lc, device=DEV)
+    crops = torch.gather(audio.expand(-1, S, -1), 2, idx).reshape(n_clips * S, 1, Lc)
+    ref = (crops - crops.mean(dim=(-2, -1), keepdim=True)) / (crops.std(dim=(-2, -1), keepdim=True) + 1e-5)
+    assert rel(of, ref) < 1e-5 and rel(ob, ref) < BF16_TOL
+    # HEAR chunking: no starts table, fixed stride, zero padding past the clip end, 2 channels normalised jointly
+    audio2 = torch.randn(3, 2, 70000, device=DEV)
+    n_chunks = 3
+    st2 = (torch.arange(n_chunks, device=DEV, dtype=torch.int32) * Lc).repeat(3)
+    of2 = torch.empty(3 * n_chunks, 2, Lc, device=DEV)
+    ops.crop_norm(audio2, st2, n_chunks, Lc, None, of2)
+    padded = F.pad(audio2, (0, n_chunks * Lc - 70000))
+    ch = padded.view(3, 2, n_chunks, Lc).permute(0, 2, 1, 3).reshape(3 * n_chunks, 2, Lc)
+    ref2 = (ch - ch.mean(dim=(-2, -1), keepdim=True)) / (ch.std(dim=(-2, -1), keepdim=True) + 1e-5)
+    assert rel(of2, ref2) < 1e-5
+
+
+def test_target_accum():
+    B, T, D, K = 5, 200, 768, 3
+    layers = [torch.randn(B * T, D, device=DEV) * (i + 1) + 0.3 * i for i in range(K)]
+    g = torch.ones(D, device=DEV)
+    b = torch.zeros(D, device=DEV)
+    targets = torch.empty(B * T, D, device=DEV)
+    inst = torch.empty(B, 2, device=DEV)
+    outs = []
+    for i, x in enumerate(layers):
+        of = torch.empty_like(x)
+        rs = torch.empty(B * T, 2, device=DEV)
+        ops.layernorm_fwd(x, g, b, 1e-6, of, None, None, rs)
+        outs.append(of)
+        ops.target_accum(of, rs, B, T, D, 1.0 / K, i == 0, inst, targets)
+    stacked = torch.stack([o.view(B, T, D) for o in outs]).transpose(2, 3)
+    ref = F.instance_norm(stacked).transpose(2, 3).mean(0)
+    assert rel(targets.view(B, T, D), ref) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------------------- attention
+def _attn_ref(qkv, cu, D, H):
+    dh = D // H
+    outs = []
+    for s in range(len(cu) - 1):
+        x = qkv[cu[s]:cu[s + 1]]
+        n = x.shape[0]
+        q, k, v = (x[:, i * D:(i + 1) * D].reshape(n, H, dh).transpose(0, 1) for i in range(3))
+        o = F.scaled_dot_product_attention(q, k, v)
+        outs.append(o.transpose(0, 1).reshape(n, D))
+    return torch.cat(outs)
+
+
+@pytest.mark.parametrize("D,H,lens", [(768, 12, [39, 72, 20, 1, 64, 65]), (384, 12, [85, 122, 128, 17]),
+                                      (768, 12, [200, 200, 200]), (384, 12, [250, 3])])
+def test_attention_fwd_bwd(D, H, lens):
+    cu_l = [0]
+    for n in lens:
+        cu_l.append(cu_l[-1] + n)
+    tot = cu_l[-1]
+    cu = torch.tensor(cu_l, device=DEV, dtype=torch.int32)
+    qkv = torch.randn(tot, 3 * D, device=DEV).bfloat16()
+    out = torch.full((tot, D), float("nan"), device=DEV, dtype=torch.bfloat16)
+    lse = torch.empty(tot, H, device=DEV)
+    ops.attn_fwd(qkv, cu, len(lens), max(lens), D, H, out, lse)
+    qr = qkv.float().requires_grad_(True)
+    ref = _attn_ref(qr, cu_l, D, H)
+    assert rel(out, ref) < 6e-3
+    do = torch.randn(tot, D, device=DEV).bfloat16()
+    ref.backward(do.float())
+    dqkv = torch.full((tot, 3 * D), float("nan"), device=DEV, dtype=torch.bfloat16)
+    ops.attn_bwd(qkv, out, do, lse, cu, len(lens), max(lens), D, H, dqkv)
+    assert rel(dqkv, qr.grad) < 1.5e-2
+
+
+# ------------------------------------------------------------------------------------------------------- elementwise
+def test_gather_scatter_assemble():
+    N, D, R = 700, 384, 1000
+    src = torch.randn(R, D, device=DEV)
+    idx = torch.randperm(R, device=DEV)[:N].int()
+    of = torch.empty(N, D, device=DEV)
+    ob = torch.empty(N, D, device=DEV, dtype=torch.bfloat16)
+    ops.gather_rows(src, idx, N, of, ob)
+    assert torch.equal(of, src[idx.long()]) and torch.equal(ob, src[idx.long()].bfloat16())
+    ops.gather_rows(src.bfloat16(), None, R, of2 := torch.empty(R, D, device=DEV), None)
+    assert torch.equal(of2, src.bfloat16().float())
+    h = torch.randn(R, D, device=DEV).bfloat16()
+    out = torch.zeros(R, D, device=DEV, dtype=torch.bfloat16)
+    ops.scatter_dgelu(of, idx, h, N, out)
+    x = h.float().requires_grad_(True)
+    F.gelu(x).sum().backward()
+    ref = torch.zeros(R, D, device=DEV)
+    ref[idx.long()] = of * x.grad[idx.long()]
+    assert rel(out, ref) < BF16_TOL
+    out.zero_()
+    ops.scatter_dgelu(src, None, h, R, out)
+    assert rel(out, src * x.grad) < BF16_TOL
+    # predictor input assembly
+    Nc, Nv, T = 300, 900, 200
+    ctx = torch.randn(Nc, D, device=DEV).bfloat16()
+    mt = torch.randn(D, device=DEV) * 0.02
+    pos = torch.randn(T, D, device=DEV)
+    vsrc = torch.randint(-1, Nc, (Nv,), device=DEV, dtype=torch.int32)
+    vpos = torch.randint(0, T, (Nv,), device=DEV, dtype=torch.int32)
+    xf = torch.empty(Nv, D, device=DEV)
+    xb = torch.empty(Nv, D, device=DEV, dtype=torch.bfloat16)
+    ops.predictor_assemble(ctx, mt, pos, vsrc, vpos, Nv, D, xf, xb)
+    base = torch.where((vsrc >= 0)[:, None], ctx.float()[vsrc.clamp(min=0).long()], mt.bfloat16().float()[None])
+    assert torch.equal(xf, base + pos[vpos.long()])
+    dx0 = torch.randn(Nv, D, device=DEV)
+    dctx = torch.zeros(Nc, D, device=DEV)
+    dmt = torch.zeros(D, device=DEV)
+    ops.predictor_assemble_bwd(dx0, vsrc, Nv, D, dctx, dmt)
+    rctx = torch.zeros(Nc, D, device=DEV).index_add_(0, vsrc.clamp(min=0).long(), dx0 * (vsrc >= 0)[:, None])
+    assert rel(dctx, rctx) < 1e-5 and rel(dmt, dx0[vsrc < 0].sum(0)) < 1e-4
+
+
+def test_masked_mse():
+    Nt, D, R = 4321, 768, 2000
+    pred = torch.randn(Nt, D, device=DEV).bfloat16()
+    tg = torch.randn(R, D, device=DEV)
+    rows = torch.randint(0, R, (Nt,), device=DEV, dtype=torch.int32)
+    loss = torch.zeros(1, device=DEV)
+    dp = torch.empty(Nt, D, device=DEV, dtype=torch.bfloat16)
+    ops.masked_mse(pred, tg, rows, Nt, D, loss, dp)
+    pr = pred.float().requires_grad_(True)
+    ref = ((pr - tg[rows.long()]) ** 2).mean(-1).sum() / (Nt + 1e-8)
+    ref.backward()
+    assert abs(loss.item() - ref.item()) / ref.item() < 1e-5
+    assert rel(dp, pr.grad) < BF16_TOL
+
+
+def test_ema_bitwise_and_optimizer_tail():
+    n = 1_000_003
+    t = torch.randn(n, device=DEV)
+    s = torch.randn(n, device=DEV)
+    r = 0.999
+    ref = t.clone().mul_(r).add_((1 - r) * s)
+    ops.ema_update(t, s, r)
+    assert torch.equal(t, ref)
+    # AdamW + clip against torch.optim.AdamW / clip_grad_norm_
+    p = torch.randn(n, device=DEV)
+    g = torch.randn(n, device=DEV) * 0.1
+    pr = torch.nn.Parameter(p.clone())
+    opt = torch.optim.AdamW([pr], lr=4e-4, betas=(0.9, 0.98), eps=1e-6, weight_decay=0.04)
+    m = torch.zeros(n, device=DEV)
+    v = torch.zeros(n, device=DEV)
+    pb = torch.empty(n, device=DEV, dtype=torch.bfloat16)
+    for step in range(1, 4):
+        pr.grad = g.clone() * step
+        torch.nn.utils.clip_grad_norm_([pr], 5.0)
+        opt.step()
+        ss = torch.zeros(1, device=DEV, dtype=torch.float64)
+        ops.sumsq(g * step, 1.0, ss)
+        ops.adamw_step(p, g * step, m, v, 4e-4, 0.9, 0.98, 1e-6, 0.04, step, 1.0, 5.0, ss, pb)
+        assert rel(p, pr.data) < 1e-6
+    assert torch.equal(pb, p.bfloat16())
+    y = torch.empty(n, device=DEV, dtype=torch.bfloat16)
+    ops.cast_bf16(s, y)
+    assert torch.equal(y, s.bfloat16())
+    x = torch.randn(3000, 768, device=DEV)
+    cs = torch.zeros(768, device=DEV)
+    ops.colsum(x.bfloat16(), cs)
+    assert rel(cs, x.bfloat16().float().sum(0)) < 1e-4

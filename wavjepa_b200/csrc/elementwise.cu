@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(256) scatter_dgelu_kernel(const float* __restr
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const long long r = i / D4;
     const int c = static_cast<int>(i - r * D4);
-    const size_t o = static_cast<size_t>(idx[r]) * D4 * 4 + c * 4;
+    const size_t o = static_cast<size_t>(idx ? idx[r] : r) * D4 * 4 + c * 4;
     float4 v = reinterpret_cast<const float4*>(src)[i];
     if (h != nullptr) {
       const float4 hv = load4(h, true, o);

@@ -13,7 +13,7 @@ import torch
 from . import _lib
 from ._lib import Epilogue, Operand, check
 
-ACT_NONE, ACT_GELU, ACT_DGELU = 0, 1, 2
+ACT_NONE, ACT_GELU, ACT_DGELU, ACT_BF16 = 0, 1, 2, 3
 
 
 def _stream() -> C.c_void_p:
@@ -141,6 +141,38 @@ def gemm_dgrad(a: Operand, w: torch.Tensor, L: int, batch: int, out: torch.Tenso
     lib = _lib.load()
     check(lib.wj_gemm_dgrad_bf16(C.byref(a), C.c_void_p(_ptr(w) + w_col_offset * 2), C.c_int64(w.stride(0)),
                                  w.shape[0], w_cols, seg, L, batch, N, K, C.byref(e), block_n, _stream()))
+
+
+def conv_operand(x: torch.Tensor, k: int) -> Operand:
+    """Implicit-GEMM view of channels-last activations x [B, L_in, C] (L_in even) for a stride-2 Conv1d of width k
+    (reference nn.Conv1d(512,512,k,2), wavjepa/extractors/audio_feature_extractor.py:70): virtual column j*C + c of
+    output row t is x[b, 2t + j, c] = pair-view (c, parity j&1, row t + j//2)."""
+    B, L_in, C = x.shape
+    if L_in % 2 != 0 or k not in (2, 3):
+        raise _lib.WavJepaLibError(f"conv_operand: stride-2 implicit GEMM needs an even input length and k in (2,3); got L={L_in} k={k}")
+    return make_operand(x, C, L_in // 2, B, nq=2, q_stride=C, row_stride=2 * C, batch_stride=L_in * C,
+                        seg_width=C, seg_q=(0, 1, 0)[:k], seg_p=(0, 0, 1)[:k])
+
+
+def conv_dgrad(dy: torch.Tensor, wk: torch.Tensor, dx: torch.Tensor, k: int, *, act: int = ACT_NONE,
+               aux: Optional[torch.Tensor] = None) -> None:
+    """Data gradient of the stride-2 Conv1d: dy [B, L_out, O] bf16, wk [O, k*C] bf16 (k-major), dx [B, L_in, C].
+    Even input positions 2m receive taps j=0 (t=m) and j=2 (t=m-1); odd positions 2m+1 receive tap j=1 (t=m):
+    two GEMMs over (shifted) views of dy, written with row pitch 2C.  act/aux: optional x GELU'(aux) epilogue
+    (aux = pre-activation of the layer below, same layout as dx)."""
+    B, L_out, O = dy.shape
+    _, L_in, C = dx.shape
+    assert dy.is_contiguous() and dx.is_contiguous() and wk.shape == (O, k * C)
+    if L_in % 2 != 0:
+        raise _lib.WavJepaLibError("conv_dgrad: odd input length is not supported")
+    half = L_in // 2
+    taps_even = (0, 2) if k == 3 else (0,)
+    a_even = make_operand(dy, O, L_out, B, seg_width=O, seg_q=(0,) * len(taps_even), seg_p=(0, -1)[:len(taps_even)])
+    a_odd = make_operand(dy, O, L_out, B, seg_width=O, seg_q=(0,), seg_p=(0,))
+    kw = dict(ld_out=2 * C, act=act, aux=aux, ld_aux=2 * C)
+    gemm_dgrad(a_even, wk, half, B, dx, K=len(taps_even) * O, N=C, seg_col_off=[j * C for j in taps_even],
+               out_offset=0, aux_offset=0, **kw)
+    gemm_dgrad(a_odd, wk, half, B, dx, K=O, N=C, seg_col_off=[C], out_offset=C, aux_offset=C, **kw)
 
 
 # ----------------------------------------------------------------------------------------------------- masks
