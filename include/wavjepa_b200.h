@@ -145,11 +145,15 @@ int wj_layernorm_fwd(const void* x, int x_is_bf16, const float* gamma, const flo
 int wj_layernorm_bwd(const float* dy, const void* x, int x_is_bf16, const float* stats, const float* gamma, int M,
                      int D, float* dx_f32, void* dx_bf16, float* dgamma, float* dbeta, float* colsum, void* stream);
 
-/* out[i] = (audio[clip, :, start_i : start_i+crop_len] - mean) / (std_unbiased + 1e-5), statistics over (C, crop_len)
- * jointly; i = clip*crops_per_clip + j; samples past clip_len read as zero.  JEPA.on_after_batch_transfer
- * (wavjepa/jepa.py:291-311) and hear_api/runtime.py:12-16 (normalize). */
-int wj_crop_norm(const float* audio, const int* starts, int n_clips, int channels, int64_t clip_len,
-                 int crops_per_clip, int crop_len, void* out_bf16, float* out_f32, void* stream);
+/* out[i] = (g*audio[clip, :, start_i : start_i+crop_len] - mean) / (std_unbiased + 1e-5), statistics over
+ * (C, crop_len) jointly; i = clip*crops_per_clip + j; samples past clip_len read as zero; g = gain[clip] (NULL = 1).
+ * JEPA.on_after_batch_transfer (wavjepa/jepa.py:291-311) and hear_api/runtime.py:12-16 (normalize). */
+int wj_crop_norm(const float* audio, const int* starts, const float* gain, int n_clips, int channels,
+                 int64_t clip_len, int crops_per_clip, int crop_len, void* out_bf16, float* out_f32, void* stream);
+/* gain[clip] = 10^((target_dbfs - 20 log10(rms)) / 20) with rms over the whole clip (1 when rms == 0):
+ * normalize_audio (hear_api/feature_helper.py:5-13). */
+int wj_clip_gain(const float* audio, int n_clips, int channels, int64_t clip_len, float target_dbfs, float* gain,
+                 void* stream);
 
 /* targets (=|+=) scale * instance_norm(x) with statistics over all T*D values of each instance (biased var, eps);
  * rowsum [B*T, 2] comes from wj_layernorm_fwd.  JEPA._make_targets (wavjepa/jepa.py:230-253). */
@@ -169,7 +173,11 @@ int wj_attn_varlen_bwd(const void* qkv_bf16, const void* out_bf16, const void* d
  * contextual_features[~ctx_masks] (wavjepa/jepa.py:399). */
 int wj_gather_rows(const void* src, int src_is_bf16, const int* idx, int N, int D, float* out_f32, void* out_bf16,
                    void* stream);
-/* out_bf16[idx[i], :] = src[i, :] * GELU'(h[idx[i], :]) (h may be NULL); rows not listed are left untouched. */
+/* out[idx[i], :] = src[i, :] (fp32): packed encoder rows back to their dense [B*T, D] positions
+ * (JEPA.get_audio_representation, wavjepa/jepa.py:456-467). */
+int wj_scatter_rows(const float* src, const int* idx, int N, int D, float* out, void* stream);
+/* out_bf16[idx[i], :] = src[i, :] * GELU'(h[idx[i], :]) (h may be NULL, idx NULL = identity); rows not listed are
+ * left untouched. */
 int wj_scatter_dgelu(const float* src, const int* idx, const void* h_bf16, int N, int D, void* out_bf16, void* stream);
 
 /* Predictor input: x0[r] = (vis_src[r] >= 0 ? ctx[vis_src[r]] : bf16(mask_token)) + pos[vis_pos[r]]

@@ -1,0 +1,191 @@
+"""CPU suite (no GPU): pins the oracle restatements against the golden fixtures produced by the executed reference
+(tests/golden/make_golden.py), and checks host-side logic and the C-ABI surface."""
+import ctypes
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import inputs as oi
+from oracle import jepa_oracle as jo
+from oracle import masks_oracle as mo
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = os.path.join(HERE, "golden")
+ROOT = os.path.dirname(HERE)
+
+
+def rel(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.linalg.norm(a - b) / (np.linalg.norm(b) + 1e-30))
+
+
+# ------------------------------------------------------------------------------------------------- masks
+def _unpack(a, shape):
+    return np.unpackbits(a)[:int(np.prod(shape))].reshape(shape).astype(bool)
+
+
+@pytest.mark.parametrize("span", [mo.span_mask_np, mo.span_mask_py])
+def test_mask_oracle_matches_reference_goldens(span):
+    g = np.load(os.path.join(GOLD, "masks.npz"))
+    c, t, v, a = mo.time_inverse_masks(1234, 100, 64, 200, span=span)
+    assert np.array_equal(c, _unpack(g["ti_ctx"], c.shape)) and np.array_equal(t, _unpack(g["ti_tgt"], t.shape))
+    assert np.array_equal(v, _unpack(g["ti_vis"], v.shape)) and np.array_equal(a, g["ti_att"])
+    c, t, v, a = mo.speech_masks(99, 0, 64, 200, tgt_prob=0.1, tgt_len=10, cutoff=0.5, min_context_len=5, span=span)
+    assert np.array_equal(c, _unpack(g["sp_ctx"], c.shape)) and np.array_equal(t, _unpack(g["sp_tgt"], t.shape))
+    assert np.array_equal(v, _unpack(g["sp_vis"], v.shape)) and np.array_equal(a, g["sp_att"])
+    c, t, v, a = mo.time_inverse_masks(5, 7, 32, 400, in_channels=2, channel_based=True, span=span)
+    assert c.shape == (32, 400)
+    assert np.array_equal(c, _unpack(g["nat_ctx"], c.shape)) and np.array_equal(t, _unpack(g["nat_tgt"], t.shape))
+    assert np.array_equal(v, _unpack(g["nat_vis"], v.shape)) and np.array_equal(a, g["nat_att"])
+    c, t, v, a = mo.time_inverse_masks(77, 0, 64, 200, cutoff=0.2, span=span)
+    assert np.array_equal(c, _unpack(g["hard_ctx"], c.shape)) and np.array_equal(a, g["hard_att"])
+    assert a.max() > 1  # the rejection loop is exercised
+
+
+def test_mask_invariants():
+    c, t, v, _ = mo.time_inverse_masks(3, 0, 128, 200)
+    ctx_visible = ~c
+    assert not (ctx_visible[:, None, :] & t).any()                       # context and targets are disjoint
+    assert np.array_equal(v, ~(ctx_visible[:, None, :] | t))             # predictor sees context U target group
+    assert (ctx_visible.sum(1) / 200 >= 0.1).all()
+
+
+def test_pcg64_chain_matches_numpy():
+    for words in ([0], [1234, 5, 6], [2**32 - 1, 0, 99]):
+        mine = mo.Pcg64(words)
+        theirs = np.random.default_rng(list(words))
+        assert [mine.random() for _ in range(4)] == [theirs.random() for _ in range(4)]
+        mine = mo.Pcg64(words)
+        theirs = np.random.default_rng(list(words))
+        assert sorted(mine.choice_no_replace(190, 13)) == sorted(theirs.choice(190, 13, replace=False).tolist())
+
+
+# ------------------------------------------------------------------------------------------------- model oracle
+def _run_oracle(cfg, n_clips, crops, seed, masker, backward=True):
+    sd = jo.make_state_dict(cfg, seed=3)
+    names = [k for k in sd if not k.startswith(("teacher_encoder.", "pos_encoding"))]
+    for k in names:
+        sd[k].requires_grad_(backward)
+    inp = oi.training_inputs(cfg, n_clips, crops, seed=seed, masker=masker)
+    out = jo.forward(inp["audio"], inp["ctx_masks"], inp["target_indices"], inp["ctx_and_target_masks"], sd, cfg)
+    if backward:
+        out["loss"].backward()
+    return sd, inp, out
+
+
+@pytest.mark.parametrize("name,cfg,crops,seed,masker", [
+    ("train_c1", jo.Cfg(), 4, 1234, "audioset"),
+    ("train_speech", jo.Cfg(), 2, 4321, "librispeech"),
+    ("train_nat", jo.Cfg(in_channels=2, per_channel=True), 2, 55, "audioset"),
+])
+def test_oracle_forward_backward_matches_reference(name, cfg, crops, seed, masker):
+    torch.set_num_threads(os.cpu_count())
+    g = np.load(os.path.join(GOLD, f"{name}.npz"))
+    meta = json.load(open(os.path.join(GOLD, f"{name}.json")))
+    sd, inp, out = _run_oracle(cfg, 1, crops, seed, masker)
+    assert abs(out["loss"].item() - float(g["loss"])) / float(g["loss"]) < 2e-5
+    B, G, T = inp["target_indices"].shape
+    preds_t = out["preds"].view(B, G, T, -1)[inp["target_indices"]]
+    for k, t in (("local_features", out["local_features"]), ("contextual_features", out["contextual_features"]),
+                 ("targets", out["targets"]), ("preds_at_targets", preds_t)):
+        assert list(t.shape) == meta[k]["shape"], k
+        assert rel(oi.subsample(t), g[k]) < 2e-4, k
+        assert abs(float(t.detach().norm()) - meta[k]["l2"]) / meta[k]["l2"] < 2e-4, k
+    for n_, ref_norm in meta["grad_norms"].items():
+        gr = sd[n_].grad
+        assert gr is not None, n_
+        assert abs(float(gr.norm()) - ref_norm) / (ref_norm + 1e-12) < 2e-3, n_
+    for k in g.files:
+        if k.startswith("grad::"):
+            assert rel(oi.subsample(sd[k[6:]].grad), g[k]) < 2e-3, k
+    with torch.no_grad():
+        jo.ema_update(sd, step=0)
+    assert np.array_equal(oi.subsample(sd["teacher_encoder.layers.3.linear1.weight"]),
+                          g["teacher_after_ema::layers.3.linear1.weight"])
+
+
+def test_oracle_hear_matches_reference():
+    torch.set_num_threads(os.cpu_count())
+    g = np.load(os.path.join(GOLD, "hear.npz"))
+    cfg = jo.Cfg()
+    sd = jo.make_state_dict(cfg, seed=3)
+    with torch.no_grad():
+        for tag, n in (("3s", 48000), ("exact", 64318)):
+            emb, ts = jo.hear_timestamp_embeddings(oi.hear_inputs(2, n, seed=11), sd, cfg)
+            assert list(emb.shape) == g[f"{tag}_shape"].tolist()
+            assert rel(oi.subsample(emb), g[f"{tag}_emb"]) < 2e-4
+            assert np.allclose(ts[0].numpy(), g[f"{tag}_ts"], rtol=1e-6, atol=1e-4)
+            if tag == "3s":
+                assert rel(emb.mean(1).numpy(), g["3s_scene"]) < 2e-4
+    # frame geometry of hear_api/runtime.py:98-145: 10 s -> 996 frames, 64318 -> 400, 1 s -> 100
+    assert jo.hear_geometry(160000, 32159, 16000, 200)[:3] == (795, 5, 996)
+    assert g["10s_shape"].tolist() == [2, 996, 768]
+    assert jo.hear_geometry(64318, 32159, 16000, 200)[2] == 400
+    assert jo.hear_geometry(16000, 32159, 16000, 200)[2] == 100
+
+
+# ------------------------------------------------------------------------------------------------- host-side logic
+def _model():
+    import wavjepa_b200 as w
+
+    ex = w.ConvFeatureExtractor(conv_layers_spec=jo.BASE_SPEC, in_channels=1)
+    return w.JEPA(feature_extractor=ex, transformer_encoder_cfg=w.TransformerEncoderCFG.create(),
+                  transformer_encoder_layers_cfg=w.TransformerLayerCFG.create(),
+                  transformer_decoder_cfg=w.TransformerEncoderCFG.create(),
+                  transformer_decoder_layers_cfg=w.TransformerLayerCFG.create(d_model=384),
+                  process_audio_seconds=2.01, nr_samples_per_audio=8, average_top_k_layers=8, lr=4e-4,
+                  adam_weight_decay=0.04)
+
+
+def test_state_dict_is_the_references():
+    keys = json.load(open(os.path.join(GOLD, "ref_state_dict_keys.json")))
+    m = _model()
+    sd = m.state_dict()
+    assert [[k, list(v.shape)] for k, v in sd.items()] == keys
+    assert m.total_patches == 200 and m.target_length == 32159 and m.encoder_embedding_dim == 768
+    assert sum(p.numel() for p in m.parameters() if p.requires_grad) == 111012864
+    # a reference-format checkpoint loads strictly, including the torch.compile `_orig_mod` free names
+    m.load_state_dict(jo.make_state_dict(jo.Cfg(), seed=3), strict=True)
+    assert torch.equal(m.pos_encoding_encoder, jo.sincos_table(200, 768))
+
+
+def test_schedules_and_geometry():
+    from transformers import get_cosine_schedule_with_warmup
+    from wavjepa_b200.extractors import out_length
+
+    m = _model()
+    p = torch.nn.Parameter(torch.zeros(1))
+    opt = torch.optim.AdamW([p], lr=4e-4)
+    sch = get_cosine_schedule_with_warmup(opt, num_warmup_steps=100000, num_training_steps=375000)
+    for step in (0, 1, 50000, 100000, 200000, 374999):
+        assert abs(m.lr_at(step) - 4e-4 * sch.lr_lambdas[0](step)) < 1e-12
+    for step in (0, 1, 99999, 100000, 200000):
+        assert m._get_ema_decay(step) == jo.ema_decay(step)
+    assert m._get_ema_decay(0) == pytest.approx(0.999)
+    assert out_length(jo.BASE_SPEC, 32159) == 200 and out_length(jo.BASE_SPEC, 64319) == 401
+    assert m.extract_audio.receptive_fields[0] == 240
+
+
+def test_no_cpu_fallback():
+    from wavjepa_b200 import _lib
+
+    m = _model()
+    with pytest.raises(_lib.WavJepaLibError):
+        m.get_audio_representation(torch.zeros(1, 1, 32159), None)
+
+
+def test_c_abi_exports_every_declared_symbol():
+    from wavjepa_b200 import _lib
+
+    hdr = open(os.path.join(ROOT, "include", "wavjepa_b200.h")).read()
+    names = sorted(set(re.findall(r"\b(wj_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(names) >= 25
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/wavjepa_b200.h but not exported"
+    assert lib.wj_version() >= 1

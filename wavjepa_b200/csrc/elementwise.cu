@@ -60,6 +60,41 @@ __global__ void __launch_bounds__(256) scatter_dgelu_kernel(const float* __restr
   }
 }
 
+// out_f32[idx[r], :] = src_f32[r, :]
+__global__ void __launch_bounds__(256) scatter_rows_kernel(const float* __restrict__ src, const int* __restrict__ idx,
+                                                           long long n4, int D4, float* __restrict__ out) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = i / D4;
+    const int c = static_cast<int>(i - r * D4);
+    reinterpret_cast<float4*>(out)[static_cast<long long>(idx[r]) * D4 + c] = reinterpret_cast<const float4*>(src)[i];
+  }
+}
+
+// gain[clip] = 10^((target_dbfs - 20 log10(rms)) / 20), rms over all channels and samples of the clip; 1 if rms == 0
+__global__ void __launch_bounds__(512) clip_gain_kernel(const float* __restrict__ audio, long long per_clip,
+                                                        float target_dbfs, float* __restrict__ gain) {
+  __shared__ double s_red[16];
+  const float* src = audio + static_cast<size_t>(blockIdx.x) * per_clip;
+  double acc = 0.0;
+  for (long long i = threadIdx.x; i < per_clip; i += blockDim.x) { const double v = src[i]; acc += v * v; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 16; ++w) t += s_red[w];
+    const float rms = sqrtf(static_cast<float>(t / static_cast<double>(per_clip)));
+    float g = 1.0f;
+    if (rms != 0.f) {
+      const float cur = 20.0f * log10f(rms);
+      g = powf(10.0f, (target_dbfs - cur) / 20.0f);
+    }
+    gain[blockIdx.x] = g;
+  }
+}
+
 // x0[r, :] = (src[r] >= 0 ? ctx[src[r], :] : bf16(mask_token)) + pos[pos_idx[r], :]
 __global__ void __launch_bounds__(256) predictor_assemble_kernel(const bf16* __restrict__ ctx,
                                                                  const float* __restrict__ mask_token,
@@ -277,6 +312,22 @@ extern "C" int wj_scatter_dgelu(const float* src, const int* idx, const void* h_
   scatter_dgelu_kernel<<<grid_for(n4), 256, 0, WJ_STREAM(stream)>>>(src, idx, reinterpret_cast<const bf16*>(h_bf16), n4,
                                                                    D / 4, reinterpret_cast<bf16*>(out_bf16));
   return check_launch("scatter_dgelu");
+}
+
+extern "C" int wj_scatter_rows(const float* src, const int* idx, int N, int D, float* out, void* stream) {
+  if (N <= 0) return WJ_OK;
+  if (D % 4 || idx == nullptr) { set_error("wj_scatter_rows: D %% 4 != 0 or idx NULL"); return WJ_ERR_ARG; }
+  const long long n4 = static_cast<long long>(N) * (D / 4);
+  scatter_rows_kernel<<<grid_for(n4), 256, 0, WJ_STREAM(stream)>>>(src, idx, n4, D / 4, out);
+  return check_launch("scatter_rows");
+}
+
+extern "C" int wj_clip_gain(const float* audio, int n_clips, int channels, int64_t clip_len, float target_dbfs,
+                            float* gain, void* stream) {
+  if (n_clips <= 0) return WJ_OK;
+  clip_gain_kernel<<<n_clips, 512, 0, WJ_STREAM(stream)>>>(audio, static_cast<long long>(channels) * clip_len,
+                                                          target_dbfs, gain);
+  return check_launch("clip_gain");
 }
 
 extern "C" int wj_predictor_assemble(const void* ctx_bf16, const float* mask_token, const float* pos,

@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
 // ------------------------------------------------------------------------------------------------ crop + normalise
 // out[i, c, :] = (x[clip, c, start:start+Lc] - mean) / (std_unbiased + 1e-5) over (C, Lc) jointly; one block / instance.
 __global__ void __launch_bounds__(512) crop_norm_kernel(const float* __restrict__ audio, const int* __restrict__ starts,
-                                                        int C, long long Lfull, int S, int Lc, float gain_dbfs_enable,
+                                                        int C, long long Lfull, int S, int Lc, const float* __restrict__ gain,
                                                         bf16* __restrict__ out_bf16, float* __restrict__ out_f32) {
   __shared__ double s_red[32];
   __shared__ double s_val[2];
@@ -184,10 +184,11 @@ __global__ void __launch_bounds__(512) crop_norm_kernel(const float* __restrict_
   const float* src = audio + static_cast<size_t>(clip) * C * Lfull;
   const int n = C * Lc;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const float gn = gain ? gain[clip] : 1.0f;  // loudness gain of hear_api/feature_helper.py:5-13 (inference only)
   auto at = [&](int i) -> float {
     const int c = i / Lc, t = i - c * Lc;
     const long long p = start + t;
-    return p < Lfull ? src[static_cast<size_t>(c) * Lfull + p] : 0.f;  // zero padding past the clip end (HEAR)
+    return p < Lfull ? __fmul_rn(src[static_cast<size_t>(c) * Lfull + p], gn) : 0.f;  // zero padding past the clip end (HEAR)
   };
   auto block_sum = [&](double v) -> double {
 #pragma unroll
@@ -315,11 +316,12 @@ extern "C" int wj_layernorm_bwd(const float* dy, const void* x, int x_is_bf16, c
   return launch_ln_bwd<float>(dy, x, stats, gamma, M, D, dx_f32, db, dgamma, dbeta, colsum, WJ_STREAM(stream));
 }
 
-extern "C" int wj_crop_norm(const float* audio, const int* starts, int n_clips, int channels, int64_t clip_len,
-                            int crops_per_clip, int crop_len, void* out_bf16, float* out_f32, void* stream) {
+extern "C" int wj_crop_norm(const float* audio, const int* starts, const float* gain, int n_clips, int channels,
+                            int64_t clip_len, int crops_per_clip, int crop_len, void* out_bf16, float* out_f32,
+                            void* stream) {
   const int n = n_clips * crops_per_clip;
   if (n <= 0) return WJ_OK;
-  crop_norm_kernel<<<n, 512, 0, WJ_STREAM(stream)>>>(audio, starts, channels, clip_len, crops_per_clip, crop_len, 0.f,
+  crop_norm_kernel<<<n, 512, 0, WJ_STREAM(stream)>>>(audio, starts, channels, clip_len, crops_per_clip, crop_len, gain,
                                                     reinterpret_cast<bf16*>(out_bf16), out_f32);
   return check_launch("crop_norm");
 }

@@ -271,13 +271,30 @@ def layernorm_bwd(dy: torch.Tensor, x: torch.Tensor, stats, gamma, dx_f32=None, 
 
 
 def crop_norm(audio: torch.Tensor, starts: Optional[torch.Tensor], crops_per_clip: int, crop_len: int,
-              out_bf16=None, out_f32=None):
+              out_bf16=None, out_f32=None, gain: Optional[torch.Tensor] = None):
     n_clips, ch, clip_len = audio.shape
     assert audio.dtype == torch.float32 and audio.is_contiguous()
     lib = _lib.load()
     p = lambda t: C.c_void_p(_ptr(t))
-    check(lib.wj_crop_norm(p(audio), p(starts), n_clips, ch, C.c_int64(clip_len), crops_per_clip, crop_len,
+    check(lib.wj_crop_norm(p(audio), p(starts), p(gain), n_clips, ch, C.c_int64(clip_len), crops_per_clip, crop_len,
                            p(out_bf16), p(out_f32), _stream()))
+
+
+def clip_gain(audio: torch.Tensor, target_dbfs: float = -14.0) -> torch.Tensor:
+    n_clips, ch, clip_len = audio.shape
+    assert audio.dtype == torch.float32 and audio.is_contiguous()
+    gain = torch.empty(n_clips, device=audio.device, dtype=torch.float32)
+    lib = _lib.load()
+    check(lib.wj_clip_gain(C.c_void_p(_ptr(audio)), n_clips, ch, C.c_int64(clip_len), C.c_float(target_dbfs),
+                           C.c_void_p(_ptr(gain)), _stream()))
+    return gain
+
+
+def scatter_rows(src: torch.Tensor, idx: torch.Tensor, N: int, out: torch.Tensor):
+    assert src.dtype == torch.float32 and out.dtype == torch.float32 and idx.dtype == torch.int32
+    lib = _lib.load()
+    p = lambda t: C.c_void_p(_ptr(t))
+    check(lib.wj_scatter_rows(p(src), p(idx), N, src.shape[-1], p(out), _stream()))
 
 
 def target_accum(x: torch.Tensor, rowsum, B: int, T: int, D: int, scale: float, first: bool, inst_stats, targets,
