@@ -26,6 +26,8 @@ extern "C" {
 
 const char* wj_last_error(void);
 int wj_version(void);
+/* Number of CUDA kernels this library has launched in the calling process so far (bench.py: gpu_launches). */
+long long wj_kernel_launches(void);
 /* 0 if the current device is sm_100 (B200); WJ_ERR_ARCH otherwise. */
 int wj_check_device(void);
 

@@ -1,0 +1,249 @@
+"""End-to-end parity on the B200: the wavjepa_b200 module API (JEPA / maskers / HEAR runtime, all compute through
+libwavjepa_b200.so) against (1) the golden fixtures produced by the executed reference (tests/golden/*.npz) and
+(2) the CPU oracle run live on the same seeded inputs.
+
+Tolerances (north_star): masks bit-exact; features / targets / predictions rel-L2 <= 1e-2; loss rel
+<= 1e-3; one-step gradients rel-L2 <= 2e-2 per parameter tensor (bf16 operands, fp32 accumulation -- the reference's
+own bf16-autocast run sits at 5e-3..9e-3 against its fp32 run)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+import wavjepa_b200 as w  # noqa: E402
+from wavjepa_b200 import _lib, hear, ops  # noqa: E402
+from oracle import inputs as oi  # noqa: E402
+from oracle import jepa_oracle as jo  # noqa: E402
+from oracle import masks_oracle as mo  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = os.path.join(HERE, "golden")
+DEV = "cuda"
+
+FEAT_TOL = 1e-2
+LOSS_TOL = 1e-3
+GRAD_TOL = 2e-2
+
+
+def rel(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.linalg.norm(a - b) / (np.linalg.norm(b) + 1e-30))
+
+
+def build_model(cfg: jo.Cfg, sd=None, **kw):
+    if cfg.per_channel:
+        ex = w.ConvChannelFeatureExtractor(conv_layers_spec=cfg.spec, in_channels=cfg.in_channels,
+                                           share_weights_over_channels=False)
+    else:
+        ex = w.ConvFeatureExtractor(conv_layers_spec=cfg.spec, in_channels=cfg.in_channels)
+    m = w.JEPA(feature_extractor=ex, transformer_encoder_cfg=w.TransformerEncoderCFG.create(),
+               transformer_encoder_layers_cfg=w.TransformerLayerCFG.create(),
+               transformer_decoder_cfg=w.TransformerEncoderCFG.create(),
+               transformer_decoder_layers_cfg=w.TransformerLayerCFG.create(d_model=384),
+               process_audio_seconds=2.01, nr_samples_per_audio=8, average_top_k_layers=cfg.top_k, lr=4e-4,
+               adam_weight_decay=0.04, **kw)
+    if sd is not None:
+        m.load_state_dict({k: v.detach() for k, v in sd.items()}, strict=True)
+    return m.to(DEV)
+
+
+@pytest.fixture(autouse=True, scope="module")
+def _device():
+    _lib.require_device()
+    torch.manual_seed(0)
+
+
+CASES = [
+    ("train_c1", dict(), 4, 1234, "audioset"),
+    ("train_speech", dict(), 2, 4321, "librispeech"),
+    ("train_nat", dict(in_channels=2, per_channel=True), 2, 55, "audioset"),
+]
+
+
+def _gpu_masks(cfg, B, seed, masker):
+    if masker == "audioset":
+        mk = w.TimeInverseBlockMasker(target_masks_per_context=4, context_mask_prob=0.65, context_mask_length=10,
+                                      target_prob=0.25, target_length=10, ratio_cutoff=0.1,
+                                      channel_based_masking=cfg.per_channel, seed=seed, row0=0)
+    else:
+        mk = w.SpeechMasker(target_masks_per_context=4, target_prob=0.1, target_length=10, ratio_cutoff=0.5,
+                            min_context_len=5, seed=seed, row0=0)
+    out = mk(batch_size=B, n_times=cfg.total_patches, in_channels=cfg.in_channels if cfg.per_channel else 1)
+    mk.check()
+    return out
+
+
+@pytest.mark.parametrize("name,cfgkw,crops,seed,masker", CASES)
+def test_train_step_matches_reference_goldens(name, cfgkw, crops, seed, masker):
+    cfg = jo.Cfg(**cfgkw)
+    g = np.load(os.path.join(GOLD, f"{name}.npz"))
+    meta = json.load(open(os.path.join(GOLD, f"{name}.json")))
+    sd = jo.make_state_dict(cfg, seed=3)
+    model = build_model(cfg, sd)
+    inp = oi.training_inputs(cfg, 1, crops, seed=seed, masker=masker)
+    B = inp["audio"].shape[0]
+    # ---- masks: the CUDA masker reproduces the oracle's (= the reference's, tests/test_oracle_cpu.py) bit for bit
+    c_m, t_m, v_m = _gpu_masks(cfg, B, seed, masker)
+    assert torch.equal(c_m.cpu(), inp["ctx_masks"])
+    assert torch.equal(t_m.cpu(), inp["target_indices"])
+    assert torch.equal(v_m.cpu(), inp["ctx_and_target_masks"])
+    # ---- crop + normalise kernel == the host-side restatement (bf16 output)
+    clips = inp["clips"].to(DEV)
+    model.nr_samples_per_audio = crops
+    x16, c2, t2, v2 = model.on_after_batch_transfer(
+        (clips, c_m[None], t_m[None], v_m[None]), 0, starts=inp["starts"].to(DEV))
+    assert rel(x16.float().cpu().numpy(), inp["audio"].numpy()) < 2e-3
+    # ---- forward (the same bf16 audio the reference saw)
+    audio = inp["audio"].to(DEV).bfloat16()
+    out = model(audio, c_m, t_m, v_m)
+    loss = out["loss"]
+    assert abs(loss.item() - float(g["loss"])) / float(g["loss"]) < LOSS_TOL
+    G, T = t_m.shape[1], t_m.shape[2]
+    preds_t = out["preds"].view(B, G, T, -1)[t_m]
+    for k, t in (("local_features", out["local_features"]), ("contextual_features", out["contextual_features"]),
+                 ("targets", out["targets"]), ("preds_at_targets", preds_t)):
+        assert list(t.shape) == meta[k]["shape"], k
+        assert rel(oi.subsample(t.cpu()), g[k]) < FEAT_TOL, (k, rel(oi.subsample(t.cpu()), g[k]))
+    # ---- backward through the autograd bridge: per-parameter gradients
+    loss.backward()
+    params = dict(model.named_parameters())
+    worst = 0.0
+    for n_, ref_norm in meta["grad_norms"].items():
+        gr = params[n_].grad
+        assert gr is not None, n_
+        e = abs(float(gr.norm()) - ref_norm) / (ref_norm + 1e-12)
+        worst = max(worst, e)
+        assert e < GRAD_TOL, (n_, e)
+    for k in g.files:
+        if k.startswith("grad::"):
+            e = rel(oi.subsample(params[k[6:]].grad.cpu()), g[k])
+            assert e < GRAD_TOL, (k, e)
+    # ---- EMA with the pre-step student (decay 0.999 at step 0)
+    model._step_teacher()
+    tw = dict(model.teacher_encoder.named_parameters())["layers.3.linear1.weight"]
+    assert np.allclose(oi.subsample(tw.cpu()), g["teacher_after_ema::layers.3.linear1.weight"], rtol=0, atol=1e-9)
+
+
+def test_forward_matches_live_oracle_on_fresh_inputs():
+    """Same comparison against the oracle executed here (inputs that are not in the fixtures)."""
+    torch.set_num_threads(os.cpu_count())
+    cfg = jo.Cfg()
+    sd = jo.make_state_dict(cfg, seed=11)
+    inp = oi.training_inputs(cfg, 1, 3, seed=777, masker="audioset", row0=40)
+    with torch.no_grad():
+        ref = jo.forward(inp["audio"], inp["ctx_masks"], inp["target_indices"], inp["ctx_and_target_masks"], sd, cfg)
+    model = build_model(cfg, sd)
+    mk = w.TimeInverseBlockMasker(4, 0.65, 10, 0.25, 10, 0.1, seed=777, row0=40)
+    c_m, t_m, v_m = mk(batch_size=3, n_times=200, in_channels=1)
+    assert torch.equal(c_m.cpu(), inp["ctx_masks"]) and torch.equal(t_m.cpu(), inp["target_indices"])
+    with torch.no_grad():
+        out = model(inp["audio"].to(DEV).bfloat16(), c_m, t_m, v_m)
+    assert abs(out["loss"].item() - ref["loss"].item()) / ref["loss"].item() < LOSS_TOL
+    assert rel(out["local_features"].cpu().numpy(), ref["local_features"].numpy()) < FEAT_TOL
+    assert rel(out["targets"].cpu().numpy(), ref["targets"].numpy()) < FEAT_TOL
+    assert rel(out["contextual_features"].float().cpu().numpy(), ref["contextual_features"].numpy()) < FEAT_TOL
+    ti = inp["target_indices"]
+    B, G, T = ti.shape
+    ours = out["preds"].view(B, G, T, -1)[t_m].float().cpu().numpy()
+    theirs = ref["preds"].view(B, G, T, -1)[ti].numpy()
+    assert rel(ours, theirs) < FEAT_TOL
+
+
+def test_fused_train_step_equals_bridge_plus_torch_adamw():
+    """train_step (hand-written backward + fused clip/AdamW/EMA) == forward().backward() + clip_grad_norm_ +
+    torch.optim.AdamW + _step_teacher on a twin model (train.py:177-178, wavjepa/jepa.py:215-228, :330-331)."""
+    cfg = jo.Cfg()
+    sd = jo.make_state_dict(cfg, seed=5)
+    inp = oi.training_inputs(cfg, 1, 4, seed=31, masker="audioset")
+    a = build_model(cfg, sd)
+    b = build_model(cfg, sd)
+    a.global_step = b.global_step = 50000          # lr(0) == 0 would hide the optimizer (warm-up from 0)
+    audio = inp["audio"].to(DEV).bfloat16()
+    c_m, t_m, v_m = (inp[k].to(DEV) for k in ("ctx_masks", "target_indices", "ctx_and_target_masks"))
+    loss_a = a.train_step(audio, c_m, t_m, v_m)
+    out = b(audio, c_m, t_m, v_m)
+    out["loss"].backward()
+    assert abs(loss_a.item() - out["loss"].item()) < 1e-6
+    trainables = [p for p in b.parameters() if p.requires_grad]
+    opt = torch.optim.AdamW(trainables, lr=b.lr_at(50000), betas=(0.9, 0.98), eps=1e-6, weight_decay=0.04)
+    for p_ in trainables:   # the optimizer has taken 50000 steps (all with zero moments here): same bias correction
+        opt.state[p_] = dict(step=torch.tensor(50000.0), exp_avg=torch.zeros_like(p_), exp_avg_sq=torch.zeros_like(p_))
+    b._step_teacher()
+    torch.nn.utils.clip_grad_norm_(trainables, 5.0)
+    opt.step()
+    pa, pb = dict(a.named_parameters()), dict(b.named_parameters())
+    for n_ in pa:
+        d = (pa[n_].detach() - pb[n_].detach()).abs().max().item()
+        scale = pb[n_].detach().abs().max().item() + 1e-12
+        assert d <= 2e-6 * scale + 1e-7, (n_, d)
+    # weights moved, teacher moved
+    moved = (pa["encoder.layers.0.linear1.weight"].detach().cpu() - sd["encoder.layers.0.linear1.weight"]).abs().max()
+    assert moved > 0
+    assert a.global_step == 50001
+
+
+def test_instances_are_independent_at_scale():
+    """Size-independent property at a larger batch: every instance's local features / targets are unaffected by the
+    other instances in the batch (no batch statistics anywhere), and the loss of the batch equals the
+    target-count-weighted mean of the per-half losses."""
+    cfg = jo.Cfg()
+    model = build_model(cfg, jo.make_state_dict(cfg, seed=2))
+    B = 48
+    g = torch.Generator().manual_seed(5)
+    audio = torch.randn(B, 1, cfg.target_length, generator=g).to(DEV).bfloat16()
+    mk = w.TimeInverseBlockMasker(4, 0.65, 10, 0.25, 10, 0.1, seed=9, row0=0)
+    c_m, t_m, v_m = mk(batch_size=B, n_times=200, in_channels=1)
+    with torch.no_grad():
+        full = model(audio, c_m, t_m, v_m)
+        h = B // 2
+        lo = model(audio[:h], c_m[:h], t_m[:h], v_m[:h])
+        hi = model(audio[h:], c_m[h:], t_m[h:], v_m[h:])
+    assert torch.equal(full["local_features"][:h], lo["local_features"])
+    assert torch.equal(full["targets"][h:], hi["targets"])
+    n_lo, n_hi = t_m[:h].sum().item(), t_m[h:].sum().item()
+    mix = (lo["loss"].item() * n_lo + hi["loss"].item() * n_hi) / (n_lo + n_hi)
+    assert abs(full["loss"].item() - mix) / mix < 1e-5
+
+
+@pytest.mark.parametrize("tag,n", [("3s", 48000), ("exact", 64318), ("10s", 160000)])
+def test_hear_entry_points_match_reference_goldens(tag, n):
+    g = np.load(os.path.join(GOLD, "hear.npz"))
+    cfg = jo.Cfg()
+    sd = jo.make_state_dict(cfg, seed=3)
+    model = hear.load_model({"state_dict": {k.replace("encoder.", "encoder._orig_mod.", 1) if k.startswith("encoder.")
+                                            else k: v for k, v in sd.items()}})
+    assert model.sample_rate == 16000 and model.scene_embedding_size == 768 and model.timestamp_embedding_size == 768
+    assert model.unit_frames == 32159 and model.output_steps == 200
+    audio = oi.hear_inputs(2, n, seed=11).to(DEV)
+    emb, ts = hear.get_timestamp_embeddings(audio, model)
+    assert list(emb.shape) == g[f"{tag}_shape"].tolist() and emb.dtype == torch.float32
+    assert rel(oi.subsample(emb.cpu()), g[f"{tag}_emb"]) < FEAT_TOL
+    assert abs(float(emb.norm()) - float(g[f"{tag}_l2"])) / float(g[f"{tag}_l2"]) < FEAT_TOL
+    assert ts.shape == emb.shape[:2]
+    assert np.allclose(ts[0].numpy(), g[f"{tag}_ts"], rtol=1e-6, atol=1e-4)
+    if tag == "3s":
+        scene = hear.get_scene_embeddings(audio, model)
+        assert rel(scene.cpu().numpy(), g["3s_scene"]) < FEAT_TOL
+
+
+def test_hear_against_live_oracle_with_silent_clip():
+    """Edge cases of hear_api/feature_helper.py:5-13 and runtime.py:107-116: an all-zero clip (rms == 0 -> no gain,
+    zero std chunks) next to a normal one, 1 s long (a single padded chunk)."""
+    torch.set_num_threads(os.cpu_count())
+    cfg = jo.Cfg()
+    sd = jo.make_state_dict(cfg, seed=3)
+    audio = oi.hear_inputs(2, 16000, seed=3)
+    audio[1] = 0
+    with torch.no_grad():
+        ref_emb, ref_ts = jo.hear_timestamp_embeddings(audio, sd, cfg)
+    model = hear.load_model({"state_dict": sd})
+    emb, ts = model(audio.to(DEV))
+    assert emb.shape == ref_emb.shape == (2, 100, 768)
+    assert rel(emb[0].cpu().numpy(), ref_emb[0].numpy()) < FEAT_TOL
+    assert rel(emb[1].cpu().numpy(), ref_emb[1].numpy()) < FEAT_TOL
+    assert torch.allclose(ts, ref_ts)

@@ -53,7 +53,73 @@ class WavJepaLibError(RuntimeError):
 _lib = None
 
 
-def load(build_if_missing: bool = False) -> C.CDLL:
+class KernelProfile:
+    """Optional per-entry-point device timing (CUDA events on the current stream around every C-ABI call), used by
+    bench.py AFTER the timed region to attribute the step time to kernel families and to measure the dominant
+    kernel's average duration for the roofline.  Not active unless `with KernelProfile() as kp:` is entered."""
+
+    def __init__(self):
+        self.records = []   # (entry point, start event, end event, meta)
+        self.meta = None
+
+    def __enter__(self):
+        global _profile
+        _profile = self
+        return self
+
+    def __exit__(self, *exc):
+        global _profile
+        _profile = None
+
+    def summary(self):
+        """-> {entry point: (calls, total ms)} (synchronises)."""
+        import torch
+        torch.cuda.synchronize()
+        out = {}
+        for name, e0, e1, _ in self.records:
+            c, t = out.get(name, (0, 0.0))
+            out[name] = (c + 1, t + e0.elapsed_time(e1))
+        return out
+
+
+_profile = None
+
+
+class _Proxy:
+    """Attribute proxy over the CDLL so that calls can be bracketed by events when a KernelProfile is active."""
+
+    def __init__(self, cdll):
+        self._cdll = cdll
+
+    def __getattr__(self, name):
+        fn = getattr(self._cdll, name)
+        if not name.startswith("wj_") or name in ("wj_last_error", "wj_version", "wj_check_device", "wj_kernel_launches"):
+            setattr(self, name, fn)
+            return fn
+
+        def call(*args):
+            if _profile is None:
+                return fn(*args)
+            import torch
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+            rc = fn(*args)
+            e1.record()
+            _profile.records.append((name, e0, e1, _profile.meta))
+            _profile.meta = None
+            return rc
+
+        setattr(self, name, call)
+        return call
+
+
+def kernel_launches() -> int:
+    """Kernels launched by libwavjepa_b200.so in this process so far."""
+    return int(load().wj_kernel_launches())
+
+
+def load(build_if_missing: bool = False) -> "_Proxy":
     """Loads the shared library (once).  Raises loudly when it does not exist."""
     global _lib
     if _lib is not None:
@@ -68,10 +134,11 @@ def load(build_if_missing: bool = False) -> C.CDLL:
                 f"{LIB_PATH} not found: build it with `python -m wavjepa_b200.build` "
                 "(wavjepa_b200 has no CPU / PyTorch fallback)"
             )
-    lib = C.CDLL(LIB_PATH)
-    lib.wj_last_error.restype = C.c_char_p
-    _lib = lib
-    return lib
+    cdll = C.CDLL(LIB_PATH)
+    cdll.wj_last_error.restype = C.c_char_p
+    cdll.wj_kernel_launches.restype = C.c_longlong
+    _lib = _Proxy(cdll)
+    return _lib
 
 
 def check(rc: int) -> None:

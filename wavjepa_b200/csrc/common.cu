@@ -3,8 +3,11 @@
 #include <stdarg.h>
 #include <stdio.h>
 
+#include <atomic>
+
 namespace wj {
 static thread_local char g_err[1024] = "";
+static std::atomic<long long> g_launches{0};
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -13,7 +16,8 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
-int check_launch(const char* what) {
+int check_launch(const char* what, int n_kernels) {
+  g_launches.fetch_add(n_kernels, std::memory_order_relaxed);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     set_error("%s: %s", what, cudaGetErrorString(e));
@@ -35,6 +39,7 @@ int sm_count() {
 
 extern "C" const char* wj_last_error(void) { return wj::g_err; }
 extern "C" int wj_version(void) { return 1; }
+extern "C" long long wj_kernel_launches(void) { return wj::g_launches.load(std::memory_order_relaxed); }
 extern "C" int wj_check_device(void) {
   int dev = 0;
   cudaDeviceProp prop;

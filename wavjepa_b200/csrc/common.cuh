@@ -5,7 +5,7 @@
 
 namespace wj {
 void set_error(const char* fmt, ...);
-int check_launch(const char* what);
+int check_launch(const char* what, int n_kernels = 1);
 int sm_count();
 }  // namespace wj
 

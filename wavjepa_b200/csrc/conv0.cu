@@ -259,7 +259,7 @@ extern "C" int wj_conv0_gn_gelu_fwd(const void* x_bf16, const float* w, const fl
     conv0_stats_kernel<2><<<grid, C / 2, 0, st>>>(a, cpb);
     conv0_fwd_kernel<2><<<grid, C / 2, 0, st>>>(a, gamma, beta, eps, reinterpret_cast<bf16*>(out_bf16), cpb);
   }
-  return check_launch("conv0_gn_gelu_fwd");
+  return check_launch("conv0_gn_gelu_fwd", 2);
 }
 
 extern "C" int wj_conv0_gn_gelu_bwd(const void* x_bf16, const float* w, const float* gamma, const float* beta, int B,
@@ -288,5 +288,5 @@ extern "C" int wj_conv0_gn_gelu_bwd(const void* x_bf16, const float* w, const fl
     conv0_bwd_red_kernel<2><<<grid1, C / 2, 0, st>>>(a, gamma, beta, eps, dy, red_scratch, cpb1);
     conv0_bwd_w_kernel<2><<<grid2, C / 2, 0, st>>>(a, gamma, beta, eps, dy, red_scratch, dw, dgamma, dbeta, cpb2);
   }
-  return check_launch("conv0_gn_gelu_bwd");
+  return check_launch("conv0_gn_gelu_bwd", 2);
 }

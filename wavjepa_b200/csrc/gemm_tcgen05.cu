@@ -495,9 +495,7 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmPara
     attr_set = true;
   }
   kern<<<grid, kThreads, Cfg<BN>::SMEM_BYTES, st>>>(tmA, tmB, p);
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) { set_error("gemm launch: %s", cudaGetErrorString(e)); return WJ_ERR_RUNTIME; }
-  return WJ_OK;
+  return check_launch("gemm_tcgen05 launch");
 }
 
 static void fill_seg(SegInfo& s, const wj_operand_t* op) {

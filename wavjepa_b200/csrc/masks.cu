@@ -412,5 +412,5 @@ extern "C" int wj_mask_indices(const uint8_t* ctx_hidden, const uint8_t* tgt, co
   mask_scan_kernel<<<1, 1024, 0, st>>>(n_c, n_v, n_t, B, B * G, cu_c, cu_v, cu_t, totals);
   mask_fill_kernel<<<(B + 3) / 4, 128, 4 * T * sizeof(int), st>>>(ctx_hidden, tgt, vis_hidden, B, G, T, cu_c, cu_v, cu_t,
                                                                   ctx_rows, vis_src, vis_pos, tgt_vrow, tgt_trow);
-  return check_launch("mask_indices");
+  return check_launch("mask_indices", 3);
 }

@@ -337,5 +337,5 @@ extern "C" int wj_target_accum(const float* x, const float* rowsum, int B, int T
   const long long cap = static_cast<long long>(sm_count()) * 16;
   if (blocks > cap) blocks = cap;
   target_accum_kernel<<<static_cast<int>(blocks), 256, 0, st>>>(x, inst_stats, n4, T * D / 4, scale, first, targets);
-  return check_launch("target_accum");
+  return check_launch("target_accum", 2);
 }

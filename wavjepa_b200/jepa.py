@@ -691,6 +691,7 @@ class JEPA(nn.Module):
         self._ensure_ready()
         self._sync_weights()
         mi = ops.mask_indices(ctx_masks, target_indices, ctx_and_target_masks)
+        self._last_mi = mi
         c = self._forward_impl(x16, mi, save=True)
         gflat = self._flat_g
         gflat.zero_()

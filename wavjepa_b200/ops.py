@@ -94,6 +94,8 @@ def gemm(a: Operand, w: torch.Tensor, L: int, batch: int, out: torch.Tensor, *, 
         assert out_rows.dtype == torch.int32
         e.out_rows = _ptr(out_rows)
     lib = _lib.load()
+    if _lib._profile is not None:
+        _lib._profile.meta = 2.0 * L * batch * N * K
     check(lib.wj_gemm_bf16(C.byref(a), C.c_void_p(_ptr(w)), C.c_int64(w.stride(0)), L, batch, N, K, C.byref(e),
                            block_n, _stream()))
 
@@ -107,6 +109,8 @@ def gemm_wgrad(dy: Operand, x: Operand, L: int, batch: int, out: torch.Tensor, *
     N = out.shape[1] if N is None else N
     ld = out.stride(0) if ld_out is None else ld_out
     lib = _lib.load()
+    if _lib._profile is not None:
+        _lib._profile.meta = 2.0 * L * batch * M * N
     check(lib.wj_gemm_wgrad_bf16(C.byref(dy), C.byref(x), L, batch, M, N, C.c_void_p(_ptr(out) + out_offset * 4),
                                  C.c_int64(ld), 1 if accumulate else 0, splits, _stream()))
 
@@ -139,6 +143,8 @@ def gemm_dgrad(a: Operand, w: torch.Tensor, L: int, batch: int, out: torch.Tenso
     seg = (C.c_int32 * 4)(*([int(v) for v in seg_col_off] + [0] * (4 - len(seg_col_off))))
     w_cols = (w.shape[1] - w_col_offset) if w_cols is None else w_cols
     lib = _lib.load()
+    if _lib._profile is not None:
+        _lib._profile.meta = 2.0 * L * batch * N * K
     check(lib.wj_gemm_dgrad_bf16(C.byref(a), C.c_void_p(_ptr(w) + w_col_offset * 2), C.c_int64(w.stride(0)),
                                  w.shape[0], w_cols, seg, L, batch, N, K, C.byref(e), block_n, _stream()))
 
