@@ -248,7 +248,7 @@ def run_native(args):
         gemm_names = ("wj_gemm_bf16", "wj_gemm_dgrad_bf16", "wj_gemm_wgrad_bf16")
         g_calls = sum(summ[n][0] for n in gemm_names if n in summ)
         g_ms = sum(summ[n][1] for n in gemm_names if n in summ)
-        g_flops = sum(m for (n, _, _, m) in kp.records if n in gemm_names and m)
+        g_flops = sum(m[0] for (n, _, _, m) in kp.records if n in gemm_names and m)
         fam_ms = {n[3:]: round(t, 3) for n, (c, t) in sorted(summ.items(), key=lambda kv: -kv[1][1])}
         fam_calls = {n[3:]: c for n, (c, t) in summ.items()}
         prof_total = sum(t for (_, t) in summ.values())

@@ -51,11 +51,12 @@ typedef struct wj_operand {
 
 /* Fused epilogue of wj_gemm_bf16, applied in this order:
  *   v = acc + bias[n]
- *   act == 1 : h = bf16(v); out2[row, n] = h (if out2); v = GELU_erf(h)          (nn.GELU, types/wavjepa_configs.py:37)
- *   act == 2 : v = v * GELU_erf'(aux[row, n])                                    (backward of the above)
+ *   act == 1 : h = bf16(v); out2[row, n] = bf16(GELU_erf'(h)) (if out2); v = GELU_erf(h)   (nn.GELU, types/wavjepa_configs.py:37)
+ *   act == 2 : v = v * aux[row, n]            (backward of the above: aux = the GELU' saved in out2 by the forward)
  *   act == 3 : v = bf16(v)                         (autocast: the Linear output is bf16 before the fp32 residual add)
  *   v += resid[row % resid_mod or row, n]                                        (residual / positional table)
  *   out[row, n] = v  (bf16, or fp32 when out_f32; fp32 reduce-add when accumulate)
+ *   colsum[n] += sum_rows out[row, n]  (optional, fp32 atomics: the bias gradient of the layer that produced `out`)
  * out_rows (optional, int32 per logical row): physical row used for out/out2/resid/aux, <0 skips the row.
  */
 typedef struct wj_epilogue {
@@ -75,6 +76,7 @@ typedef struct wj_epilogue {
   int32_t act;
   int32_t _pad;
   const int32_t* out_rows;
+  float* colsum;
 } wj_epilogue_t;
 
 /* out[b*L + t, n] = epilogue( sum_vc A(vc; t, b) * W[n, vc] ),  W bf16 [N, K] row-major with leading dim ldw.
@@ -178,8 +180,8 @@ int wj_gather_rows(const void* src, int src_is_bf16, const int* idx, int N, int 
 /* out[idx[i], :] = src[i, :] (fp32): packed encoder rows back to their dense [B*T, D] positions
  * (JEPA.get_audio_representation, wavjepa/jepa.py:456-467). */
 int wj_scatter_rows(const float* src, const int* idx, int N, int D, float* out, void* stream);
-/* out_bf16[idx[i], :] = src[i, :] * GELU'(h[idx[i], :]) (h may be NULL, idx NULL = identity); rows not listed are
- * left untouched. */
+/* out_bf16[idx[i], :] = src[i, :] * h[idx[i], :] (h = the GELU' factors saved by an act == 1 GEMM epilogue; may be
+ * NULL; idx NULL = identity); rows not listed are left untouched. */
 int wj_scatter_dgelu(const float* src, const int* idx, const void* h_bf16, int N, int D, void* out_bf16, void* stream);
 
 /* Predictor input: x0[r] = (vis_src[r] >= 0 ? ctx[vis_src[r]] : bf16(mask_token)) + pos[vis_pos[r]]

@@ -43,6 +43,7 @@ class Epilogue(C.Structure):
         ("act", C.c_int32),
         ("_pad", C.c_int32),
         ("out_rows", C.c_void_p),
+        ("colsum", C.c_void_p),
     ]
 
 

@@ -42,7 +42,8 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const void* __restrict
   }
 }
 
-// out_bf16[idx[r], :] = src_f32[r, :] * gelu'(h[idx[r], :])   (rows not listed stay as the caller zeroed them)
+// out_bf16[idx[r], :] = src_f32[r, :] * h[idx[r], :]   (h = GELU' saved by the forward epilogue; rows not listed stay as
+// the caller zeroed them)
 __global__ void __launch_bounds__(256) scatter_dgelu_kernel(const float* __restrict__ src, const int* __restrict__ idx,
                                                             const bf16* __restrict__ h, long long n4, int D4,
                                                             bf16* __restrict__ out) {
@@ -54,7 +55,7 @@ __global__ void __launch_bounds__(256) scatter_dgelu_kernel(const float* __restr
     float4 v = reinterpret_cast<const float4*>(src)[i];
     if (h != nullptr) {
       const float4 hv = load4(h, true, o);
-      v.x *= gelu_erf_grad(hv.x); v.y *= gelu_erf_grad(hv.y); v.z *= gelu_erf_grad(hv.z); v.w *= gelu_erf_grad(hv.w);
+      v.x *= hv.x; v.y *= hv.y; v.z *= hv.z; v.w *= hv.w;
     }
     store4(nullptr, out, o, v);
   }

@@ -7,12 +7,12 @@
 //                                           (reference: nn.Conv1d, wavjepa/extractors/audio_feature_extractor.py:70)
 //   * weight gradients (WGRAD mode: both operands MN-major, split over the token dimension, fp32 reduce-add)
 //
-// Layout of a CTA (384 threads, 1 CTA / SM, grid = min(#tiles, #SMs), static round-robin tile schedule):
+// Layout of a CTA (640 threads, 1 CTA / SM, grid = min(#tiles, #SMs), static round-robin tile schedule):
 //   warp 0      : TMA producer (one elected lane)   global -> 128B-swizzled smem ring (STAGES deep)
 //   warp 1      : MMA issuer   (one elected lane)   tcgen05.mma.cta_group::1.kind::f16, D in TMEM (2 accumulators)
 //   warp 2      : TMEM allocator / deallocator
 //   warp 3      : idle
-//   warps 4..11 : epilogue: tcgen05.ld -> registers -> fused bias / GELU / GELU' / residual -> global
+//   warps 4..19 : epilogue: tcgen05.ld -> registers -> fused bias / GELU / GELU' / residual -> global
 //
 // Operand addressing is "virtual column" based so that the same kernel covers implicit-GEMM convolutions: the
 // reduction (normal mode) or output-column (WGRAD mode) index vc is split into segments of `seg.width` columns;
@@ -58,17 +58,20 @@ struct GemmParams {
   int resid_f32;
   long long ld_resid;
   int resid_mod;     // residual row = row % resid_mod when > 0 (positional table broadcast)
-  const bf16* aux;   // pre-activation for act == 2
+  const bf16* aux;   // GELU'(pre-activation) saved by an act == 1 forward, for act == 2
   long long ld_aux;
-  int act;           // 0 none; 1: h = bf16(acc + bias), out2 = h, v = gelu(h); 2: v = acc * gelu'(aux); 3: v = bf16(v)
+  int act;           // 0 none; 1: h = bf16(acc + bias), out2 = gelu'(h), v = gelu(h); 2: v = acc * aux; 3: v = bf16(v)
   const int* out_rows;  // optional row indirection for the output / residual / aux rows (scatter), -1 = skip
+  float* colsum;        // optional: colsum[n] += sum over rows of the stored output (bias gradients)
 };
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int kThreads = 384;
+constexpr int kThreads = 640;
 constexpr int kEpiWarp0 = 4;
-constexpr int kEpiWarps = 8;
+constexpr int kEpiWarps = 16;
+constexpr int kEpiRegs = 104;     // setmaxnreg targets: launch allocation is <= 96 / thread (640 threads)
+constexpr int kCtrlRegs = 40;
 
 template <int BN>
 struct Cfg {
@@ -149,6 +152,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
   };
 
+  if (warp < kEpiWarp0) reg_dealloc<kCtrlRegs>();
   if (warp == 0) {
     // ======================================================================================= TMA producer
     if (lane == 0) {
@@ -252,11 +256,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
     }
   } else if (warp >= kEpiWarp0) {
-    // ======================================================================================= epilogue
+    // ======================================================================================= epilogue (16 warps)
+    // Shared-memory bandwidth belongs to the MMA (a 128x256x16 UMMA reads 12 KB of operands per 128 cycles = 96 of the
+    // 128 B/cycle), so the epilogue never touches smem: tcgen05.ld.16x256b hands every quad of lanes 8 consecutive
+    // columns of a row (2 per lane), a 4x4 quad transpose through warp shuffles gives each lane 8 CONSECUTIVE columns
+    // (32 B fp32 / 16 B bf16) of rows g and g+8, and all global traffic (bias, residual, saved GELU', outputs) is
+    // 16-byte vectors with 64-128 contiguous bytes per row per instruction.  Work unit = 16 TMEM lanes x 32 columns;
+    // the next unit's TMEM load is in flight during the math of the current one.  16 warps (4 per scheduler) hide the
+    // shuffle / global-load latencies; registers come from the producer/MMA warpgroup via setmaxnreg.
+    reg_alloc<kEpiRegs>();
     const int ew = warp - kEpiWarp0;
     const int lane_grp = warp & 3;            // TMEM lanes [32*lane_grp, +32) are accessible to this warp
-    const int col_half = ew >> 2;             // which half of the BN columns this warp handles
-    constexpr int CHUNKS = BN / 32 / 2;       // 32-column chunks per warp
+    const int col_q = ew >> 2;                // which quarter of the BN columns this warp handles
+    constexpr int CHUNKS = BN / 32 / 4;       // 32-column chunks per warp
+    constexpr int UNITS = CHUNKS * 2;
+    const int g = lane >> 2, tg = lane & 3;
     int it = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
@@ -277,144 +291,157 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-
-      const int r_local = lane_grp * 32 + lane;
-      long long row;     // logical output row
-      bool row_ok;
-      if constexpr (!WGRAD) {
-        const int rib = row_in_batch0 + r_local;
-        row_ok = rib < p.L;
-        row = static_cast<long long>(b) * p.L + rib;
-      } else {
-        row = static_cast<long long>(m_blk) * BM + r_local;
-        row_ok = row < p.M;
-      }
-      long long orow = row;
-      if (p.out_rows != nullptr && row_ok) {
-        const int r = p.out_rows[row];
-        row_ok = r >= 0;
-        orow = r;
-      }
-
+      const uint32_t t_base = tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16) + acc * BN + col_q * (CHUNKS * 32);
+      uint32_t v[16];
+      tmem_ld_16x256b_x4(t_base, v);
 #pragma unroll 1
-      for (int ch = 0; ch < CHUNKS; ++ch) {
-        const int col_local = (col_half * CHUNKS + ch) * 32;
-        const int n0 = n_blk * BN + col_local;
-        uint32_t v[32];
-        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16) + acc * BN + col_local, v);
+      for (int u = 0; u < UNITS; ++u) {
+        const int ch = u >> 1, half = u & 1;
         tmem_ld_wait();
-        if (row_ok && n0 < p.N && have_k) {
-        float f[32];
+        // v[4*j + 2*hr + {0,1}] = (row g + 8*hr + 16*half, columns 8*j + 2*tg + {0,1}) of this warp's 32 x 32 chunk
+        float f[2][8];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-        // columns valid in this chunk (N is a multiple of 8)
-        const int ncols = min(32, p.N - n0);
-        if (p.bias != nullptr) {
+        for (int hr = 0; hr < 2; ++hr) {
+          uint32_t a[8];
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            if (j < ncols) {
-              const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
-              f[j] += bb.x; f[j + 1] += bb.y; f[j + 2] += bb.z; f[j + 3] += bb.w;
-            }
-          }
+          for (int j = 0; j < 4; ++j) { a[2 * j] = v[4 * j + 2 * hr]; a[2 * j + 1] = v[4 * j + 2 * hr + 1]; }
+          quad_transpose(a, tg);   // -> a[0..7] = columns 8*tg .. 8*tg+7 of that row
+#pragma unroll
+          for (int c = 0; c < 8; ++c) f[hr][c] = __uint_as_float(a[c]);
         }
-        if (p.act == 3) {
-          // linear output is bf16 under autocast before it meets the fp32 residual / positional table
+        if (u + 1 < UNITS) {
+          const int nu = u + 1;
+          tmem_ld_16x256b_x4(t_base + (static_cast<uint32_t>((nu & 1) * 16) << 16) + (nu >> 1) * 32, v);
+        } else {
+          // every lane has executed tcgen05.wait::ld for its last unit -> hand the accumulator back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        }
+
+        const int n0 = n_blk * BN + (col_q * CHUNKS + ch) * 32 + tg * 8;
+        const bool col_ok = n0 < p.N;   // N is a multiple of 8: groups of 8 columns are all-or-nothing
+        float bias8[8];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = bf16_round(f[j]);
-        } else if (p.act == 1) {
-          // reference autocast semantics: linear/conv output is bf16, GELU evaluated on that bf16 value
+        for (int c = 0; c < 8; ++c) bias8[c] = 0.f;
+        if (p.bias != nullptr && col_ok) {
+          const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n0));
+          const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + 4));
+          bias8[0] = b0.x; bias8[1] = b0.y; bias8[2] = b0.z; bias8[3] = b0.w;
+          bias8[4] = b1.x; bias8[5] = b1.y; bias8[6] = b1.z; bias8[7] = b1.w;
+        }
+        float cs[8];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = bf16_round(f[j]);
-          if (p.out2 != nullptr) {
-            bf16* o2 = p.out2 + orow * p.ld_out2 + n0;
+        for (int c = 0; c < 8; ++c) cs[c] = 0.f;
 #pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              if (j < ncols) {
-                uint4 w;
-                w.x = pack_bf16x2(f[j], f[j + 1]); w.y = pack_bf16x2(f[j + 2], f[j + 3]);
-                w.z = pack_bf16x2(f[j + 4], f[j + 5]); w.w = pack_bf16x2(f[j + 6], f[j + 7]);
-                *reinterpret_cast<uint4*>(o2 + j) = w;
-              }
+        for (int hr = 0; hr < 2; ++hr) {
+          // physical output row of tile row (lane_grp*32 + 16*half + 8*hr + g); -1 = nothing to write
+          long long orow;
+          {
+            const int r_local = lane_grp * 32 + half * 16 + hr * 8 + g;
+            bool ok;
+            if constexpr (!WGRAD) {
+              const int rib = row_in_batch0 + r_local;
+              ok = rib < p.L;
+              orow = static_cast<long long>(b) * p.L + rib;
+            } else {
+              orow = static_cast<long long>(m_blk) * BM + r_local;
+              ok = orow < p.M && have_k;
+            }
+            if (ok && p.out_rows != nullptr) orow = p.out_rows[orow];
+            if (!ok) orow = -1;
+          }
+          if (orow < 0 || !col_ok) continue;
+          float* x = f[hr];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) x[c] += bias8[c];
+          if (p.act == 3) {
+            // the Linear output is bf16 under autocast before it meets the fp32 residual / positional table
+#pragma unroll
+            for (int c = 0; c < 8; ++c) x[c] = bf16_round(x[c]);
+          } else if (p.act == 1) {
+            // autocast semantics: the linear/conv output is bf16 and GELU is evaluated on that bf16 value; out2
+            // receives GELU'(h) (bf16), which is all the backward needs of the pre-activation
+#pragma unroll
+            for (int c = 0; c < 8; ++c) x[c] = bf16_round(x[c]);
+            if (p.out2 != nullptr) {
+              float d[8];
+#pragma unroll
+              for (int c = 0; c < 8; ++c) gelu_fast2(x[c], x[c], d[c]);
+              uint4 w;
+              w.x = pack_bf16x2(d[0], d[1]); w.y = pack_bf16x2(d[2], d[3]);
+              w.z = pack_bf16x2(d[4], d[5]); w.w = pack_bf16x2(d[6], d[7]);
+              *reinterpret_cast<uint4*>(p.out2 + orow * p.ld_out2 + n0) = w;
+            } else {
+#pragma unroll
+              for (int c = 0; c < 8; ++c) x[c] = gelu_fast(x[c]);
+            }
+          } else if (p.act == 2) {
+            const uint4 w = *reinterpret_cast<const uint4*>(p.aux + orow * p.ld_aux + n0);
+            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&w);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const float2 hh = __bfloat1622float2(h2[t]);
+              x[2 * t] *= hh.x; x[2 * t + 1] *= hh.y;
             }
           }
-#pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
-        } else if (p.act == 2) {
-          const bf16* ax = p.aux + orow * p.ld_aux + n0;
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            if (j < ncols) {
-              const uint4 w = *reinterpret_cast<const uint4*>(ax + j);
+          if (p.resid != nullptr) {
+            const long long rrow = p.resid_mod > 0 ? (orow % p.resid_mod) : orow;
+            if (p.resid_f32) {
+              const float* rp = reinterpret_cast<const float*>(p.resid) + rrow * p.ld_resid + n0;
+              const float4 r0 = *reinterpret_cast<const float4*>(rp);
+              const float4 r1 = *reinterpret_cast<const float4*>(rp + 4);
+              x[0] += r0.x; x[1] += r0.y; x[2] += r0.z; x[3] += r0.w;
+              x[4] += r1.x; x[5] += r1.y; x[6] += r1.z; x[7] += r1.w;
+            } else {
+              const uint4 w = *reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p.resid) + rrow * p.ld_resid + n0);
               const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&w);
 #pragma unroll
               for (int t = 0; t < 4; ++t) {
                 const float2 hh = __bfloat1622float2(h2[t]);
-                f[j + 2 * t] *= gelu_erf_grad(hh.x);
-                f[j + 2 * t + 1] *= gelu_erf_grad(hh.y);
+                x[2 * t] += hh.x; x[2 * t + 1] += hh.y;
               }
             }
           }
-        }
-        if (p.resid != nullptr) {
-          const long long rrow = p.resid_mod > 0 ? (orow % p.resid_mod) : orow;
-          if (p.resid_f32) {
-            const float* rp = reinterpret_cast<const float*>(p.resid) + rrow * p.ld_resid + n0;
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              if (j < ncols) {
-                const float4 rr = *reinterpret_cast<const float4*>(rp + j);
-                f[j] += rr.x; f[j + 1] += rr.y; f[j + 2] += rr.z; f[j + 3] += rr.w;
-              }
+          if (p.out_f32) {
+            float* op = reinterpret_cast<float*>(p.out) + orow * p.ld_out + n0;
+            if (p.accumulate) {
+              red_add_v4(op, x[0], x[1], x[2], x[3]);
+              red_add_v4(op + 4, x[4], x[5], x[6], x[7]);
+            } else {
+              *reinterpret_cast<float4*>(op) = make_float4(x[0], x[1], x[2], x[3]);
+              *reinterpret_cast<float4*>(op + 4) = make_float4(x[4], x[5], x[6], x[7]);
             }
           } else {
-            const bf16* rp = reinterpret_cast<const bf16*>(p.resid) + rrow * p.ld_resid + n0;
+            uint4 w;
+            w.x = pack_bf16x2(x[0], x[1]); w.y = pack_bf16x2(x[2], x[3]);
+            w.z = pack_bf16x2(x[4], x[5]); w.w = pack_bf16x2(x[6], x[7]);
+            *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + orow * p.ld_out + n0) = w;
+            if (p.colsum != nullptr) {   // sums of the values as stored (bf16), like autograd's bias gradient
+              const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&w);
 #pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              if (j < ncols) {
-                const uint4 w = *reinterpret_cast<const uint4*>(rp + j);
-                const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&w);
-#pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                  const float2 hh = __bfloat1622float2(h2[t]);
-                  f[j + 2 * t] += hh.x;
-                  f[j + 2 * t + 1] += hh.y;
-                }
+              for (int t = 0; t < 4; ++t) {
+                const float2 hh = __bfloat1622float2(h2[t]);
+                x[2 * t] = hh.x; x[2 * t + 1] = hh.y;
               }
             }
           }
+#pragma unroll
+          for (int c = 0; c < 8; ++c) cs[c] += x[c];
         }
-        if (p.out_f32) {
-          float* op = reinterpret_cast<float*>(p.out) + orow * p.ld_out + n0;
-          if (p.accumulate) {
+        if (p.colsum != nullptr) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              if (j < ncols) red_add_v4(op + j, f[j], f[j + 1], f[j + 2], f[j + 3]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              if (j < ncols) *reinterpret_cast<float4*>(op + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-            }
+          for (int c = 0; c < 8; ++c) {
+            cs[c] += __shfl_xor_sync(0xffffffffu, cs[c], 4);
+            cs[c] += __shfl_xor_sync(0xffffffffu, cs[c], 8);
+            cs[c] += __shfl_xor_sync(0xffffffffu, cs[c], 16);
           }
-        } else {
-          bf16* op = reinterpret_cast<bf16*>(p.out) + orow * p.ld_out + n0;
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            if (j < ncols) {
-              uint4 w;
-              w.x = pack_bf16x2(f[j], f[j + 1]); w.y = pack_bf16x2(f[j + 2], f[j + 3]);
-              w.z = pack_bf16x2(f[j + 4], f[j + 5]); w.w = pack_bf16x2(f[j + 6], f[j + 7]);
-              *reinterpret_cast<uint4*>(op + j) = w;
-            }
+          if (g == 0 && col_ok) {
+            red_add_v4(p.colsum + n0, cs[0], cs[1], cs[2], cs[3]);
+            red_add_v4(p.colsum + n0 + 4, cs[4], cs[5], cs[6], cs[7]);
           }
         }
-        }  // row_ok
-        __syncwarp();
       }
-      // all TMEM reads of this accumulator are complete (tcgen05.wait::ld above) -> hand it back to the MMA warp
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
     }
   }
 
@@ -508,7 +535,7 @@ static void fill_epilogue(GemmParams& p, const wj_epilogue_t* e) {
   p.out2 = reinterpret_cast<bf16*>(e->out2); p.ld_out2 = e->ld_out2;
   p.bias = e->bias; p.resid = e->resid; p.resid_f32 = e->resid_f32; p.ld_resid = e->ld_resid;
   p.resid_mod = e->resid_mod; p.aux = reinterpret_cast<const bf16*>(e->aux); p.ld_aux = e->ld_aux;
-  p.act = e->act; p.out_rows = e->out_rows;
+  p.act = e->act; p.out_rows = e->out_rows; p.colsum = e->colsum;
 }
 
 }  // namespace wj

@@ -127,6 +127,31 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32])
       : "r"(taddr)
       : "memory");
 }
+// 16 TMEM lanes x 32 fp32 columns -> 16 registers per thread, mma-accumulator-like distribution: with g = lane / 4 and
+// tg = lane % 4, v[4*j + 2*hr + e] = (TMEM lane base + g + 8*hr, column 8*j + 2*tg + e), j = 0..3, hr, e = 0..1.
+__device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+// 4x4 transpose of 64-bit items across a quad of lanes (tg = lane % 4): in: a[2j], a[2j+1] = item j of this lane;
+// out: a[2j], a[2j+1] = item tg of lane j.  Two xor-shuffle rounds, 8 SHFL.
+__device__ __forceinline__ void quad_exchange(uint32_t& lo0, uint32_t& lo1, uint32_t& hi0, uint32_t& hi1, bool has_bit,
+                                              int bit) {
+  const uint32_t x0 = has_bit ? lo0 : hi0, x1 = has_bit ? lo1 : hi1;
+  const uint32_t y0 = __shfl_xor_sync(0xffffffffu, x0, bit), y1 = __shfl_xor_sync(0xffffffffu, x1, bit);
+  if (has_bit) { lo0 = y0; lo1 = y1; } else { hi0 = y0; hi1 = y1; }
+}
+__device__ __forceinline__ void quad_transpose(uint32_t (&a)[8], int tg) {
+  quad_exchange(a[0], a[1], a[2], a[3], (tg & 1) != 0, 1);
+  quad_exchange(a[4], a[5], a[6], a[7], (tg & 1) != 0, 1);
+  quad_exchange(a[0], a[1], a[4], a[5], (tg & 2) != 0, 2);
+  quad_exchange(a[2], a[3], a[6], a[7], (tg & 2) != 0, 2);
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // UMMA shared-memory matrix descriptor (PTX ISA "tcgen05 shared memory descriptor"):
@@ -149,12 +174,60 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, bool a_mn_m
          (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
 }
 
+// Warpgroup register re-allocation (executed by all 4 warps of an aligned warpgroup).
+template <int N>
+__device__ __forceinline__ void reg_alloc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N>
+__device__ __forceinline__ void reg_dealloc() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+
 // ----------------------------------------------------------------------------------------------- misc math
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 __device__ __forceinline__ float gelu_erf_grad(float x) {
   const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
   const float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
   return cdf + x * pdf;
+}
+// Exact-erf GELU at fp32 accuracy without erff(): erfc(|x|/sqrt2) = poly(t) * exp(-x^2/2), t = 1/(1 + p|x|/sqrt2)
+// (Abramowitz & Stegun 7.1.26, |error| <= 1.5e-7), so
+//   gelu(x)  = max(x, 0) - 0.5 |x| erfc(|x|/sqrt2)            (no cancellation in the negative tail)
+//   gelu'(x) = Phi(x) + x phi(x),  Phi = x > 0 ? 1 - 0.5 erfc : 0.5 erfc,  phi = exp(-x^2/2) / sqrt(2 pi)
+// ~12 FMA-pipe + 2 MUFU instructions per value (|error| < 4e-7 for both on [-8, 8], checked against scipy).
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void gelu_terms(float x, float& ax, float& e, float& pe) {
+  ax = fabsf(x);
+  const float t = rcp_approx(fmaf(0.3275911f * 0.70710678f, ax, 1.0f));
+  float q = fmaf(t, 1.061405429f, -1.453152027f);
+  q = fmaf(t, q, 1.421413741f);
+  q = fmaf(t, q, -0.284496736f);
+  q = fmaf(t, q, 0.254829592f);
+  e = ex2_approx(-0.72134752f * x * x);
+  pe = q * t * e;
+}
+__device__ __forceinline__ float gelu_fast(float x) {
+  float ax, e, pe;
+  gelu_terms(x, ax, e, pe);
+  return fmaf(-0.5f * ax, pe, fmaxf(x, 0.0f));
+}
+__device__ __forceinline__ void gelu_fast2(float x, float& g, float& dg) {
+  float ax, e, pe;
+  gelu_terms(x, ax, e, pe);
+  const float hp = 0.5f * pe;
+  g = fmaf(-ax, hp, fmaxf(x, 0.0f));
+  dg = fmaf(x * 0.39894228f, e, x > 0.0f ? 1.0f - hp : hp);
+}
+__device__ __forceinline__ float gelu_fast_grad(float x) {
+  float g, dg;
+  gelu_fast2(x, g, dg);
+  return dg;
 }
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);

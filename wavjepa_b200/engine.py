@@ -106,8 +106,8 @@ class TransformerStack:
             ops.layernorm_bwd(dx, s.y2, s.st2, w.g2, dy2, dy2_16, gw.g2, gw.be2, gw.b2)
             ops.gemm_wgrad(ops.plain_operand(dy2_16), ops.plain_operand(s.g), M, 1, gw.w2, accumulate=True)
             dh = _empty((M, ff), bf, dev)
-            ops.gemm_dgrad(ops.plain_operand(dy2_16), w.w2, M, 1, dh, K=d, N=ff, act=ops.ACT_DGELU, aux=s.h)
-            ops.colsum(dh, gw.b1)
+            ops.gemm_dgrad(ops.plain_operand(dy2_16), w.w2, M, 1, dh, K=d, N=ff, act=ops.ACT_DGELU, aux=s.h,
+                           colsum=gw.b1)
             ops.gemm_wgrad(ops.plain_operand(dh), ops.plain_operand(s.x1_16), M, 1, gw.w1, accumulate=True)
             dx1 = _empty((M, d), f32, dev)
             ops.gemm_dgrad(ops.plain_operand(dh), w.w1, M, 1, dx1, K=ff, N=d, resid=dy2)

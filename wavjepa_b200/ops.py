@@ -61,7 +61,8 @@ def gemm(a: Operand, w: torch.Tensor, L: int, batch: int, out: torch.Tensor, *, 
          ld_out2: Optional[int] = None, out2_offset: int = 0,
          resid: Optional[torch.Tensor] = None, ld_resid: Optional[int] = None, resid_mod: int = 0,
          resid_offset: int = 0, aux: Optional[torch.Tensor] = None, ld_aux: Optional[int] = None, aux_offset: int = 0,
-         accumulate: bool = False, out_rows: Optional[torch.Tensor] = None, block_n: int = 0) -> None:
+         accumulate: bool = False, out_rows: Optional[torch.Tensor] = None, block_n: int = 0,
+         colsum: Optional[torch.Tensor] = None) -> None:
     """out[b*L+t, :] = epilogue(A(t,b) @ w.T); w is bf16 [N, K] (row-major)."""
     assert w.dtype == torch.bfloat16 and w.stride(-1) == 1
     N = w.shape[0] if N is None else N
@@ -93,9 +94,12 @@ def gemm(a: Operand, w: torch.Tensor, L: int, batch: int, out: torch.Tensor, *, 
     if out_rows is not None:
         assert out_rows.dtype == torch.int32
         e.out_rows = _ptr(out_rows)
+    if colsum is not None:
+        assert colsum.dtype == torch.float32
+        e.colsum = _ptr(colsum)
     lib = _lib.load()
     if _lib._profile is not None:
-        _lib._profile.meta = 2.0 * L * batch * N * K
+        _lib._profile.meta = (2.0 * L * batch * N * K, L * batch, N, K, e.act, int(e.out_f32))
     check(lib.wj_gemm_bf16(C.byref(a), C.c_void_p(_ptr(w)), C.c_int64(w.stride(0)), L, batch, N, K, C.byref(e),
                            block_n, _stream()))
 
@@ -110,7 +114,7 @@ def gemm_wgrad(dy: Operand, x: Operand, L: int, batch: int, out: torch.Tensor, *
     ld = out.stride(0) if ld_out is None else ld_out
     lib = _lib.load()
     if _lib._profile is not None:
-        _lib._profile.meta = 2.0 * L * batch * M * N
+        _lib._profile.meta = (2.0 * L * batch * M * N, L * batch, M, N, 0, 1)
     check(lib.wj_gemm_wgrad_bf16(C.byref(dy), C.byref(x), L, batch, M, N, C.c_void_p(_ptr(out) + out_offset * 4),
                                  C.c_int64(ld), 1 if accumulate else 0, splits, _stream()))
 
@@ -120,7 +124,8 @@ def gemm_dgrad(a: Operand, w: torch.Tensor, L: int, batch: int, out: torch.Tenso
                ld_out: Optional[int] = None, out_offset: int = 0, act: int = ACT_NONE,
                aux: Optional[torch.Tensor] = None, ld_aux: Optional[int] = None, aux_offset: int = 0,
                resid: Optional[torch.Tensor] = None, ld_resid: Optional[int] = None, resid_offset: int = 0,
-               accumulate: bool = False, out_rows: Optional[torch.Tensor] = None, block_n: int = 0) -> None:
+               accumulate: bool = False, out_rows: Optional[torch.Tensor] = None, block_n: int = 0,
+               colsum: Optional[torch.Tensor] = None) -> None:
     """out[b*L+t, n] = epilogue(sum_r A(r; t, b) * w[r, w_col_offset + seg_col_off[s] + n]); w bf16 [R, cols] row-major."""
     assert w.dtype == torch.bfloat16 and w.dim() == 2 and w.stride(1) == 1
     e = Epilogue()
@@ -140,11 +145,14 @@ def gemm_dgrad(a: Operand, w: torch.Tensor, L: int, batch: int, out: torch.Tenso
     e.act = act
     if out_rows is not None:
         e.out_rows = _ptr(out_rows)
+    if colsum is not None:
+        assert colsum.dtype == torch.float32
+        e.colsum = _ptr(colsum)
     seg = (C.c_int32 * 4)(*([int(v) for v in seg_col_off] + [0] * (4 - len(seg_col_off))))
     w_cols = (w.shape[1] - w_col_offset) if w_cols is None else w_cols
     lib = _lib.load()
     if _lib._profile is not None:
-        _lib._profile.meta = 2.0 * L * batch * N * K
+        _lib._profile.meta = (2.0 * L * batch * N * K, L * batch, N, K, e.act, int(e.out_f32))
     check(lib.wj_gemm_dgrad_bf16(C.byref(a), C.c_void_p(_ptr(w) + w_col_offset * 2), C.c_int64(w.stride(0)),
                                  w.shape[0], w_cols, seg, L, batch, N, K, C.byref(e), block_n, _stream()))
 
@@ -164,8 +172,8 @@ def conv_dgrad(dy: torch.Tensor, wk: torch.Tensor, dx: torch.Tensor, k: int, *, 
                aux: Optional[torch.Tensor] = None) -> None:
     """Data gradient of the stride-2 Conv1d: dy [B, L_out, O] bf16, wk [O, k*C] bf16 (k-major), dx [B, L_in, C].
     Even input positions 2m receive taps j=0 (t=m) and j=2 (t=m-1); odd positions 2m+1 receive tap j=1 (t=m):
-    two GEMMs over (shifted) views of dy, written with row pitch 2C.  act/aux: optional x GELU'(aux) epilogue
-    (aux = pre-activation of the layer below, same layout as dx)."""
+    two GEMMs over (shifted) views of dy, written with row pitch 2C.  act/aux: optional x aux epilogue
+    (aux = GELU' of the layer below saved by its forward epilogue, same layout as dx)."""
     B, L_out, O = dy.shape
     _, L_in, C = dx.shape
     assert dy.is_contiguous() and dx.is_contiguous() and wk.shape == (O, k * C)
@@ -262,6 +270,8 @@ def layernorm_fwd(x: torch.Tensor, gamma, beta, eps: float, out_f32=None, out_bf
     assert x.is_contiguous()
     lib = _lib.load()
     p = lambda t: C.c_void_p(_ptr(t))
+    if _lib._profile is not None:
+        _lib._profile.meta = (0.0, M, D, str(x.dtype)[6:], out_f32 is not None, out_bf16 is not None)
     check(lib.wj_layernorm_fwd(p(x), 1 if x.dtype == torch.bfloat16 else 0, p(gamma), p(beta), C.c_float(eps), M, D,
                                p(out_f32), p(out_bf16), p(stats), p(rowsum), _stream()))
 
@@ -272,6 +282,8 @@ def layernorm_bwd(dy: torch.Tensor, x: torch.Tensor, stats, gamma, dx_f32=None, 
     assert dy.dtype == torch.float32 and dy.is_contiguous() and x.is_contiguous()
     lib = _lib.load()
     p = lambda t: C.c_void_p(_ptr(t))
+    if _lib._profile is not None:
+        _lib._profile.meta = (0.0, M, D, colsum is not None)
     check(lib.wj_layernorm_bwd(p(dy), p(x), 1 if x.dtype == torch.bfloat16 else 0, p(stats), p(gamma), M, D, p(dx_f32),
                                p(dx_bf16), p(dgamma), p(dbeta), p(colsum), _stream()))
 
@@ -316,12 +328,16 @@ def attn_fwd(qkv: torch.Tensor, cu: torch.Tensor, n_seqs: int, max_len: int, D: 
              lse2=None):
     lib = _lib.load()
     p = lambda t: C.c_void_p(_ptr(t))
+    if _lib._profile is not None:
+        _lib._profile.meta = (0.0, n_seqs, max_len, D, H, qkv.shape[0])
     check(lib.wj_attn_varlen_fwd(p(qkv), p(cu), n_seqs, max_len, D, H, p(out), p(lse2), _stream()))
 
 
 def attn_bwd(qkv, out, dout, lse2, cu, n_seqs: int, max_len: int, D: int, H: int, dqkv):
     lib = _lib.load()
     p = lambda t: C.c_void_p(_ptr(t))
+    if _lib._profile is not None:
+        _lib._profile.meta = (0.0, n_seqs, max_len, D, H, qkv.shape[0])
     check(lib.wj_attn_varlen_bwd(p(qkv), p(out), p(dout), p(lse2), p(cu), n_seqs, max_len, D, H, p(dqkv), _stream()))
 
 
@@ -391,6 +407,8 @@ def colsum(x: torch.Tensor, out: torch.Tensor, M: Optional[int] = None):
     M = x.shape[0] if M is None else M
     lib = _lib.load()
     p = lambda t: C.c_void_p(_ptr(t))
+    if _lib._profile is not None:
+        _lib._profile.meta = (0.0, M, x.shape[1], str(x.dtype)[6:])
     check(lib.wj_colsum(p(x), 1 if x.dtype == torch.bfloat16 else 0, C.c_int64(M), x.shape[1], C.c_int64(x.stride(0)),
                         p(out), _stream()))
 
