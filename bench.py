@@ -27,6 +27,10 @@ import sys
 import tempfile
 import time
 
+# activations of consecutive steps differ in size (mask-dependent token counts): let the caching allocator grow its
+# segments in place instead of cudaMalloc-ing new ones in the middle of a timed step
+os.environ.setdefault("PYTORCH_CUDA_ALLOC_CONF", "expandable_segments:True")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)

@@ -129,15 +129,19 @@ int wj_mask_indices(const uint8_t* ctx_hidden, const uint8_t* tgt, const uint8_t
 /* ------------------------------------------------------------------------------------------------------------------
  * Waveform encoder block 0: Conv1d(Cin->C, k=10, s=5, no bias) + GroupNorm(C, C, eps) + exact GELU, fused, output
  * channels-last bf16 [B, L_out, C].  x is [B, Cin, L] bf16, w the fp32 master weight [C, Cin, 10] (rounded to bf16 on
- * load, as autocast does).  stats [B, C, 2] fp64 (sum, sum of squares of the bf16 conv output) is written by the
- * forward and consumed by the backward.  Reference: wavjepa/extractors/audio_feature_extractor.py:70,94,95. */
+ * load, as autocast does).  Workspaces written by the forward and consumed by the backward:
+ *   moments [B, wj_conv0_moment_count(Cin)] fp64: window sums s[a] and second moments R[a][a'] of the input
+ *   stats   [B, C, 2] fp32: GroupNorm (mean, rstd) of every (instance, channel), closed form from the moments.
+ * Reference: wavjepa/extractors/audio_feature_extractor.py:70,94,95. */
+int wj_conv0_moment_count(int Cin);
 int wj_conv0_gn_gelu_fwd(const void* x_bf16, const float* w, const float* gamma, const float* beta, int B, int Cin,
-                         int L, int C, int k, int stride, float eps, double* stats, void* out_bf16, void* stream);
+                         int L, int C, int k, int stride, float eps, double* moments, float* stats, void* out_bf16,
+                         void* stream);
 /* Backward of the block above given dY (bf16 [B, L_out, C]); accumulates into dw [C, Cin, 10], dgamma, dbeta (fp32).
- * red_scratch: [B, C, 2] fp64 workspace. */
+ * red_scratch: [B, 2 + Cin*10, C] fp32 workspace. */
 int wj_conv0_gn_gelu_bwd(const void* x_bf16, const float* w, const float* gamma, const float* beta, int B, int Cin,
-                         int L, int C, int k, int stride, float eps, const double* stats, const void* dy_bf16,
-                         double* red_scratch, float* dw, float* dgamma, float* dbeta, void* stream);
+                         int L, int C, int k, int stride, float eps, const double* moments, const float* stats,
+                         const void* dy_bf16, float* red_scratch, float* dw, float* dgamma, float* dbeta, void* stream);
 
 /* LayerNorm over the last dim (D in {128,256,384,512,768,1024}), biased variance, one warp per row.
  * Writes any of: out_f32, out_bf16, stats [M,2] = (mean, rstd), rowsum [M,2] = (sum, sum of squares of the OUTPUT row).

@@ -33,9 +33,13 @@ def step():
     return model.train_step(x16, ctx, tgt, vis)
 
 
-for _ in range(3):
+import time  # noqa: E402
+for i in range(8):
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
     step()
-torch.cuda.synchronize()
+    torch.cuda.synchronize()
+    print(f"warm-up step {i}: {(time.perf_counter() - t0) * 1e3:.1f} ms, reserved {torch.cuda.memory_reserved() / 2**30:.1f} GiB")
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
 for _ in range(3):
@@ -43,7 +47,6 @@ for _ in range(3):
 e1.record()
 torch.cuda.synchronize()
 print(f"step (unprofiled): {e0.elapsed_time(e1) / 3:.2f} ms")
-import time  # noqa: E402
 for _ in range(2):
     torch.cuda.synchronize()
     t0 = time.perf_counter()

@@ -219,7 +219,7 @@ def test_mask_indices():
 
 
 # ------------------------------------------------------------------------------------------------------- conv0
-@pytest.mark.parametrize("Cin,L", [(1, 32159), (2, 4000)])
+@pytest.mark.parametrize("Cin,L", [(1, 32159), (2, 4000), (1, 2577)])
 def test_conv0_gn_gelu_fwd_bwd(Cin, L):
     B, C = 3, 512
     x = torch.randn(B, Cin, L, device=DEV).bfloat16()
@@ -228,8 +228,8 @@ def test_conv0_gn_gelu_fwd_bwd(Cin, L):
     beta = 0.1 * torch.randn(C, device=DEV)
     L_out = (L - 10) // 5 + 1
     out = torch.empty(B, L_out, C, device=DEV, dtype=torch.bfloat16)
-    stats = torch.empty(B, C, 2, device=DEV, dtype=torch.float64)
-    ops.conv0_fwd(x, w, gamma, beta, out, stats)
+    mom, stats, red = ops.conv0_workspaces(B, Cin, C, DEV, backward=True)
+    ops.conv0_fwd(x, w, gamma, beta, out, mom, stats)
     wr = w.bfloat16().float().requires_grad_(True)
     gr = gamma.clone().requires_grad_(True)
     br = beta.clone().requires_grad_(True)
@@ -242,8 +242,11 @@ def test_conv0_gn_gelu_fwd_bwd(Cin, L):
     dw = torch.zeros_like(w)
     dg = torch.zeros(C, device=DEV)
     db = torch.zeros(C, device=DEV)
-    red = torch.empty(B, C, 2, device=DEV, dtype=torch.float64)
-    ops.conv0_bwd(x, w, gamma, beta, stats, dy, red, dw, dg, db)
+    ops.conv0_bwd(x, w, gamma, beta, mom, stats, dy, red, dw, dg, db)
+    # closed-form GroupNorm statistics == statistics of the conv output (to fp32 accuracy)
+    hm = h.detach().mean(dim=2)
+    assert (stats[..., 0] - hm).abs().max() < 1e-4
+    assert rel(stats[..., 1], 1.0 / torch.sqrt(h.detach().var(dim=2, unbiased=False) + 1e-5)) < 1e-4
     assert rel(dw, wr.grad) < 2e-3
     assert rel(dg, gr.grad) < 2e-3
     assert rel(db, br.grad) < 2e-3

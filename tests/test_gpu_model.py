@@ -180,7 +180,9 @@ def test_fused_train_step_equals_bridge_plus_torch_adamw():
     for n_ in pa:
         d = (pa[n_].detach() - pb[n_].detach()).abs().max().item()
         scale = pb[n_].detach().abs().max().item() + 1e-12
-        assert d <= 2e-6 * scale + 1e-7, (n_, d)
+        # fp32 atomics make the two gradient evaluations differ in the last bits; Adam's first update is
+        # lr * g / (|g| + eps), so allow 2% of one step on top of fp32 rounding
+        assert d <= 2e-6 * scale + 0.02 * b.lr_at(50000), (n_, d)
     # weights moved, teacher moved
     moved = (pa["encoder.layers.0.linear1.weight"].detach().cpu() - sd["encoder.layers.0.linear1.weight"]).abs().max()
     assert moved > 0

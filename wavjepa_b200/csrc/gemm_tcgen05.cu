@@ -297,6 +297,49 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll 1
       for (int u = 0; u < UNITS; ++u) {
         const int ch = u >> 1, half = u & 1;
+        const int n0 = n_blk * BN + (col_q * CHUNKS + ch) * 32 + tg * 8;
+        const bool col_ok = n0 < p.N;   // N is a multiple of 8: groups of 8 columns are all-or-nothing
+        // physical output rows of tile rows (lane_grp*32 + 16*half + 8*hr + g); -1 = nothing to write
+        long long orow2[2];
+#pragma unroll
+        for (int hr = 0; hr < 2; ++hr) {
+          const int r_local = lane_grp * 32 + half * 16 + hr * 8 + g;
+          long long orow;
+          bool ok;
+          if constexpr (!WGRAD) {
+            const int rib = row_in_batch0 + r_local;
+            ok = rib < p.L;
+            orow = static_cast<long long>(b) * p.L + rib;
+          } else {
+            orow = static_cast<long long>(m_blk) * BM + r_local;
+            ok = orow < p.M && have_k;
+          }
+          if (ok && p.out_rows != nullptr) orow = p.out_rows[orow];
+          orow2[hr] = (ok && col_ok) ? orow : -1;
+        }
+        // the global inputs of this unit (fp32/bf16 residual or the saved GELU') are requested BEFORE waiting for TMEM
+        uint4 pre[2][2];
+        const bool pre_resid = p.resid != nullptr;
+        const bool pre_aux = !pre_resid && p.act == 2;
+#pragma unroll
+        for (int hr = 0; hr < 2; ++hr) {
+          pre[hr][0] = make_uint4(0u, 0u, 0u, 0u);
+          pre[hr][1] = make_uint4(0u, 0u, 0u, 0u);
+          if (orow2[hr] >= 0) {
+            if (pre_resid) {
+              const long long rrow = p.resid_mod > 0 ? (orow2[hr] % p.resid_mod) : orow2[hr];
+              if (p.resid_f32) {
+                const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(p.resid) + rrow * p.ld_resid + n0);
+                pre[hr][0] = rp[0];
+                pre[hr][1] = rp[1];
+              } else {
+                pre[hr][0] = *reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p.resid) + rrow * p.ld_resid + n0);
+              }
+            } else if (pre_aux) {
+              pre[hr][0] = *reinterpret_cast<const uint4*>(p.aux + orow2[hr] * p.ld_aux + n0);
+            }
+          }
+        }
         tmem_ld_wait();
         // v[4*j + 2*hr + {0,1}] = (row g + 8*hr + 16*half, columns 8*j + 2*tg + {0,1}) of this warp's 32 x 32 chunk
         float f[2][8];
@@ -319,8 +362,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           if (lane == 0) mbar_arrive(&tempty_bar[acc]);
         }
 
-        const int n0 = n_blk * BN + (col_q * CHUNKS + ch) * 32 + tg * 8;
-        const bool col_ok = n0 < p.N;   // N is a multiple of 8: groups of 8 columns are all-or-nothing
         float bias8[8];
 #pragma unroll
         for (int c = 0; c < 8; ++c) bias8[c] = 0.f;
@@ -335,23 +376,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         for (int c = 0; c < 8; ++c) cs[c] = 0.f;
 #pragma unroll
         for (int hr = 0; hr < 2; ++hr) {
-          // physical output row of tile row (lane_grp*32 + 16*half + 8*hr + g); -1 = nothing to write
-          long long orow;
-          {
-            const int r_local = lane_grp * 32 + half * 16 + hr * 8 + g;
-            bool ok;
-            if constexpr (!WGRAD) {
-              const int rib = row_in_batch0 + r_local;
-              ok = rib < p.L;
-              orow = static_cast<long long>(b) * p.L + rib;
-            } else {
-              orow = static_cast<long long>(m_blk) * BM + r_local;
-              ok = orow < p.M && have_k;
-            }
-            if (ok && p.out_rows != nullptr) orow = p.out_rows[orow];
-            if (!ok) orow = -1;
-          }
-          if (orow < 0 || !col_ok) continue;
+          const long long orow = orow2[hr];
+          if (orow < 0) continue;
           float* x = f[hr];
 #pragma unroll
           for (int c = 0; c < 8; ++c) x[c] += bias8[c];
@@ -377,7 +403,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               for (int c = 0; c < 8; ++c) x[c] = gelu_fast(x[c]);
             }
           } else if (p.act == 2) {
-            const uint4 w = *reinterpret_cast<const uint4*>(p.aux + orow * p.ld_aux + n0);
+            const uint4 w = pre_aux ? pre[hr][0] : *reinterpret_cast<const uint4*>(p.aux + orow * p.ld_aux + n0);
             const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&w);
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
@@ -386,16 +412,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             }
           }
           if (p.resid != nullptr) {
-            const long long rrow = p.resid_mod > 0 ? (orow % p.resid_mod) : orow;
             if (p.resid_f32) {
-              const float* rp = reinterpret_cast<const float*>(p.resid) + rrow * p.ld_resid + n0;
-              const float4 r0 = *reinterpret_cast<const float4*>(rp);
-              const float4 r1 = *reinterpret_cast<const float4*>(rp + 4);
+              const float4 r0 = *reinterpret_cast<const float4*>(&pre[hr][0]);
+              const float4 r1 = *reinterpret_cast<const float4*>(&pre[hr][1]);
               x[0] += r0.x; x[1] += r0.y; x[2] += r0.z; x[3] += r0.w;
               x[4] += r1.x; x[5] += r1.y; x[6] += r1.z; x[7] += r1.w;
             } else {
-              const uint4 w = *reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p.resid) + rrow * p.ld_resid + n0);
-              const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&w);
+              const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&pre[hr][0]);
 #pragma unroll
               for (int t = 0; t < 4; ++t) {
                 const float2 hh = __bfloat1622float2(h2[t]);
@@ -593,10 +616,20 @@ extern "C" int wj_gemm_wgrad_bf16(const wj_operand_t* dY, const wj_operand_t* X,
   p.kb_per_batch = (L + BK - 1) / BK;
   const int kb_total = batch * p.kb_per_batch;
   if (splits <= 0) {
+    // (m, n) tiles x splits should fill whole rounds of the persistent grid: pick the split count with the best
+    // occupancy over 1..4 rounds (ties: fewer rounds = fewer fp32 reduce-adds)
     const int mn = p.m_blocks * p.n_blocks;
-    splits = (2 * num_sms() + mn - 1) / mn;
-    if (splits > kb_total) splits = kb_total;
-    if (splits < 1) splits = 1;
+    const int sms = num_sms();
+    double best = -1.0;
+    splits = 1;
+    for (int r = 1; r <= 4; ++r) {
+      int sp = (r * sms) / mn;
+      if (sp < 1) sp = 1;
+      if (sp > kb_total) sp = kb_total;
+      const int tiles = sp * mn;
+      const double eff = static_cast<double>(tiles) / (static_cast<double>((tiles + sms - 1) / sms) * sms);
+      if (eff > best + 0.02) { best = eff; splits = sp; }
+    }
   }
   // make every split non-empty
   const int per = (kb_total + splits - 1) / splits;

@@ -95,7 +95,7 @@ def kmajor_weight(w: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.
 
 
 class ConvSaved:
-    __slots__ = ("x16", "stats", "acts", "pre")
+    __slots__ = ("x16", "moments", "stats", "acts", "pre")
 
 
 def conv_stack_forward(spec, x16: torch.Tensor, w0: torch.Tensor, gn_w: torch.Tensor, gn_b: torch.Tensor,
@@ -109,8 +109,8 @@ def conv_stack_forward(spec, x16: torch.Tensor, w0: torch.Tensor, gn_w: torch.Te
     if L0 <= 0:
         raise WavJepaLibError("input shorter than the first conv kernel")
     a = torch.empty(B, L0, C, device=dev, dtype=torch.bfloat16)
-    stats = torch.empty(B, C, 2, device=dev, dtype=torch.float64)
-    ops.conv0_fwd(x16, w0, gn_w, gn_b, a, stats, eps=gn_eps)
+    moments, stats = ops.conv0_workspaces(B, Cin, C, dev)
+    ops.conv0_fwd(x16, w0, gn_w, gn_b, a, moments, stats, eps=gn_eps)
     acts, pre = [a], [None]
     for i, (_, k, _) in enumerate(spec[1:], start=1):
         x = acts[-1]
@@ -133,7 +133,7 @@ def conv_stack_forward(spec, x16: torch.Tensor, w0: torch.Tensor, gn_w: torch.Te
     sv = None
     if save:
         sv = ConvSaved()
-        sv.x16, sv.stats, sv.acts, sv.pre = x16, stats, acts, pre
+        sv.x16, sv.moments, sv.stats, sv.acts, sv.pre = x16, moments, stats, acts, pre
     return acts[-1], sv
 
 
@@ -164,8 +164,8 @@ def conv_stack_backward(spec, sv: ConvSaved, dh_last: torch.Tensor, w0, gn_w, gn
         dh = dx
         if on_layer_done is not None:
             on_layer_done(i)
-    red = torch.empty(B, C, 2, device=dev, dtype=torch.float64)
-    ops.conv0_bwd(sv.x16, w0, gn_w, gn_b, sv.stats, dh, red, g_w0, g_gn_w, g_gn_b, eps=gn_eps)
+    red = torch.empty(B, 2 + sv.x16.shape[1] * 10, C, device=dev, dtype=torch.float32)
+    ops.conv0_bwd(sv.x16, w0, gn_w, gn_b, sv.moments, sv.stats, dh, red, g_w0, g_gn_w, g_gn_b, eps=gn_eps)
     if on_layer_done is not None:
         on_layer_done(0)
 

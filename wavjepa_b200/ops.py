@@ -245,23 +245,36 @@ def mask_indices(ctx_hidden: torch.Tensor, tgt: torch.Tensor, vis_hidden: torch.
 
 
 # ----------------------------------------------------------------------------------------------------- conv0
+def conv0_workspaces(B: int, Cin: int, C: int, device, backward: bool = False):
+    """(moments fp64 [B, n], stats fp32 [B, C, 2][, red_scratch fp32 [B, 2 + Cin*10, C]]) for conv0_fwd / conv0_bwd."""
+    n = int(_lib.load().wj_conv0_moment_count(Cin))
+    mom = torch.empty(B, n, device=device, dtype=torch.float64)
+    stats = torch.empty(B, C, 2, device=device, dtype=torch.float32)
+    if backward:
+        return mom, stats, torch.empty(B, 2 + Cin * 10, C, device=device, dtype=torch.float32)
+    return mom, stats
+
+
 def conv0_fwd(x: torch.Tensor, w: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, out: torch.Tensor,
-              stats: torch.Tensor, k: int = 10, stride: int = 5, eps: float = 1e-5) -> None:
+              moments: torch.Tensor, stats: torch.Tensor, k: int = 10, stride: int = 5, eps: float = 1e-5) -> None:
     B, Cin, L = x.shape
     assert x.dtype == torch.bfloat16 and x.is_contiguous() and w.dtype == torch.float32
+    assert moments.dtype == torch.float64 and stats.dtype == torch.float32
     lib = _lib.load()
     check(lib.wj_conv0_gn_gelu_fwd(C.c_void_p(_ptr(x)), C.c_void_p(_ptr(w)), C.c_void_p(_ptr(gamma)),
                                    C.c_void_p(_ptr(beta)), B, Cin, L, w.shape[0], k, stride, C.c_float(eps),
-                                   C.c_void_p(_ptr(stats)), C.c_void_p(_ptr(out)), _stream()))
+                                   C.c_void_p(_ptr(moments)), C.c_void_p(_ptr(stats)), C.c_void_p(_ptr(out)),
+                                   _stream()))
 
 
-def conv0_bwd(x, w, gamma, beta, stats, dy, red_scratch, dw, dgamma, dbeta, k: int = 10, stride: int = 5,
+def conv0_bwd(x, w, gamma, beta, moments, stats, dy, red_scratch, dw, dgamma, dbeta, k: int = 10, stride: int = 5,
               eps: float = 1e-5) -> None:
     B, Cin, L = x.shape
+    assert red_scratch.dtype == torch.float32 and red_scratch.numel() >= B * (2 + Cin * 10) * w.shape[0]
     lib = _lib.load()
     p = lambda t: C.c_void_p(_ptr(t))
     check(lib.wj_conv0_gn_gelu_bwd(p(x), p(w), p(gamma), p(beta), B, Cin, L, w.shape[0], k, stride, C.c_float(eps),
-                                   p(stats), p(dy), p(red_scratch), p(dw), p(dgamma), p(dbeta), _stream()))
+                                   p(moments), p(stats), p(dy), p(red_scratch), p(dw), p(dgamma), p(dbeta), _stream()))
 
 
 # ----------------------------------------------------------------------------------------------------- norms
