@@ -177,12 +177,16 @@ def test_fused_train_step_equals_bridge_plus_torch_adamw():
     torch.nn.utils.clip_grad_norm_(trainables, 5.0)
     opt.step()
     pa, pb = dict(a.named_parameters()), dict(b.named_parameters())
+    lr = b.lr_at(50000)
     for n_ in pa:
-        d = (pa[n_].detach() - pb[n_].detach()).abs().max().item()
-        scale = pb[n_].detach().abs().max().item() + 1e-12
-        # fp32 atomics make the two gradient evaluations differ in the last bits; Adam's first update is
-        # lr * g / (|g| + eps), so allow 2% of one step on top of fp32 rounding
-        assert d <= 2e-6 * scale + 0.02 * b.lr_at(50000), (n_, d)
+        # fp32 atomics (split-K wgrad, conv0 reductions) make two gradient evaluations differ in the last bits, and
+        # Adam's normalised update g / (|g| + eps) amplifies that for the few near-zero gradients: compare the UPDATES
+        # in relative L2 per tensor and bound the worst element by a fraction of one step
+        p0 = sd[n_].to(DEV)
+        da, db_ = pa[n_].detach() - p0, pb[n_].detach() - p0
+        if db_.norm() > 0:
+            assert ((da - db_).norm() / db_.norm()).item() < 2e-3, n_
+        assert (da - db_).abs().max().item() <= 0.25 * lr, n_
     # weights moved, teacher moved
     moved = (pa["encoder.layers.0.linear1.weight"].detach().cpu() - sd["encoder.layers.0.linear1.weight"]).abs().max()
     assert moved > 0
