@@ -242,12 +242,19 @@ def run_native(args):
     h2d = CLIPS * CLIP_LEN * 4
     d2h = 4 + 8 * 4   # loss scalar + the mask totals read by the host to size the packed buffers
 
+    # ---------------------------------------------------------------- per-kernel attribution (outside the timed region)
+    # every rank runs this extra step (its gradient all-reduce is a collective); only rank 0 brackets its launches
+    kp = None
+    if rank == 0:
+        with _lib.KernelProfile() as kp:
+            step(dev_clips[0])
+    else:
+        step(dev_clips[0])
+    barrier()
+
     out = None
     if rank == 0:
         peaks = load_peaks()
-        # ------------------------------------------------------------ per-kernel attribution (outside the timed region)
-        with _lib.KernelProfile() as kp:
-            step(dev_clips[0])
         summ = kp.summary()
         gemm_names = ("wj_gemm_bf16", "wj_gemm_dgrad_bf16", "wj_gemm_wgrad_bf16")
         g_calls = sum(summ[n][0] for n in gemm_names if n in summ)
