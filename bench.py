@@ -191,6 +191,10 @@ def run_native(args):
         last_mi["mi"] = model._last_mi
         return loss
 
+    def note(msg):
+        if os.environ.get("WJ_BENCH_VERBOSE"):
+            print(f"[bench rank {rank}] {msg}", file=sys.stderr, flush=True)
+
     def barrier():
         if world > 1:
             dist.barrier()
@@ -204,8 +208,10 @@ def run_native(args):
         return t.item()
 
     # ---------------------------------------------------------------- device-resident arm (`value`)
+    note("model built")
     for i in range(args.warmup):
         step(dev_clips[i % n_pool])
+        note(f"warm-up step {i} issued")
     sampler = ClockSampler(local) if rank == 0 else None
     barrier()
     if sampler:
@@ -224,6 +230,7 @@ def run_native(args):
     ms_step = ms_total / args.steps
     value = world * B * args.steps / (ms_total / 1e3)
     final_loss = loss.item()
+    note(f"timed region done: {ms_step:.1f} ms/step")
 
     # ---------------------------------------------------------------- end-to-end arm (`e2e`): host clips in, loss out
     def e2e_step(i):
@@ -239,6 +246,7 @@ def run_native(args):
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e_value = world * B * args.steps / e2e_s
+    note("e2e region done")
     h2d = CLIPS * CLIP_LEN * 4
     d2h = 4 + 8 * 4   # loss scalar + the mask totals read by the host to size the packed buffers
 
