@@ -13,7 +13,7 @@ ncu = "--ncu" in sys.argv
 torch.manual_seed(0)
 
 
-def run(name, M, N, K, *, act=0, f32=False, resid=False, out2=False, aux=False, bias=True, mode="fwd", reps=20):
+def run(name, M, N, K, *, act=0, f32=False, resid=False, out2=False, aux=False, bias=True, mode="fwd", reps=20, bn=0):
     a = torch.randn(M, K, device=dev).bfloat16()
     w = (torch.randn(N, K, device=dev) * 0.05).bfloat16() if mode == "fwd" else (torch.randn(K, N, device=dev) * 0.05).bfloat16()
     outs = [torch.empty(M, N, device=dev, dtype=torch.float32 if f32 else torch.bfloat16) for _ in range(2)]
@@ -24,7 +24,7 @@ def run(name, M, N, K, *, act=0, f32=False, resid=False, out2=False, aux=False, 
 
     def call(i):
         if mode == "fwd":
-            ops.gemm(ops.plain_operand(a), w, M, 1, outs[i % 2], bias=b, act=act, resid=r, out2=o2, aux=ax)
+            ops.gemm(ops.plain_operand(a), w, M, 1, outs[i % 2], bias=b, act=act, resid=r, out2=o2, aux=ax, block_n=bn)
         else:
             ops.gemm_dgrad(ops.plain_operand(a), w, M, 1, outs[i % 2], K=K, N=N, act=act, aux=ax, resid=r)
 
@@ -45,6 +45,56 @@ def run(name, M, N, K, *, act=0, f32=False, resid=False, out2=False, aux=False, 
     print(f"{name:34s} M{M} N{N} K{K} act{act} f32{int(f32)} resid{int(resid)}: {ms:.3f} ms  {2.0 * M * N * K / ms / 1e9:.0f} TFLOP/s")
 
 
+def run_conv_wgrad(B=512, L_in=6430, C=512, k=3, reps=5):
+    L_out = (L_in - k) // 2 + 1
+    x = torch.randn(B, L_in, C, device=dev).bfloat16()
+    dy = torch.randn(B, L_out, C, device=dev).bfloat16()
+    out = torch.empty(C, k * C, device=dev)
+
+    def call():
+        ops.gemm_wgrad(ops.make_operand(dy, C, L_out, B), ops.conv_operand(x, k), L_out, B, out)
+
+    def call_plain():   # same FLOPs, B operand as a plain [B*L_out, k*C] matrix (no segments): isolates the addressing
+        ops.gemm_wgrad(ops.make_operand(dy, C, L_out, B), ops.make_operand(x, 1024, L_out, B, row_stride=1024, batch_stride=L_in * C),
+                       L_out, B, out[:, :1024], N=1024, ld_out=k * C)
+
+    if ncu:
+        call()
+        torch.cuda.synchronize()
+        return
+    for nm, fn, ncols in (("conv1 wgrad (segments)", call, k * C), ("conv1 wgrad (plain 1024 cols)", call_plain, 1024)):
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        print(f"{nm:34s} B{B} L_out{L_out}: {ms:.3f} ms  {2.0 * B * L_out * C * ncols / ms / 1e9:.0f} TFLOP/s")
+
+
+if "--pair" in sys.argv:
+    for bn in (0, -256):
+        tag = "pair" if bn < 0 else "1cta"
+        run(f"{tag} teacher fc1 plain", 102400, 3072, 768, bn=bn)
+        run(f"{tag} teacher fc1 gelu", 102400, 3072, 768, act=1, bn=bn)
+        run(f"{tag} teacher qkv plain", 102400, 2304, 768, bn=bn)
+        run(f"{tag} teacher fc2 resid f32", 102400, 768, 3072, act=3, f32=True, resid=True, bn=bn)
+        run(f"{tag} teacher outproj resid f32", 102400, 768, 768, act=3, f32=True, resid=True, bn=bn)
+        run(f"{tag} pred fc1 plain", 172433, 1536, 384, bn=bn)
+        run(f"{tag} pred fc1 gelu+save", 172433, 1536, 384, act=1, out2=True, bn=bn)
+        run(f"{tag} conv-like M1.6M N512 K1536", 1645568, 512, 1536, act=1, bias=False, bn=bn, reps=5)
+    for bn in (0, -128):
+        tag = "pair128" if bn < 0 else "1cta"
+        run(f"{tag} pred qkv plain", 172433, 1152, 384, bn=bn)
+        run(f"{tag} pred fc2 resid f32", 172433, 384, 1536, act=3, f32=True, resid=True, bn=bn)
+        run(f"{tag} pred outproj resid f32", 172433, 384, 384, act=3, f32=True, resid=True, bn=bn)
+    sys.exit(0)
+if "--conv-wgrad" in sys.argv:
+    run_conv_wgrad()
+    sys.exit(0)
 run("pred qkv plain", 172433, 1152, 384)
 run("pred fc1 gelu+save", 172433, 1536, 384, act=1, out2=True)
 run("pred fc1 gelu", 172433, 1536, 384, act=1)

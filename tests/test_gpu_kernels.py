@@ -447,3 +447,50 @@ def test_ema_bitwise_and_optimizer_tail():
     cs = torch.zeros(768, device=DEV)
     ops.colsum(x.bfloat16(), cs)
     assert rel(cs, x.bfloat16().float().sum(0)) < 1e-4
+    # fp32 input, ragged row count, non-multiple-of-8 width (generic kernel), strided view (ld > N)
+    for (M, N, dt) in ((1237, 1152, torch.bfloat16), (999, 384, torch.float32), (77, 1150, torch.bfloat16)):
+        xx = torch.randn(M, N + 8, device=DEV).to(dt)[:, :N]
+        cs = torch.ones(N, device=DEV)
+        ops.colsum(xx, cs)
+        assert rel(cs, 1.0 + xx.float().sum(0)) < 1e-4, (M, N, dt)
+
+
+# ------------------------------------------------------------------------------------------------------- CTA-pair GEMM
+@pytest.mark.parametrize("M,N,K,bn", [(256, 256, 64, -256), (300, 768, 512, -256), (20000, 2304, 768, -256),
+                                      (777, 384, 384, -128), (5000, 1152, 384, -128), (131, 3072, 768, -256)])
+def test_gemm_pair_plain(M, N, K, bn):
+    """tcgen05 cta_group::2 kernel (256-row tiles shared by two CTAs of a cluster): same results as the 1-CTA path."""
+    a = torch.randn(M, K, device=DEV).bfloat16()
+    w = (torch.randn(N, K, device=DEV) * 0.05).bfloat16()
+    out = torch.full((M, N), float("nan"), device=DEV, dtype=torch.bfloat16)
+    ops.gemm(ops.plain_operand(a), w, M, 1, out, block_n=bn)
+    assert rel(out, a.float() @ w.float().t()) < BF16_TOL
+    ref = torch.empty_like(out)
+    ops.gemm(ops.plain_operand(a), w, M, 1, ref, block_n=-bn)
+    assert torch.equal(out, ref)
+
+
+def test_gemm_pair_epilogues_and_conv():
+    M, N, K = 1000, 1536, 384
+    a = torch.randn(M, K, device=DEV).bfloat16()
+    w = (torch.randn(N, K, device=DEV) * 0.05).bfloat16()
+    bias = torch.randn(N, device=DEV)
+    res = torch.randn(M, N, device=DEV)
+    base = a.float() @ w.float().t()
+    o = torch.empty(M, N, device=DEV)
+    ops.gemm(ops.plain_operand(a), w, M, 1, o, bias=bias, resid=res, act=ops.ACT_BF16, block_n=-256)
+    assert rel(o, (base + bias).bfloat16().float() + res) < 1e-4
+    out = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+    out2 = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+    ops.gemm(ops.plain_operand(a), w, M, 1, out, bias=bias, act=ops.ACT_GELU, out2=out2, block_n=-256)
+    assert rel(out, F.gelu((base + bias).bfloat16().float())) < BF16_TOL
+    # implicit-GEMM conv (k3, stride 2) over channels-last activations, ragged L_out per batch entry
+    B, L_in, C = 3, 802, 512
+    x = torch.randn(B, L_in, C, device=DEV).bfloat16()
+    wc = (torch.randn(C, C, 3, device=DEV) * 0.03)
+    wk = wc.permute(0, 2, 1).reshape(C, 3 * C).bfloat16().contiguous()
+    L_out = (L_in - 3) // 2 + 1
+    y = torch.empty(B, L_out, C, device=DEV, dtype=torch.bfloat16)
+    ops.gemm(ops.conv_operand(x, 3), wk, L_out, B, y.view(-1, C), block_n=-256)
+    ref = F.conv1d(x.float().transpose(1, 2), wk.float().view(C, 3, C).permute(0, 2, 1), stride=2).transpose(1, 2)
+    assert rel(y, ref) < BF16_TOL

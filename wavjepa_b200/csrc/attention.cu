@@ -116,7 +116,7 @@ __device__ __forceinline__ void mm_pb(float (&acc)[DH / 8][4], const float (&pf)
 // One CTA per (sequence, head): Q, K, V of the whole sequence are brought into smem once (cp.async, one wait), then
 // every warp walks its 16-query blocks over 64-key blocks with an online softmax; no block-level sync in the loop.
 template <int DH>
-__global__ void __launch_bounds__(128) attn_fwd_kernel(const bf16* __restrict__ qkv, const int* __restrict__ cu, int D,
+__global__ void __launch_bounds__(256) attn_fwd_kernel(const bf16* __restrict__ qkv, const int* __restrict__ cu, int D,
                                                        int H, int NPAD, float scale_log2, bf16* __restrict__ out,
                                                        float* __restrict__ lse2) {
   constexpr int PITCH = DH + 8;
@@ -205,7 +205,7 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const bf16* __restrict__ 
 // One CTA per (sequence, head); Q, K, V, dO of the whole sequence live in smem (NPAD rows each).
 //   phase A: warps own 16-query blocks -> dQ;  phase B: warps own 16-key blocks -> dK, dV.  No atomics.
 template <int DH>
-__global__ void __launch_bounds__(128) attn_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ out,
+__global__ void __launch_bounds__(128, (DH == 32 ? 4 : 2)) attn_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ out,
                                                        const bf16* __restrict__ dout, const float* __restrict__ lse2,
                                                        const int* __restrict__ cu, int D, int H, int NPAD, float scale,
                                                        float scale_log2, bf16* __restrict__ dqkv) {
@@ -363,17 +363,18 @@ extern "C" int wj_attn_varlen_fwd(const void* qkv_bf16, const int* cu_seqlens, i
   if (smem > 227 * 1024) { set_error("wj_attn_varlen_fwd: sequence of %d tokens (head dim %d) exceeds the shared-memory resident design", max_len, dh); return WJ_ERR_ARG; }
   const float scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(dh));
   dim3 grid(H, n_seqs);
+  const int threads = max_len > 96 ? 256 : 128;   // one warp per 16-query block per round
   const bf16* q = reinterpret_cast<const bf16*>(qkv_bf16);
   bf16* o = reinterpret_cast<bf16*>(out_bf16);
   cudaError_t e;
   if (dh == 64) {
     e = cudaFuncSetAttribute(attn_fwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) { set_error("attn_fwd attr: %s", cudaGetErrorString(e)); return WJ_ERR_RUNTIME; }
-    attn_fwd_kernel<64><<<grid, 128, smem, WJ_STREAM(stream)>>>(q, cu_seqlens, D, H, npad, scale_log2, o, lse2);
+    attn_fwd_kernel<64><<<grid, threads, smem, WJ_STREAM(stream)>>>(q, cu_seqlens, D, H, npad, scale_log2, o, lse2);
   } else {
     e = cudaFuncSetAttribute(attn_fwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) { set_error("attn_fwd attr: %s", cudaGetErrorString(e)); return WJ_ERR_RUNTIME; }
-    attn_fwd_kernel<32><<<grid, 128, smem, WJ_STREAM(stream)>>>(q, cu_seqlens, D, H, npad, scale_log2, o, lse2);
+    attn_fwd_kernel<32><<<grid, threads, smem, WJ_STREAM(stream)>>>(q, cu_seqlens, D, H, npad, scale_log2, o, lse2);
   }
   return check_launch("attn_varlen_fwd");
 }

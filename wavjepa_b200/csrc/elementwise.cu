@@ -251,7 +251,69 @@ __global__ void __launch_bounds__(256) cast_kernel(const float* __restrict__ x, 
     for (long long i = n4 * 4; i < n; ++i) y[i] = __float2bfloat16_rn(x[i]);
 }
 
-// out[n] += sum_m x[m, n]  (x bf16 or fp32, row-major with leading dimension ld)
+// out[n] += sum_m x[m, n]  (x bf16 or fp32, row-major with leading dimension ld; N % 8 == 0 fast path).
+// Block (32, 8): thread (tx, ty) owns 8 consecutive columns (one 16-byte bf16 vector / two fp32 vectors) and every
+// 8th row of the block's row range, 4 rows in flight; the 8 row-partials meet in smem, one atomic per column per block.
+__global__ void __launch_bounds__(256) colsum8_kernel(const void* __restrict__ x, int is_bf16, long long M, int N,
+                                                      long long ld, int rows_per_block, float* __restrict__ out) {
+  __shared__ float s_acc[8][32][9];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int c = (blockIdx.x * 32 + tx) * 8;
+  const long long r0 = static_cast<long long>(blockIdx.y) * rows_per_block;
+  const long long r1 = min(M, r0 + rows_per_block);
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  if (c < N) {
+    if (is_bf16) {
+      const bf16* p = reinterpret_cast<const bf16*>(x) + c;
+      long long r = r0 + ty;
+      for (; r + 24 < r1; r += 32) {
+        uint4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = *reinterpret_cast<const uint4*>(p + (r + 8 * u) * ld);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&v[u]);
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const float2 f = __bfloat1622float2(h2[t]);
+            acc[2 * t] += f.x; acc[2 * t + 1] += f.y;
+          }
+        }
+      }
+      for (; r < r1; r += 8) {
+        const uint4 v = *reinterpret_cast<const uint4*>(p + r * ld);
+        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const float2 f = __bfloat1622float2(h2[t]);
+          acc[2 * t] += f.x; acc[2 * t + 1] += f.y;
+        }
+      }
+    } else {
+      const float* p = reinterpret_cast<const float*>(x) + c;
+      for (long long r = r0 + ty; r < r1; r += 8) {
+        const float4 a = *reinterpret_cast<const float4*>(p + r * ld);
+        const float4 b = *reinterpret_cast<const float4*>(p + r * ld + 4);
+        acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
+        acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s_acc[ty][tx][i] = acc[i];
+  __syncthreads();
+  // 256 threads finish 32 x 8 columns: thread (tx, ty) sums column ty of group tx over the 8 row-partials
+  if (c < N) {
+    float v = 0.f;
+#pragma unroll
+    for (int y = 0; y < 8; ++y) v += s_acc[y][tx][ty];
+    atomicAdd(out + c + ty, v);
+  }
+}
+
+// generic fallback (N even)
 __global__ void __launch_bounds__(256) colsum_kernel(const void* __restrict__ x, int is_bf16, long long M, int N,
                                                      long long ld, int rows_per_block, float* __restrict__ out) {
   const long long r0 = static_cast<long long>(blockIdx.y) * rows_per_block;
@@ -401,12 +463,22 @@ extern "C" int wj_cast_bf16(const float* x, void* y_bf16, int64_t n, void* strea
 extern "C" int wj_colsum(const void* x, int x_is_bf16, int64_t M, int N, int64_t ld, float* out, void* stream) {
   if (M <= 0) return WJ_OK;
   if (N % 2) { set_error("wj_colsum: N must be even"); return WJ_ERR_ARG; }
-  const int bx = (N / 2 + 255) / 256;
-  int by = (2 * sm_count() + bx - 1) / bx;
-  if (by > M) by = static_cast<int>(M);
-  const int rows_per_block = static_cast<int>((M + by - 1) / by);
-  by = static_cast<int>((M + rows_per_block - 1) / rows_per_block);
-  colsum_kernel<<<dim3(bx, by), 256, 0, WJ_STREAM(stream)>>>(x, x_is_bf16, M, N, ld, rows_per_block, out);
+  const bool aligned = (reinterpret_cast<uintptr_t>(x) % 16 == 0) && (ld % 8 == 0);
+  if (N % 8 == 0 && aligned) {
+    const int bx = (N / 8 + 31) / 32;
+    int by = (8 * sm_count() + bx - 1) / bx;
+    if (by > (M + 31) / 32) by = static_cast<int>((M + 31) / 32);
+    const int rows_per_block = static_cast<int>((M + by - 1) / by);
+    by = static_cast<int>((M + rows_per_block - 1) / rows_per_block);
+    colsum8_kernel<<<dim3(bx, by), dim3(32, 8), 0, WJ_STREAM(stream)>>>(x, x_is_bf16, M, N, ld, rows_per_block, out);
+  } else {
+    const int bx = (N / 2 + 255) / 256;
+    int by = (2 * sm_count() + bx - 1) / bx;
+    if (by > M) by = static_cast<int>(M);
+    const int rows_per_block = static_cast<int>((M + by - 1) / by);
+    by = static_cast<int>((M + rows_per_block - 1) / rows_per_block);
+    colsum_kernel<<<dim3(bx, by), 256, 0, WJ_STREAM(stream)>>>(x, x_is_bf16, M, N, ld, rows_per_block, out);
+  }
   return check_launch("colsum");
 }
 

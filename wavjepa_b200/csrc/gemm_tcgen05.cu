@@ -95,6 +95,200 @@ __device__ __forceinline__ void seg_coords(const SegInfo& s, int vc, int& c0, in
   }
 }
 
+// One accumulator tile (this warp's 32 TMEM lanes x BN/4 columns) -> fused epilogue -> global memory.
+// Shared-memory bandwidth belongs to the MMA (a 128x256x16 UMMA reads 12 KB of operands per 128 cycles = 96 of the
+// 128 B/cycle), so the epilogue never touches smem: tcgen05.ld.16x256b hands every quad of lanes 8 consecutive
+// columns of a row (2 per lane), a 4x4 quad transpose through warp shuffles gives each lane 8 CONSECUTIVE columns
+// (32 B fp32 / 16 B bf16) of rows g and g+8, and all global traffic (bias, residual, saved GELU', outputs) is
+// 16-byte vectors with 64-128 contiguous bytes per row per instruction.  Work unit = 16 TMEM lanes x 32 columns;
+// the next unit's TMEM load is in flight during the math of the current one.  `arrive()` hands the accumulator back
+// to the MMA warp as soon as this warp's last tcgen05.ld has completed.
+template <int BN, bool WGRAD, typename Arrive>
+__device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t t_base, int lane, int lane_grp, int col_q,
+                                              int n_blk, int b, int row_in_batch0, long long wgrad_row0, bool have_k,
+                                              Arrive arrive) {
+  constexpr int CHUNKS = BN / 32 / 4;       // 32-column chunks per warp
+  constexpr int UNITS = CHUNKS * 2;
+  const int g = lane >> 2, tg = lane & 3;
+  uint32_t v[16];
+  tmem_ld_16x256b_x4(t_base, v);
+#pragma unroll 1
+  for (int u = 0; u < UNITS; ++u) {
+    const int ch = u >> 1, half = u & 1;
+    const int n0 = n_blk * BN + (col_q * CHUNKS + ch) * 32 + tg * 8;
+    const bool col_ok = n0 < p.N;   // N is a multiple of 8: groups of 8 columns are all-or-nothing
+    // physical output rows of tile rows (lane_grp*32 + 16*half + 8*hr + g); -1 = nothing to write
+    long long orow2[2];
+#pragma unroll
+    for (int hr = 0; hr < 2; ++hr) {
+      const int r_local = lane_grp * 32 + half * 16 + hr * 8 + g;
+      long long orow;
+      bool ok;
+      if constexpr (!WGRAD) {
+        const int rib = row_in_batch0 + r_local;
+        ok = rib < p.L;
+        orow = static_cast<long long>(b) * p.L + rib;
+      } else {
+        orow = wgrad_row0 + r_local;
+        ok = orow < p.M && have_k;
+      }
+      if (ok && p.out_rows != nullptr) orow = p.out_rows[orow];
+      orow2[hr] = (ok && col_ok) ? orow : -1;
+    }
+    // the global inputs of this unit (fp32/bf16 residual or the saved GELU') are requested BEFORE waiting for TMEM
+    uint4 pre[2][2];
+    const bool pre_resid = p.resid != nullptr;
+    const bool pre_aux = !pre_resid && p.act == 2;
+#pragma unroll
+    for (int hr = 0; hr < 2; ++hr) {
+      pre[hr][0] = make_uint4(0u, 0u, 0u, 0u);
+      pre[hr][1] = make_uint4(0u, 0u, 0u, 0u);
+      if (orow2[hr] >= 0) {
+        if (pre_resid) {
+          const long long rrow = p.resid_mod > 0 ? (orow2[hr] % p.resid_mod) : orow2[hr];
+          if (p.resid_f32) {
+            const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(p.resid) + rrow * p.ld_resid + n0);
+            pre[hr][0] = rp[0];
+            pre[hr][1] = rp[1];
+          } else {
+            pre[hr][0] = *reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p.resid) + rrow * p.ld_resid + n0);
+          }
+        } else if (pre_aux) {
+          pre[hr][0] = *reinterpret_cast<const uint4*>(p.aux + orow2[hr] * p.ld_aux + n0);
+        }
+      }
+    }
+    tmem_ld_wait();
+    // v[4*j + 2*hr + {0,1}] = (row g + 8*hr + 16*half, columns 8*j + 2*tg + {0,1}) of this warp's 32 x 32 chunk
+    float f[2][8];
+#pragma unroll
+    for (int hr = 0; hr < 2; ++hr) {
+      uint32_t a[8];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { a[2 * j] = v[4 * j + 2 * hr]; a[2 * j + 1] = v[4 * j + 2 * hr + 1]; }
+      quad_transpose(a, tg);   // -> a[0..7] = columns 8*tg .. 8*tg+7 of that row
+#pragma unroll
+      for (int c = 0; c < 8; ++c) f[hr][c] = __uint_as_float(a[c]);
+    }
+    if (u + 1 < UNITS) {
+      const int nu = u + 1;
+      tmem_ld_16x256b_x4(t_base + (static_cast<uint32_t>((nu & 1) * 16) << 16) + (nu >> 1) * 32, v);
+    } else {
+      // every lane has executed tcgen05.wait::ld for its last unit -> hand the accumulator back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) arrive();
+    }
+
+    float bias8[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) bias8[c] = 0.f;
+    if (p.bias != nullptr && col_ok) {
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n0));
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + 4));
+      bias8[0] = b0.x; bias8[1] = b0.y; bias8[2] = b0.z; bias8[3] = b0.w;
+      bias8[4] = b1.x; bias8[5] = b1.y; bias8[6] = b1.z; bias8[7] = b1.w;
+    }
+    float cs[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) cs[c] = 0.f;
+#pragma unroll
+    for (int hr = 0; hr < 2; ++hr) {
+      const long long orow = orow2[hr];
+      if (orow < 0) continue;
+      float* x = f[hr];
+      if (p.bias != nullptr) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) x[c] += bias8[c];
+      }
+      if (p.act == 3) {
+        // the Linear output is bf16 under autocast before it meets the fp32 residual / positional table
+#pragma unroll
+        for (int c = 0; c < 8; ++c) x[c] = bf16_round(x[c]);
+      } else if (p.act == 1) {
+        // autocast semantics: the linear/conv output is bf16 and GELU is evaluated on that bf16 value; out2
+        // receives GELU'(h) (bf16), which is all the backward needs of the pre-activation
+#pragma unroll
+        for (int c = 0; c < 8; ++c) x[c] = bf16_round(x[c]);
+        if (p.out2 != nullptr) {
+          float d[8];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) gelu_fast2(x[c], x[c], d[c]);
+          uint4 w;
+          w.x = pack_bf16x2(d[0], d[1]); w.y = pack_bf16x2(d[2], d[3]);
+          w.z = pack_bf16x2(d[4], d[5]); w.w = pack_bf16x2(d[6], d[7]);
+          *reinterpret_cast<uint4*>(p.out2 + orow * p.ld_out2 + n0) = w;
+        } else {
+#pragma unroll
+          for (int c = 0; c < 8; ++c) x[c] = gelu_fast(x[c]);
+        }
+      } else if (p.act == 2) {
+        const uint4 w = pre_aux ? pre[hr][0] : *reinterpret_cast<const uint4*>(p.aux + orow * p.ld_aux + n0);
+        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&w);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const float2 hh = __bfloat1622float2(h2[t]);
+          x[2 * t] *= hh.x; x[2 * t + 1] *= hh.y;
+        }
+      }
+      if (p.resid != nullptr) {
+        if (p.resid_f32) {
+          const float4 r0 = *reinterpret_cast<const float4*>(&pre[hr][0]);
+          const float4 r1 = *reinterpret_cast<const float4*>(&pre[hr][1]);
+          x[0] += r0.x; x[1] += r0.y; x[2] += r0.z; x[3] += r0.w;
+          x[4] += r1.x; x[5] += r1.y; x[6] += r1.z; x[7] += r1.w;
+        } else {
+          const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&pre[hr][0]);
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const float2 hh = __bfloat1622float2(h2[t]);
+            x[2 * t] += hh.x; x[2 * t + 1] += hh.y;
+          }
+        }
+      }
+      if (p.out_f32) {
+        float* op = reinterpret_cast<float*>(p.out) + orow * p.ld_out + n0;
+        if (p.accumulate) {
+          red_add_v4(op, x[0], x[1], x[2], x[3]);
+          red_add_v4(op + 4, x[4], x[5], x[6], x[7]);
+        } else {
+          *reinterpret_cast<float4*>(op) = make_float4(x[0], x[1], x[2], x[3]);
+          *reinterpret_cast<float4*>(op + 4) = make_float4(x[4], x[5], x[6], x[7]);
+        }
+      } else {
+        uint4 w;
+        w.x = pack_bf16x2(x[0], x[1]); w.y = pack_bf16x2(x[2], x[3]);
+        w.z = pack_bf16x2(x[4], x[5]); w.w = pack_bf16x2(x[6], x[7]);
+        *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + orow * p.ld_out + n0) = w;
+        if (p.colsum != nullptr) {   // sums of the values as stored (bf16), like autograd's bias gradient
+          const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&w);
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const float2 hh = __bfloat1622float2(h2[t]);
+            x[2 * t] = hh.x; x[2 * t + 1] = hh.y;
+          }
+        }
+      }
+      if (p.colsum != nullptr) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) cs[c] += x[c];
+      }
+    }
+    if (p.colsum != nullptr) {
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        cs[c] += __shfl_xor_sync(0xffffffffu, cs[c], 4);
+        cs[c] += __shfl_xor_sync(0xffffffffu, cs[c], 8);
+        cs[c] += __shfl_xor_sync(0xffffffffu, cs[c], 16);
+      }
+      if (g == 0 && col_ok) {
+        red_add_v4(p.colsum + n0, cs[0], cs[1], cs[2], cs[3]);
+        red_add_v4(p.colsum + n0 + 4, cs[4], cs[5], cs[6], cs[7]);
+      }
+    }
+  }
+}
+
 // MODE 0: A K-major, B K-major (fwd)   MODE 1: A, B MN-major (wgrad)   MODE 2: A K-major, B MN-major (dgrad)
 template <int BN, int MODE>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -269,8 +463,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const int lane_grp = warp & 3;            // TMEM lanes [32*lane_grp, +32) are accessible to this warp
     const int col_q = ew >> 2;                // which quarter of the BN columns this warp handles
     constexpr int CHUNKS = BN / 32 / 4;       // 32-column chunks per warp
-    constexpr int UNITS = CHUNKS * 2;
-    const int g = lane >> 2, tg = lane & 3;
     int it = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
@@ -292,179 +484,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_base = tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16) + acc * BN + col_q * (CHUNKS * 32);
-      uint32_t v[16];
-      tmem_ld_16x256b_x4(t_base, v);
-#pragma unroll 1
-      for (int u = 0; u < UNITS; ++u) {
-        const int ch = u >> 1, half = u & 1;
-        const int n0 = n_blk * BN + (col_q * CHUNKS + ch) * 32 + tg * 8;
-        const bool col_ok = n0 < p.N;   // N is a multiple of 8: groups of 8 columns are all-or-nothing
-        // physical output rows of tile rows (lane_grp*32 + 16*half + 8*hr + g); -1 = nothing to write
-        long long orow2[2];
-#pragma unroll
-        for (int hr = 0; hr < 2; ++hr) {
-          const int r_local = lane_grp * 32 + half * 16 + hr * 8 + g;
-          long long orow;
-          bool ok;
-          if constexpr (!WGRAD) {
-            const int rib = row_in_batch0 + r_local;
-            ok = rib < p.L;
-            orow = static_cast<long long>(b) * p.L + rib;
-          } else {
-            orow = static_cast<long long>(m_blk) * BM + r_local;
-            ok = orow < p.M && have_k;
-          }
-          if (ok && p.out_rows != nullptr) orow = p.out_rows[orow];
-          orow2[hr] = (ok && col_ok) ? orow : -1;
-        }
-        // the global inputs of this unit (fp32/bf16 residual or the saved GELU') are requested BEFORE waiting for TMEM
-        uint4 pre[2][2];
-        const bool pre_resid = p.resid != nullptr;
-        const bool pre_aux = !pre_resid && p.act == 2;
-#pragma unroll
-        for (int hr = 0; hr < 2; ++hr) {
-          pre[hr][0] = make_uint4(0u, 0u, 0u, 0u);
-          pre[hr][1] = make_uint4(0u, 0u, 0u, 0u);
-          if (orow2[hr] >= 0) {
-            if (pre_resid) {
-              const long long rrow = p.resid_mod > 0 ? (orow2[hr] % p.resid_mod) : orow2[hr];
-              if (p.resid_f32) {
-                const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(p.resid) + rrow * p.ld_resid + n0);
-                pre[hr][0] = rp[0];
-                pre[hr][1] = rp[1];
-              } else {
-                pre[hr][0] = *reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p.resid) + rrow * p.ld_resid + n0);
-              }
-            } else if (pre_aux) {
-              pre[hr][0] = *reinterpret_cast<const uint4*>(p.aux + orow2[hr] * p.ld_aux + n0);
-            }
-          }
-        }
-        tmem_ld_wait();
-        // v[4*j + 2*hr + {0,1}] = (row g + 8*hr + 16*half, columns 8*j + 2*tg + {0,1}) of this warp's 32 x 32 chunk
-        float f[2][8];
-#pragma unroll
-        for (int hr = 0; hr < 2; ++hr) {
-          uint32_t a[8];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) { a[2 * j] = v[4 * j + 2 * hr]; a[2 * j + 1] = v[4 * j + 2 * hr + 1]; }
-          quad_transpose(a, tg);   // -> a[0..7] = columns 8*tg .. 8*tg+7 of that row
-#pragma unroll
-          for (int c = 0; c < 8; ++c) f[hr][c] = __uint_as_float(a[c]);
-        }
-        if (u + 1 < UNITS) {
-          const int nu = u + 1;
-          tmem_ld_16x256b_x4(t_base + (static_cast<uint32_t>((nu & 1) * 16) << 16) + (nu >> 1) * 32, v);
-        } else {
-          // every lane has executed tcgen05.wait::ld for its last unit -> hand the accumulator back to the MMA warp
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-        }
-
-        float bias8[8];
-#pragma unroll
-        for (int c = 0; c < 8; ++c) bias8[c] = 0.f;
-        if (p.bias != nullptr && col_ok) {
-          const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n0));
-          const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + 4));
-          bias8[0] = b0.x; bias8[1] = b0.y; bias8[2] = b0.z; bias8[3] = b0.w;
-          bias8[4] = b1.x; bias8[5] = b1.y; bias8[6] = b1.z; bias8[7] = b1.w;
-        }
-        float cs[8];
-#pragma unroll
-        for (int c = 0; c < 8; ++c) cs[c] = 0.f;
-#pragma unroll
-        for (int hr = 0; hr < 2; ++hr) {
-          const long long orow = orow2[hr];
-          if (orow < 0) continue;
-          float* x = f[hr];
-#pragma unroll
-          for (int c = 0; c < 8; ++c) x[c] += bias8[c];
-          if (p.act == 3) {
-            // the Linear output is bf16 under autocast before it meets the fp32 residual / positional table
-#pragma unroll
-            for (int c = 0; c < 8; ++c) x[c] = bf16_round(x[c]);
-          } else if (p.act == 1) {
-            // autocast semantics: the linear/conv output is bf16 and GELU is evaluated on that bf16 value; out2
-            // receives GELU'(h) (bf16), which is all the backward needs of the pre-activation
-#pragma unroll
-            for (int c = 0; c < 8; ++c) x[c] = bf16_round(x[c]);
-            if (p.out2 != nullptr) {
-              float d[8];
-#pragma unroll
-              for (int c = 0; c < 8; ++c) gelu_fast2(x[c], x[c], d[c]);
-              uint4 w;
-              w.x = pack_bf16x2(d[0], d[1]); w.y = pack_bf16x2(d[2], d[3]);
-              w.z = pack_bf16x2(d[4], d[5]); w.w = pack_bf16x2(d[6], d[7]);
-              *reinterpret_cast<uint4*>(p.out2 + orow * p.ld_out2 + n0) = w;
-            } else {
-#pragma unroll
-              for (int c = 0; c < 8; ++c) x[c] = gelu_fast(x[c]);
-            }
-          } else if (p.act == 2) {
-            const uint4 w = pre_aux ? pre[hr][0] : *reinterpret_cast<const uint4*>(p.aux + orow * p.ld_aux + n0);
-            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&w);
-#pragma unroll
-            for (int t = 0; t < 4; ++t) {
-              const float2 hh = __bfloat1622float2(h2[t]);
-              x[2 * t] *= hh.x; x[2 * t + 1] *= hh.y;
-            }
-          }
-          if (p.resid != nullptr) {
-            if (p.resid_f32) {
-              const float4 r0 = *reinterpret_cast<const float4*>(&pre[hr][0]);
-              const float4 r1 = *reinterpret_cast<const float4*>(&pre[hr][1]);
-              x[0] += r0.x; x[1] += r0.y; x[2] += r0.z; x[3] += r0.w;
-              x[4] += r1.x; x[5] += r1.y; x[6] += r1.z; x[7] += r1.w;
-            } else {
-              const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&pre[hr][0]);
-#pragma unroll
-              for (int t = 0; t < 4; ++t) {
-                const float2 hh = __bfloat1622float2(h2[t]);
-                x[2 * t] += hh.x; x[2 * t + 1] += hh.y;
-              }
-            }
-          }
-          if (p.out_f32) {
-            float* op = reinterpret_cast<float*>(p.out) + orow * p.ld_out + n0;
-            if (p.accumulate) {
-              red_add_v4(op, x[0], x[1], x[2], x[3]);
-              red_add_v4(op + 4, x[4], x[5], x[6], x[7]);
-            } else {
-              *reinterpret_cast<float4*>(op) = make_float4(x[0], x[1], x[2], x[3]);
-              *reinterpret_cast<float4*>(op + 4) = make_float4(x[4], x[5], x[6], x[7]);
-            }
-          } else {
-            uint4 w;
-            w.x = pack_bf16x2(x[0], x[1]); w.y = pack_bf16x2(x[2], x[3]);
-            w.z = pack_bf16x2(x[4], x[5]); w.w = pack_bf16x2(x[6], x[7]);
-            *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + orow * p.ld_out + n0) = w;
-            if (p.colsum != nullptr) {   // sums of the values as stored (bf16), like autograd's bias gradient
-              const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&w);
-#pragma unroll
-              for (int t = 0; t < 4; ++t) {
-                const float2 hh = __bfloat1622float2(h2[t]);
-                x[2 * t] = hh.x; x[2 * t + 1] = hh.y;
-              }
-            }
-          }
-#pragma unroll
-          for (int c = 0; c < 8; ++c) cs[c] += x[c];
-        }
-        if (p.colsum != nullptr) {
-#pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            cs[c] += __shfl_xor_sync(0xffffffffu, cs[c], 4);
-            cs[c] += __shfl_xor_sync(0xffffffffu, cs[c], 8);
-            cs[c] += __shfl_xor_sync(0xffffffffu, cs[c], 16);
-          }
-          if (g == 0 && col_ok) {
-            red_add_v4(p.colsum + n0, cs[0], cs[1], cs[2], cs[3]);
-            red_add_v4(p.colsum + n0 + 4, cs[4], cs[5], cs[6], cs[7]);
-          }
-        }
-      }
+      epilogue_tile<BN, WGRAD>(p, t_base, lane, lane_grp, col_q, n_blk, b, row_in_batch0,
+                               static_cast<long long>(m_blk) * BM, have_k, [&]() { mbar_arrive(&tempty_bar[acc]); });
     }
   }
 
@@ -473,6 +494,225 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// =================================================================================================== CTA-pair kernel
+// Same roles as gemm_kernel, but two CTAs of a cluster (one TPC) work on one 256 x BN tile with
+// tcgen05.mma.cta_group::2: each CTA stages its own 128 rows of A and its own HALF of B (BN/2 columns), the leader's
+// single MMA thread drives both tensor cores, and each CTA's TMEM receives its 128 accumulator rows.  Per SM that is
+// 32 KB of operands per 128 x 256 x 64 of MMA work instead of 48 KB (less L2 -> SM traffic, 6 pipeline stages instead
+// of 4 in the same shared memory, and only 2/3 of the shared-memory read bandwidth), which is what the single-CTA
+// kernel runs out of.  Barrier protocol: both producers signal the LEADER's full barriers (TMA .cta_group::2), the
+// leader's commits are multicast to the empty / accumulator-full barriers of both CTAs, the epilogue warps of both
+// CTAs arrive on the leader's accumulator-empty barrier.
+template <int BN>
+struct CfgPair {
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = (BN / 2) * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN == 256) ? 6 : 8;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BN, int MODE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+  using C = CfgPair<BN>;
+  constexpr bool WGRAD = (MODE == 1);
+  constexpr bool B_MN = (MODE != 0);
+  constexpr int STAGES = C::STAGES;
+  constexpr int BMP = 2 * BM;   // rows of a pair tile
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * C::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int pair_id = blockIdx.x >> 1;
+  const int n_pairs = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 2 * kEpiWarps);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc_pair(tmem_slot, 512);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto num_kb = [&](int tile) -> int {
+    if constexpr (!WGRAD) {
+      return p.K / BK;
+    } else {
+      const int split = tile / (p.m_blocks * p.n_blocks);
+      const int kb_total = p.batch * p.kb_per_batch;
+      const int per = (kb_total + p.splits - 1) / p.splits;
+      const int lo = split * per;
+      int hi = lo + per;
+      if (hi > kb_total) hi = kb_total;
+      return hi > lo ? hi - lo : 0;
+    }
+  };
+
+  if (warp < kEpiWarp0) reg_dealloc<kCtrlRegs>();
+  if (warp == 0) {
+    // ======================================================================================= TMA producer (both CTAs)
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = pair_id; tile < p.total_tiles; tile += n_pairs) {
+        if constexpr (!WGRAD) {
+          const int m_blk = tile / p.n_blocks;
+          const int n_blk = tile - m_blk * p.n_blocks;
+          const int b = m_blk / p.mb_per_batch;
+          const int row0 = (m_blk - b * p.mb_per_batch) * BMP + static_cast<int>(rank) * BM;
+          const int nkb = p.K / BK;
+          for (int kb = 0; kb < nkb; ++kb) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* sa = smem + stage * C::STAGE_BYTES;
+            uint8_t* sb = sa + C::A_BYTES;
+            const uint32_t fb = mapa_shared(smem_u32(&full_bar[stage]), 0);
+            int c0, q, po;
+            seg_coords(p.seg, kb * BK, c0, q, po);
+            if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * C::STAGE_BYTES);
+            tma_load_4d_pair(sa, &tmA, fb, c0, q, row0 + po, b);
+            if constexpr (!B_MN) {
+              tma_load_2d_pair(sb, &tmB, fb, kb * BK, n_blk * BN + static_cast<int>(rank) * (BN / 2));
+            } else {
+              const int si = p.seg.width > 0 ? (kb * BK) / p.seg.width : 0;
+              const int r0 = kb * BK - si * (p.seg.width > 0 ? p.seg.width : 0);
+#pragma unroll
+              for (int a = 0; a < BN / 128; ++a)
+                tma_load_2d_pair(sb + a * (BK * 128), &tmB, fb,
+                                 p.segB_col[si] + n_blk * BN + static_cast<int>(rank) * (BN / 2) + a * 64, r0);
+            }
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        } else {
+          const int mn = p.m_blocks * p.n_blocks;
+          const int split = tile / mn;
+          const int rem = tile - split * mn;
+          const int m_blk = rem / p.n_blocks;
+          const int n_blk = rem - m_blk * p.n_blocks;
+          const int kb_total = p.batch * p.kb_per_batch;
+          const int per = (kb_total + p.splits - 1) / p.splits;
+          const int lo = split * per;
+          const int hi = min(lo + per, kb_total);
+          for (int kb = lo; kb < hi; ++kb) {
+            const int b = kb / p.kb_per_batch;
+            const int row0 = (kb - b * p.kb_per_batch) * BK;
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* sa = smem + stage * C::STAGE_BYTES;
+            uint8_t* sb = sa + C::A_BYTES;
+            const uint32_t fb = mapa_shared(smem_u32(&full_bar[stage]), 0);
+            if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * C::STAGE_BYTES);
+#pragma unroll
+            for (int a = 0; a < BM / 64; ++a)
+              tma_load_4d_pair(sa + a * (BK * 128), &tmA, fb, m_blk * BMP + static_cast<int>(rank) * BM + a * 64, 0, row0, b);
+#pragma unroll
+            for (int a = 0; a < BN / 128; ++a) {
+              int c0, q, po;
+              seg_coords(p.seg, n_blk * BN + static_cast<int>(rank) * (BN / 2) + a * 64, c0, q, po);
+              tma_load_4d_pair(sb + a * (BK * 128), &tmB, fb, c0, q, row0 + po, b);
+            }
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ======================================================================================= MMA issuer (leader CTA)
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BMP, BN, WGRAD, B_MN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = pair_id; tile < p.total_tiles; tile += n_pairs, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        const int nkb = num_kb(tile);
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
+          const uint32_t sb = sa + C::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            uint64_t da, db;
+            if constexpr (!WGRAD) da = umma_smem_desc_sw128(sa + k * 32, 0, 1024);
+            else da = umma_smem_desc_sw128(sa + k * 2048, BK * 128, 1024);
+            if constexpr (!B_MN) db = umma_smem_desc_sw128(sb + k * 32, 0, 1024);
+            else db = umma_smem_desc_sw128(sb + k * 2048, BK * 128, 1024);
+            umma_bf16_pair(d_tmem, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit_pair(&empty_bar[stage]);   // frees this smem slot in both CTAs
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_pair(&tfull_bar[acc]);       // accumulator complete -> epilogue warps of both CTAs
+      }
+    }
+  } else if (warp >= kEpiWarp0) {
+    // ======================================================================================= epilogue (both CTAs)
+    reg_alloc<kEpiRegs>();
+    const int ew = warp - kEpiWarp0;
+    const int lane_grp = warp & 3;
+    const int col_q = ew >> 2;
+    constexpr int CHUNKS = BN / 32 / 4;
+    int it = 0;
+    for (int tile = pair_id; tile < p.total_tiles; tile += n_pairs, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      int m_blk, n_blk, b = 0, row_in_batch0 = 0;
+      bool have_k = true;
+      if constexpr (!WGRAD) {
+        m_blk = tile / p.n_blocks;
+        n_blk = tile - m_blk * p.n_blocks;
+        b = m_blk / p.mb_per_batch;
+        row_in_batch0 = (m_blk - b * p.mb_per_batch) * BMP + static_cast<int>(rank) * BM;
+      } else {
+        const int mn = p.m_blocks * p.n_blocks;
+        const int rem = tile % mn;
+        m_blk = rem / p.n_blocks;
+        n_blk = rem - m_blk * p.n_blocks;
+        have_k = num_kb(tile) > 0;
+      }
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_base = tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16) + acc * BN + col_q * (CHUNKS * 32);
+      const uint32_t te = mapa_shared(smem_u32(&tempty_bar[acc]), 0);
+      epilogue_tile<BN, WGRAD>(p, t_base, lane, lane_grp, col_q, n_blk, b, row_in_batch0,
+                               static_cast<long long>(m_blk) * BMP + static_cast<long long>(rank) * BM, have_k,
+                               [&]() { mbar_arrive_cluster(te); });
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, 512);
   }
 }
 
@@ -548,6 +788,21 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmPara
   return check_launch("gemm_tcgen05 launch");
 }
 
+template <int BN, int MODE>
+static int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t st) {
+  static bool attr_set = false;
+  auto kern = gemm_pair_kernel<BN, MODE>;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgPair<BN>::SMEM_BYTES);
+    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(pair): %s", cudaGetErrorString(e)); return WJ_ERR_RUNTIME; }
+    attr_set = true;
+  }
+  int pairs = num_sms() / 2;
+  if (p.total_tiles < pairs) pairs = p.total_tiles;
+  kern<<<2 * pairs, kThreads, CfgPair<BN>::SMEM_BYTES, st>>>(tmA, tmB, p);
+  return check_launch("gemm_tcgen05 pair launch");
+}
+
 static void fill_seg(SegInfo& s, const wj_operand_t* op) {
   s.width = op->seg_width;
   for (int i = 0; i < 4; ++i) { s.q[i] = op->seg_q[i]; s.p[i] = op->seg_p[i]; }
@@ -571,17 +826,30 @@ extern "C" int wj_gemm_bf16(const wj_operand_t* A, const void* W, int64_t ldw, i
   if (L <= 0 || batch <= 0) return WJ_OK;
   if (K % BK != 0 || N % 8 != 0) { set_error("wj_gemm_bf16: K must be a multiple of 64 and N of 8 (K=%d N=%d)", K, N); return WJ_ERR_ARG; }
   if (A->seg_width > 0 && (A->seg_width % BK != 0 || K > 4 * A->seg_width)) { set_error("wj_gemm_bf16: bad segment width"); return WJ_ERR_ARG; }
+  const bool pair = block_n < 0;   // -128 / -256: CTA-pair kernel (256-row tiles, tcgen05 cta_group::2)
+  if (pair) block_n = -block_n;
   if (block_n == 0) block_n = (N % 256 == 0 || N > 1024) ? 256 : 128;
   if (block_n != 128 && block_n != 256) { set_error("wj_gemm_bf16: block_n must be 128 or 256"); return WJ_ERR_ARG; }
   CUtensorMap tmA, tmB;
   const uint32_t boxA[4] = {BK, 1, BM, 1};
   int rc = encode_map(&tmA, A, boxA);
   if (rc) return rc;
-  rc = encode_map_2d(&tmB, W, (uint64_t)K, (uint64_t)N, (uint64_t)ldw * 2, BK, (uint32_t)block_n);
+  rc = encode_map_2d(&tmB, W, (uint64_t)K, (uint64_t)N, (uint64_t)ldw * 2, BK, (uint32_t)(pair ? block_n / 2 : block_n));
   if (rc) return rc;
   GemmParams p;
   memset(&p, 0, sizeof(p));
   p.L = L; p.batch = batch; p.N = N; p.K = K;
+  if (pair) {
+    p.mb_per_batch = (L + 2 * BM - 1) / (2 * BM);
+    p.m_blocks = batch * p.mb_per_batch;
+    p.n_blocks = (N + block_n - 1) / block_n;
+    p.total_tiles = p.m_blocks * p.n_blocks;
+    fill_seg(p.seg, A);
+    fill_epilogue(p, epi);
+    cudaStream_t stp = reinterpret_cast<cudaStream_t>(stream);
+    if (block_n == 256) return launch_pair<256, 0>(tmA, tmB, p, stp);
+    return launch_pair<128, 0>(tmA, tmB, p, stp);
+  }
   p.mb_per_batch = (L + BM - 1) / BM;
   p.m_blocks = batch * p.mb_per_batch;
   p.n_blocks = (N + block_n - 1) / block_n;
