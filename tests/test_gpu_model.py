@@ -155,38 +155,45 @@ def test_forward_matches_live_oracle_on_fresh_inputs():
 
 
 def test_fused_train_step_equals_bridge_plus_torch_adamw():
-    """train_step (hand-written backward + fused clip/AdamW/EMA) == forward().backward() + clip_grad_norm_ +
-    torch.optim.AdamW + _step_teacher on a twin model (train.py:177-178, wavjepa/jepa.py:215-228, :330-331)."""
+    """train_step (hand-written backward + fused clip/AdamW/EMA) against the reference-style loop on a twin model
+    (train.py:177-178, wavjepa/jepa.py:215-228, :330-331):
+      (1) its gradients == the autograd-bridge gradients of forward().backward() up to the bf16 noise floor (fp32 atomics
+          in the predictor-input scatter flip a few bf16 roundings, which the student / conv backward amplifies to
+          ~4e-3 on the conv-0 weight -- two runs of the SAME path differ by as much);
+      (2) its parameter update == clip_grad_norm_ + torch.optim.AdamW applied to those same gradients (tight);
+      (3) the teacher moved by the EMA of the PRE-step student."""
     cfg = jo.Cfg()
     sd = jo.make_state_dict(cfg, seed=5)
     inp = oi.training_inputs(cfg, 1, 4, seed=31, masker="audioset")
     a = build_model(cfg, sd)
     b = build_model(cfg, sd)
     a.global_step = b.global_step = 50000          # lr(0) == 0 would hide the optimizer (warm-up from 0)
+    lr = b.lr_at(50000)
     audio = inp["audio"].to(DEV).bfloat16()
     c_m, t_m, v_m = (inp[k].to(DEV) for k in ("ctx_masks", "target_indices", "ctx_and_target_masks"))
     loss_a = a.train_step(audio, c_m, t_m, v_m)
+    grads_a = {n: a._view(a._flat_g, n).clone() for n in a._train_names}
     out = b(audio, c_m, t_m, v_m)
     out["loss"].backward()
     assert abs(loss_a.item() - out["loss"].item()) < 1e-6
+    pb = dict(b.named_parameters())
+    for n_, g in grads_a.items():
+        assert rel(g.cpu().numpy(), pb[n_].grad.cpu().numpy()) < GRAD_TOL, n_
+    # (2) the reference optimizer step on model b, fed with model a's gradients
     trainables = [p for p in b.parameters() if p.requires_grad]
-    opt = torch.optim.AdamW(trainables, lr=b.lr_at(50000), betas=(0.9, 0.98), eps=1e-6, weight_decay=0.04)
+    for n_, g in grads_a.items():
+        pb[n_].grad = g.clone()
+    opt = torch.optim.AdamW(trainables, lr=lr, betas=(0.9, 0.98), eps=1e-6, weight_decay=0.04)
     for p_ in trainables:   # the optimizer has taken 50000 steps (all with zero moments here): same bias correction
         opt.state[p_] = dict(step=torch.tensor(50000.0), exp_avg=torch.zeros_like(p_), exp_avg_sq=torch.zeros_like(p_))
     b._step_teacher()
     torch.nn.utils.clip_grad_norm_(trainables, 5.0)
     opt.step()
-    pa, pb = dict(a.named_parameters()), dict(b.named_parameters())
-    lr = b.lr_at(50000)
+    pa = dict(a.named_parameters())
     for n_ in pa:
-        # fp32 atomics (split-K wgrad, conv0 reductions) make two gradient evaluations differ in the last bits, and
-        # Adam's normalised update g / (|g| + eps) amplifies that for the few near-zero gradients: compare the UPDATES
-        # in relative L2 per tensor and bound the worst element by a fraction of one step
-        p0 = sd[n_].to(DEV)
-        da, db_ = pa[n_].detach() - p0, pb[n_].detach() - p0
-        if db_.norm() > 0:
-            assert ((da - db_).norm() / db_.norm()).item() < 2e-3, n_
-        assert (da - db_).abs().max().item() <= 0.25 * lr, n_
+        d = (pa[n_].detach() - pb[n_].detach()).abs().max().item()
+        scale = pb[n_].detach().abs().max().item() + 1e-12
+        assert d <= 2e-6 * scale + 1e-3 * lr, (n_, d)
     # weights moved, teacher moved
     moved = (pa["encoder.layers.0.linear1.weight"].detach().cpu() - sd["encoder.layers.0.linear1.weight"]).abs().max()
     assert moved > 0
