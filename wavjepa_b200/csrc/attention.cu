@@ -205,7 +205,7 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(const bf16* __restrict__ 
 // One CTA per (sequence, head); Q, K, V, dO of the whole sequence live in smem (NPAD rows each).
 //   phase A: warps own 16-query blocks -> dQ;  phase B: warps own 16-key blocks -> dK, dV.  No atomics.
 template <int DH>
-__global__ void __launch_bounds__(128, (DH == 32 ? 4 : 2)) attn_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ out,
+__global__ void __launch_bounds__(128) attn_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ out,
                                                        const bf16* __restrict__ dout, const float* __restrict__ lse2,
                                                        const int* __restrict__ cu, int D, int H, int NPAD, float scale,
                                                        float scale_log2, bf16* __restrict__ dqkv) {
@@ -363,7 +363,7 @@ extern "C" int wj_attn_varlen_fwd(const void* qkv_bf16, const int* cu_seqlens, i
   if (smem > 227 * 1024) { set_error("wj_attn_varlen_fwd: sequence of %d tokens (head dim %d) exceeds the shared-memory resident design", max_len, dh); return WJ_ERR_ARG; }
   const float scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(dh));
   dim3 grid(H, n_seqs);
-  const int threads = max_len > 96 ? 256 : 128;   // one warp per 16-query block per round
+  const int threads = max_len > 144 ? 256 : 128;   // long sequences (teacher / inference: 200 tokens): 8 warps share K/V
   const bf16* q = reinterpret_cast<const bf16*>(qkv_bf16);
   bf16* o = reinterpret_cast<bf16*>(out_bf16);
   cudaError_t e;
