@@ -280,6 +280,13 @@ def run_native(args):
                     "peak_source": peaks["source"] + ", sustained figure (kernel timed inside a long step)",
                     "launches_per_step": g_calls, "avg_launch_ms": round(g_ms / max(g_calls, 1), 4),
                     "flops_per_step": g_flops, "share_of_step": round(g_ms / prof_total, 4), "traffic": None}
+        tr = os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")
+        if os.path.exists(tr):   # dram__bytes_read.sum + dram__bytes_write.sum over the GEMM launches of one step (ncu)
+            t = json.load(open(tr))
+            roofline["traffic"] = t["dram_bytes_per_launch_avg"]
+            roofline["traffic_note"] = ("average DRAM bytes per GEMM launch, ncu over the %d launches of one step "
+                                        "(profiles/r01_gemm_traffic.json); algorithmic bytes/launch (A + W + outputs) "
+                                        "are of the same order: the kernel is tensor-bound, not HBM-bound" % t["launches"])
         out = {"metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
                "warmup": args.warmup, "ms_per_step": round(ms_step, 3), "higher_is_better": True, "scaling": "weak",
                "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
