@@ -66,13 +66,13 @@ __device__ __forceinline__ void load_a_frags(uint32_t (&f)[DH / 16][4], const bf
 // C[16 x 64] = A[16 x DH] * Bm[64 x DH]^T  with Bm rows in smem (row-major, padded).  Only the first `ntiles`
 // 8-column tiles (rounded up to a pair) are computed; the others are zeroed.  B fragments come from ldmatrix.x4:
 // one instruction feeds two n-tiles of one 16-deep k-step.
-template <int DH>
-__device__ __forceinline__ void mm_abT(float (&c)[8][4], const uint32_t (&a)[DH / 16][4], const bf16* sB, int brow0,
+template <int DH, int NT = 8>
+__device__ __forceinline__ void mm_abT(float (&c)[NT][4], const uint32_t (&a)[DH / 16][4], const bf16* sB, int brow0,
                                        int lane, int ntiles) {
   constexpr int PITCH = DH + 8;
   const bf16* base = sB + (brow0 + (lane & 7) + ((lane >> 4) << 3)) * PITCH + ((lane >> 3) & 1) * 8;
 #pragma unroll
-  for (int nt = 0; nt < 8; nt += 2) {
+  for (int nt = 0; nt < NT; nt += 2) {
     c[nt][0] = c[nt][1] = c[nt][2] = c[nt][3] = 0.f;
     c[nt + 1][0] = c[nt + 1][1] = c[nt + 1][2] = c[nt + 1][3] = 0.f;
     if (nt < ntiles) {
@@ -89,12 +89,12 @@ __device__ __forceinline__ void mm_abT(float (&c)[8][4], const uint32_t (&a)[DH 
 
 // acc[16 x DH] += P[16 x 64] * Bm[64 x DH]  (P given as C-fragments, packed on the fly; Bm rows in smem); only the
 // first `kchunks` 16-row chunks of Bm contribute.
-template <int DH>
-__device__ __forceinline__ void mm_pb(float (&acc)[DH / 8][4], const float (&pf)[8][4], const bf16* sB, int brow0,
+template <int DH, int NT = 8>
+__device__ __forceinline__ void mm_pb(float (&acc)[DH / 8][4], const float (&pf)[NT][4], const bf16* sB, int brow0,
                                       int lane, int kchunks) {
   constexpr int PITCH = DH + 8;
 #pragma unroll
-  for (int kk = 0; kk < 4; ++kk) {
+  for (int kk = 0; kk < NT / 2; ++kk) {
     if (kk < kchunks) {
       uint32_t a[4];
       a[0] = pack_bf16x2(pf[2 * kk][0], pf[2 * kk][1]);
@@ -205,11 +205,13 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(const bf16* __restrict__ 
 // One CTA per (sequence, head); Q, K, V, dO of the whole sequence live in smem (NPAD rows each).
 //   phase A: warps own 16-query blocks -> dQ;  phase B: warps own 16-key blocks -> dK, dV.  No atomics.
 template <int DH>
-__global__ void __launch_bounds__(128) attn_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ out,
+__global__ void __launch_bounds__(128, (DH == 32 ? 4 : 2)) attn_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ out,
                                                        const bf16* __restrict__ dout, const float* __restrict__ lse2,
                                                        const int* __restrict__ cu, int D, int H, int NPAD, float scale,
                                                        float scale_log2, bf16* __restrict__ dqkv) {
   constexpr int PITCH = DH + 8;
+  constexpr int NT = (DH == 32) ? 4 : 8;   // 8-wide tiles per inner block: 32-wide blocks keep the DH=32 kernel at
+  constexpr int KB = NT * 8;               // <= 128 registers (4 CTAs / SM); the lse / delta arrays stay padded to 64
   extern __shared__ __align__(16) uint8_t smem_attn[];
   bf16* sQ = reinterpret_cast<bf16*>(smem_attn);
   bf16* sK = sQ + NPAD * PITCH;
@@ -264,14 +266,14 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(const bf16* __restrict__ 
     float dq[DH / 8][4];
 #pragma unroll
     for (int i = 0; i < DH / 8; ++i) dq[i][0] = dq[i][1] = dq[i][2] = dq[i][3] = 0.f;
-    for (int kb = 0; kb * 64 < n; ++kb) {
-      float sc[8][4], dp[8][4];
-      const int valid = min(64, n - kb * 64);
-      mm_abT<DH>(sc, qf, sK, kb * 64, lane, (valid + 7) >> 3);
-      mm_abT<DH>(dp, dof, sV, kb * 64, lane, (valid + 7) >> 3);
+    for (int kb = 0; kb * KB < n; ++kb) {
+      float sc[NT][4], dp[NT][4];
+      const int valid = min(KB, n - kb * KB);
+      mm_abT<DH, NT>(sc, qf, sK, kb * KB, lane, (valid + 7) >> 3);
+      mm_abT<DH, NT>(dp, dof, sV, kb * KB, lane, (valid + 7) >> 3);
 #pragma unroll
-      for (int nt = 0; nt < 8; ++nt) {
-        const int key = kb * 64 + nt * 8 + 2 * tg;
+      for (int nt = 0; nt < NT; ++nt) {
+        const int key = kb * KB + nt * 8 + 2 * tg;
         const float p0 = key < n ? ex2_approx(sc[nt][0] * scale_log2 - la) : 0.f;
         const float p1 = key + 1 < n ? ex2_approx(sc[nt][1] * scale_log2 - la) : 0.f;
         const float p2 = key < n ? ex2_approx(sc[nt][2] * scale_log2 - lb) : 0.f;
@@ -279,7 +281,7 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(const bf16* __restrict__ 
         sc[nt][0] = p0 * (dp[nt][0] - da); sc[nt][1] = p1 * (dp[nt][1] - da);
         sc[nt][2] = p2 * (dp[nt][2] - db); sc[nt][3] = p3 * (dp[nt][3] - db);
       }
-      mm_pb<DH>(dq, sc, sK, kb * 64, lane, (valid + 15) >> 4);
+      mm_pb<DH, NT>(dq, sc, sK, kb * KB, lane, (valid + 15) >> 4);
     }
     const int ra = rb * 16 + g, rbb = ra + 8;
     if (ra < n) {
@@ -306,14 +308,14 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(const bf16* __restrict__ 
       dv[i][0] = dv[i][1] = dv[i][2] = dv[i][3] = 0.f;
     }
     const bool ka = cb * 16 + g < n, kbv = cb * 16 + g + 8 < n;
-    for (int qb = 0; qb * 64 < n; ++qb) {
-      float st[8][4], dpt[8][4];
-      const int valid = min(64, n - qb * 64);
-      mm_abT<DH>(st, kf, sQ, qb * 64, lane, (valid + 7) >> 3);     // S^T tile: rows = keys, cols = queries
-      mm_abT<DH>(dpt, vf, sdO, qb * 64, lane, (valid + 7) >> 3);   // dP^T tile
+    for (int qb = 0; qb * KB < n; ++qb) {
+      float st[NT][4], dpt[NT][4];
+      const int valid = min(KB, n - qb * KB);
+      mm_abT<DH, NT>(st, kf, sQ, qb * KB, lane, (valid + 7) >> 3);     // S^T tile: rows = keys, cols = queries
+      mm_abT<DH, NT>(dpt, vf, sdO, qb * KB, lane, (valid + 7) >> 3);   // dP^T tile
 #pragma unroll
-      for (int nt = 0; nt < 8; ++nt) {
-        const int q = qb * 64 + nt * 8 + 2 * tg;
+      for (int nt = 0; nt < NT; ++nt) {
+        const int q = qb * KB + nt * 8 + 2 * tg;
         const float l0 = sLse[q], l1 = sLse[q + 1], d0 = sDl[q], d1 = sDl[q + 1];
         const bool q0 = q < n, q1 = q + 1 < n;
         const float p0 = (ka && q0) ? ex2_approx(st[nt][0] * scale_log2 - l0) : 0.f;
@@ -324,8 +326,8 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(const bf16* __restrict__ 
         dpt[nt][0] = p0 * (dpt[nt][0] - d0); dpt[nt][1] = p1 * (dpt[nt][1] - d1);
         dpt[nt][2] = p2 * (dpt[nt][2] - d0); dpt[nt][3] = p3 * (dpt[nt][3] - d1);
       }
-      mm_pb<DH>(dv, st, sdO, qb * 64, lane, (valid + 15) >> 4);
-      mm_pb<DH>(dk, dpt, sQ, qb * 64, lane, (valid + 15) >> 4);
+      mm_pb<DH, NT>(dv, st, sdO, qb * KB, lane, (valid + 15) >> 4);
+      mm_pb<DH, NT>(dk, dpt, sQ, qb * KB, lane, (valid + 15) >> 4);
     }
     const int ra = cb * 16 + g, rbb = ra + 8;
     if (ra < n) {
