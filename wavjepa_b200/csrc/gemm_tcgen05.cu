@@ -43,6 +43,7 @@ struct GemmParams {
   int n_blocks;
   int total_tiles;
   int splits;        // wgrad: split of the reduction
+  int b_single;      // wgrad: the BN columns of a B tile lie in one segment -> one TMA per k-block
   int kb_per_batch;  // wgrad: ceil(L / 64)
   SegInfo seg;       // normal/dgrad: segments of A's K;  wgrad: segments of B's N
   int segB_col[4];   // dgrad: column offset into W for each reduction segment
@@ -292,7 +293,8 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t t_ba
 // MODE 0: A K-major, B K-major (fwd)   MODE 1: A, B MN-major (wgrad)   MODE 2: A K-major, B MN-major (dgrad)
 template <int BN, int MODE>
 __global__ void __launch_bounds__(kThreads, 1)
-gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+            const __grid_constant__ CUtensorMap tmB1, const GemmParams p) {
   using C = Cfg<BN>;
   constexpr bool WGRAD = (MODE == 1);
   constexpr bool B_MN = (MODE != 0);
@@ -370,12 +372,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             if constexpr (!B_MN) {
               tma_load_2d(sb, &tmB, &full_bar[stage], kb * BK, n_blk * BN);
             } else {
-              // dgrad: W is [reduction rows, output cols] row-major -> BN/64 MN-major atoms of 64 reduction rows
+              // dgrad: W is [reduction rows, output cols] row-major -> BN/64 MN-major atoms of 64 reduction rows, all
+              // fetched by ONE TMA instruction through a 3-D view {64 cols, rows, column atoms} (the TMA unit is
+              // instruction-rate limited: 5-6 small boxes per k-block held these modes at ~600-900 TFLOP/s)
               const int si = p.seg.width > 0 ? (kb * BK) / p.seg.width : 0;
               const int r0 = kb * BK - si * (p.seg.width > 0 ? p.seg.width : 0);
-#pragma unroll
-              for (int a = 0; a < BN / 64; ++a)
-                tma_load_2d(sb + a * (BK * 128), &tmB, &full_bar[stage], p.segB_col[si] + n_blk * BN + a * 64, r0);
+              tma_load_3d(sb, &tmB, &full_bar[stage], 0, r0, (p.segB_col[si] + n_blk * BN) >> 6);
             }
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
@@ -396,16 +398,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             uint8_t* sa = smem + stage * C::STAGE_BYTES;
             uint8_t* sb = sa + C::A_BYTES;
             mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
-            // A operand: dY[b, row, m] (m contiguous): two 64-wide MN atoms of 64 reduction rows each
-#pragma unroll
-            for (int a = 0; a < BM / 64; ++a)
-              tma_load_4d(sa + a * (BK * 128), &tmA, &full_bar[stage], m_blk * BM + a * 64, 0, row0, b);
-            // B operand: X[b, row + p, (q), n] : BN/64 atoms, each may live in a different segment
-#pragma unroll
-            for (int a = 0; a < BN / 64; ++a) {
+            // A operand: dY[b, row, m] (m contiguous): BM/64 MN atoms of 64 reduction rows, one 5-D TMA
+            // {64 cols, rows, column atoms, q, batch}
+            tma_load_5d(sa, &tmA, &full_bar[stage], 0, row0, (m_blk * BM) >> 6, 0, b);
+            // B operand: X[b, row + p, (q), n]: BN/64 atoms; one TMA when the tile lies inside one segment
+            if (p.b_single) {
               int c0, q, po;
-              seg_coords(p.seg, n_blk * BN + a * 64, c0, q, po);
-              tma_load_4d(sb + a * (BK * 128), &tmB, &full_bar[stage], c0, q, row0 + po, b);
+              seg_coords(p.seg, n_blk * BN, c0, q, po);
+              tma_load_5d(sb, &tmB, &full_bar[stage], 0, row0 + po, c0 >> 6, q, b);
+            } else {
+#pragma unroll
+              for (int a = 0; a < BN / 64; ++a) {
+                int c0, q, po;
+                seg_coords(p.seg, n_blk * BN + a * 64, c0, q, po);
+                tma_load_5d(sb + a * (BK * 128), &tmB1, &full_bar[stage], 0, row0 + po, c0 >> 6, q, b);
+              }
             }
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
@@ -773,10 +780,48 @@ static int encode_map_2d(CUtensorMap* tm, const void* ptr, uint64_t inner, uint6
   return WJ_OK;
 }
 
+// MN-major operand view {64 contiguous columns, rows, column atoms (stride 128 B), q, batch}: a box {64, 64, atoms, 1, 1}
+// lands in smem as [atom][64 rows][128 B] = the UMMA MN-major 128B-swizzle layout, with ONE TMA instruction.
+static int encode_map_mn5(CUtensorMap* tm, const wj_operand_t* op, uint32_t atoms_box) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)"); return WJ_ERR_RUNTIME; }
+  if (op->dim[0] % 64 != 0) { set_error("MN-major operand: column count %lld is not a multiple of 64", (long long)op->dim[0]); return WJ_ERR_ARG; }
+  cuuint64_t dims[5] = {64, (cuuint64_t)op->dim[2], (cuuint64_t)(op->dim[0] / 64), (cuuint64_t)op->dim[1], (cuuint64_t)op->dim[3]};
+  cuuint64_t strides[4] = {(cuuint64_t)op->stride_bytes[1], 128, (cuuint64_t)op->stride_bytes[0], (cuuint64_t)op->stride_bytes[2]};
+  cuuint32_t bx[5] = {64, 64, atoms_box, 1, 1}, es[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(op->ptr), dims, strides, bx, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(mn5) failed: %d (dims %llu %llu %llu %llu %llu strides %llu %llu %llu %llu)", (int)r,
+              dims[0], dims[1], dims[2], dims[3], dims[4], strides[0], strides[1], strides[2], strides[3]);
+    return WJ_ERR_RUNTIME;
+  }
+  return WJ_OK;
+}
+static int encode_map_mn3(CUtensorMap* tm, const void* ptr, uint64_t rows, uint64_t cols, uint64_t stride_bytes,
+                          uint32_t atoms_box) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)"); return WJ_ERR_RUNTIME; }
+  cuuint64_t dims[3] = {64, rows, (cols + 63) / 64};
+  cuuint64_t strides[2] = {stride_bytes, 128};
+  cuuint32_t bx[3] = {64, 64, atoms_box}, es[3] = {1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, bx, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(mn3) failed: %d (dims %llu %llu %llu strides %llu %llu)", (int)r, dims[0], dims[1],
+              dims[2], strides[0], strides[1]);
+    return WJ_ERR_RUNTIME;
+  }
+  return WJ_OK;
+}
+
 static int num_sms() { return sm_count(); }
 
 template <int BN, int MODE>
-static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int grid, cudaStream_t st) {
+static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmB1, const GemmParams& p, int grid,
+                  cudaStream_t st) {
   static bool attr_set = false;
   auto kern = gemm_kernel<BN, MODE>;
   if (!attr_set) {
@@ -784,7 +829,7 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmPara
     if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return WJ_ERR_RUNTIME; }
     attr_set = true;
   }
-  kern<<<grid, kThreads, Cfg<BN>::SMEM_BYTES, st>>>(tmA, tmB, p);
+  kern<<<grid, kThreads, Cfg<BN>::SMEM_BYTES, st>>>(tmA, tmB, tmB1, p);
   return check_launch("gemm_tcgen05 launch");
 }
 
@@ -858,8 +903,8 @@ extern "C" int wj_gemm_bf16(const wj_operand_t* A, const void* W, int64_t ldw, i
   fill_epilogue(p, epi);
   const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (block_n == 256) return launch<256, 0>(tmA, tmB, p, grid, st);
-  return launch<128, 0>(tmA, tmB, p, grid, st);
+  if (block_n == 256) return launch<256, 0>(tmA, tmB, tmB, p, grid, st);
+  return launch<128, 0>(tmA, tmB, tmB, p, grid, st);
 }
 
 // dW[m, vc] (+)= sum_{b, t} dY(b, t; m) * X(vc; t, b)      fp32 output, reduce-add when splits > 1 or accumulate.
@@ -870,11 +915,12 @@ extern "C" int wj_gemm_wgrad_bf16(const wj_operand_t* dY, const wj_operand_t* X,
   const int block_n = (N % 256 == 0) ? 256 : ((N % 128 == 0) ? 128 : 0);
   if (block_n == 0) { set_error("wj_gemm_wgrad_bf16: N must be a multiple of 128"); return WJ_ERR_ARG; }
   if (X->seg_width > 0 && X->seg_width % 64 != 0) { set_error("wj_gemm_wgrad_bf16: bad segment width"); return WJ_ERR_ARG; }
-  CUtensorMap tmA, tmB;
-  const uint32_t box[4] = {64, 1, BK, 1};
-  int rc = encode_map(&tmA, dY, box);
+  CUtensorMap tmA, tmB, tmB1;
+  int rc = encode_map_mn5(&tmA, dY, BM / 64);
   if (rc) return rc;
-  rc = encode_map(&tmB, X, box);
+  rc = encode_map_mn5(&tmB, X, (uint32_t)(block_n / 64));
+  if (rc) return rc;
+  rc = encode_map_mn5(&tmB1, X, 1);
   if (rc) return rc;
   GemmParams p;
   memset(&p, 0, sizeof(p));
@@ -905,6 +951,7 @@ extern "C" int wj_gemm_wgrad_bf16(const wj_operand_t* dY, const wj_operand_t* X,
   p.splits = splits;
   p.total_tiles = p.m_blocks * p.n_blocks * splits;
   fill_seg(p.seg, X);
+  p.b_single = (X->seg_width == 0 || X->seg_width % block_n == 0) ? 1 : 0;
   p.out = out; p.ld_out = ld_out; p.out_f32 = 1;
   p.accumulate = (accumulate || splits > 1) ? 1 : 0;
   if (splits > 1 && !accumulate) {
@@ -915,8 +962,8 @@ extern "C" int wj_gemm_wgrad_bf16(const wj_operand_t* dY, const wj_operand_t* X,
   }
   const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (block_n == 256) return launch<256, 1>(tmA, tmB, p, grid, st);
-  return launch<128, 1>(tmA, tmB, p, grid, st);
+  if (block_n == 256) return launch<256, 1>(tmA, tmB, tmB1, p, grid, st);
+  return launch<128, 1>(tmA, tmB, tmB1, p, grid, st);
 }
 
 // out[b*L + t, n] = epilogue( sum_{s, r} A(s*width + r; t, b) * W[r, col_off[s] + n] ),  W bf16 row-major [R, ldw]:
@@ -933,7 +980,7 @@ extern "C" int wj_gemm_dgrad_bf16(const wj_operand_t* A, const void* W, int64_t 
   const uint32_t boxA[4] = {BK, 1, BM, 1};
   int rc = encode_map(&tmA, A, boxA);
   if (rc) return rc;
-  rc = encode_map_2d(&tmB, W, (uint64_t)w_cols, (uint64_t)w_rows, (uint64_t)ldw * 2, 64, 64);
+  rc = encode_map_mn3(&tmB, W, (uint64_t)w_rows, (uint64_t)w_cols, (uint64_t)ldw * 2, (uint32_t)(block_n / 64));
   if (rc) return rc;
   GemmParams p;
   memset(&p, 0, sizeof(p));
@@ -947,6 +994,6 @@ extern "C" int wj_gemm_dgrad_bf16(const wj_operand_t* A, const void* W, int64_t 
   fill_epilogue(p, epi);
   const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (block_n == 256) return launch<256, 2>(tmA, tmB, p, grid, st);
-  return launch<128, 2>(tmA, tmB, p, grid, st);
+  if (block_n == 256) return launch<256, 2>(tmA, tmB, tmB, p, grid, st);
+  return launch<128, 2>(tmA, tmB, tmB, p, grid, st);
 }
