@@ -64,6 +64,12 @@ struct GemmParams {
   int act;           // 0 none; 1: h = bf16(acc + bias), out2 = gelu'(h), v = gelu(h); 2: v = acc * aux; 3: v = bf16(v)
   const int* out_rows;  // optional row indirection for the output / residual / aux rows (scatter), -1 = skip
   float* colsum;        // optional: colsum[n] += sum over rows of the stored output (bias gradients)
+  int tma_store;        // bf16 outputs without residual / aux / scatter: staged in smem and written by TMA stores
+};
+
+struct OutMaps {
+  CUtensorMap o;    // out  as {N, L, batch} bf16, box {32, 32, 1}, 64-byte swizzle
+  CUtensorMap o2;   // out2 (saved GELU')
 };
 
 constexpr int BM = 128;
@@ -80,7 +86,8 @@ struct Cfg {
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (BN == 256) ? 4 : ((BN == 128) ? 6 : 8);
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int STAGING_OFF = STAGES * STAGE_BYTES + 1024;   // barriers live in the 1 KB before it
+  static constexpr int SMEM_BYTES = STAGING_OFF + 1024 /*align slack*/ + kEpiWarps * 2048 /*TMA-store staging*/;
 };
 
 __device__ __forceinline__ void seg_coords(const SegInfo& s, int vc, int& c0, int& q, int& p) {
@@ -290,11 +297,97 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t t_ba
   }
 }
 
+// bf16 outputs with nothing but bias / GELU in the epilogue (QKV projections, MLP fc1 fwd, conv fwd, plain dgrads) skip
+// the per-element addressing, transposes and predicates of the generic path: tcgen05.ld.32x32b (row per lane) -> math
+// -> 4 x st.shared.v4 into a 64B-swizzled 32 x 32 staging tile (2 KB per warp) -> ONE TMA store per 32 x 32 chunk
+// (the hardware clips rows >= L and columns >= N).  ~5x fewer issued instructions per element than the generic path.
+template <int BN, typename Arrive>
+__device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const OutMaps& om, uint32_t t_base, uint8_t* stg,
+                                                  int lane, int lane_grp, int col_q, int n_blk, int b, int row_in_batch0,
+                                                  Arrive arrive) {
+  constexpr int CHUNKS = BN / 32 / 4;
+  const int row0 = row_in_batch0 + lane_grp * 32;
+  uint32_t v[32];
+  tmem_ld_32x32(t_base, v);
+#pragma unroll 1
+  for (int ch = 0; ch < CHUNKS; ++ch) {
+    tmem_ld_wait();
+    float f[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+    if (ch + 1 < CHUNKS) {
+      tmem_ld_32x32(t_base + (ch + 1) * 32, v);
+    } else {
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) arrive();
+    }
+    const int n0 = n_blk * BN + (col_q * CHUNKS + ch) * 32;
+    if (n0 >= p.N || row0 >= p.L) continue;   // warp-uniform
+    if (p.bias != nullptr) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        if (n0 + j < p.N) {
+          const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
+          f[j] += bb.x; f[j + 1] += bb.y; f[j + 2] += bb.z; f[j + 3] += bb.w;
+        }
+      }
+    }
+    uint32_t w[16], w2[16];
+    if (p.act == 1) {
+      // autocast semantics: the linear/conv output is bf16 and GELU is evaluated on that bf16 value
+      if (p.out2 != nullptr) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          float g0, d0, g1, d1;
+          gelu_fast2(bf16_round(f[j]), g0, d0);
+          gelu_fast2(bf16_round(f[j + 1]), g1, d1);
+          w[j >> 1] = pack_bf16x2(g0, g1);
+          w2[j >> 1] = pack_bf16x2(d0, d1);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) w[j >> 1] = pack_bf16x2(gelu_fast(bf16_round(f[j])), gelu_fast(bf16_round(f[j + 1])));
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; j += 2) w[j >> 1] = pack_bf16x2(f[j], f[j + 1]);
+    }
+    // staging row = lane (64 B), 16-byte chunk c stored at c ^ ((row >> 1) & 3)  (CU_TENSOR_MAP_SWIZZLE_64B)
+    uint8_t* srow = stg + lane * 64;
+    const int sw = (lane >> 1) & 3;
+    if (lane == 0) bulk_wait_read0();   // the previous TMA store of this warp has finished reading the staging tile
+    __syncwarp();
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+      *reinterpret_cast<uint4*>(srow + ((c ^ sw) << 4)) = make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      tma_store_3d(&om.o, stg, n0, row0, b);
+      bulk_commit();
+    }
+    if (p.act == 1 && p.out2 != nullptr) {
+      if (lane == 0) bulk_wait_read0();
+      __syncwarp();
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        *reinterpret_cast<uint4*>(srow + ((c ^ sw) << 4)) = make_uint4(w2[4 * c], w2[4 * c + 1], w2[4 * c + 2], w2[4 * c + 3]);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_3d(&om.o2, stg, n0, row0, b);
+        bulk_commit();
+      }
+    }
+  }
+}
+
 // MODE 0: A K-major, B K-major (fwd)   MODE 1: A, B MN-major (wgrad)   MODE 2: A K-major, B MN-major (dgrad)
 template <int BN, int MODE>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-            const __grid_constant__ CUtensorMap tmB1, const GemmParams p) {
+            const __grid_constant__ CUtensorMap tmB1, const __grid_constant__ OutMaps om, const GemmParams p) {
   using C = Cfg<BN>;
   constexpr bool WGRAD = (MODE == 1);
   constexpr bool B_MN = (MODE != 0);
@@ -491,9 +584,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_base = tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16) + acc * BN + col_q * (CHUNKS * 32);
+      if constexpr (!WGRAD) {
+        if (p.tma_store) {
+          epilogue_tile_tma<BN>(p, om, t_base, smem + C::STAGING_OFF + ew * 2048, lane, lane_grp, col_q, n_blk, b,
+                                row_in_batch0, [&]() { mbar_arrive(&tempty_bar[acc]); });
+          continue;
+        }
+      }
       epilogue_tile<BN, WGRAD>(p, t_base, lane, lane_grp, col_q, n_blk, b, row_in_batch0,
                                static_cast<long long>(m_blk) * BM, have_k, [&]() { mbar_arrive(&tempty_bar[acc]); });
     }
+    if (p.tma_store && lane == 0) bulk_wait0();   // all TMA stores of this warp are complete before smem goes away
   }
 
   tc_fence_before();
@@ -817,11 +918,47 @@ static int encode_map_mn3(CUtensorMap* tm, const void* ptr, uint64_t rows, uint6
   return WJ_OK;
 }
 
+// bf16 output viewed as {N, L, batch} for the TMA-store epilogue (box 32 x 32, 64-byte swizzle)
+static int encode_out_map(CUtensorMap* tm, const void* ptr, int N, int L, int batch, int64_t ld) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)"); return WJ_ERR_RUNTIME; }
+  cuuint64_t dims[3] = {(cuuint64_t)N, (cuuint64_t)L, (cuuint64_t)batch};
+  cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)L * (cuuint64_t)ld * 2};
+  cuuint32_t bx[3] = {32, 32, 1}, es[3] = {1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, bx, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(out) failed: %d (dims %llu %llu %llu strides %llu %llu)", (int)r, dims[0], dims[1],
+              dims[2], strides[0], strides[1]);
+    return WJ_ERR_RUNTIME;
+  }
+  return WJ_OK;
+}
+
+// Decides whether the epilogue can take the TMA-store path and builds its maps.
+static int setup_out_maps(GemmParams& p, OutMaps& om, int N, int L, int batch) {
+  memset(&om, 0, sizeof(om));
+  p.tma_store = 0;
+  const bool ok = !p.out_f32 && !p.accumulate && p.resid == nullptr && p.out_rows == nullptr && p.colsum == nullptr &&
+                  (p.act == 0 || p.act == 1) && (p.ld_out % 8 == 0) && (reinterpret_cast<uintptr_t>(p.out) % 16 == 0) &&
+                  (p.out2 == nullptr || (p.ld_out2 % 8 == 0 && reinterpret_cast<uintptr_t>(p.out2) % 16 == 0));
+  if (!ok) return WJ_OK;
+  int rc = encode_out_map(&om.o, p.out, N, L, batch, p.ld_out);
+  if (rc) return rc;
+  if (p.out2 != nullptr) {
+    rc = encode_out_map(&om.o2, p.out2, N, L, batch, p.ld_out2);
+    if (rc) return rc;
+  }
+  p.tma_store = 1;
+  return WJ_OK;
+}
+
 static int num_sms() { return sm_count(); }
 
 template <int BN, int MODE>
-static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmB1, const GemmParams& p, int grid,
-                  cudaStream_t st) {
+static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmB1, const OutMaps& om,
+                  const GemmParams& p, int grid, cudaStream_t st) {
   static bool attr_set = false;
   auto kern = gemm_kernel<BN, MODE>;
   if (!attr_set) {
@@ -829,7 +966,7 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensor
     if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return WJ_ERR_RUNTIME; }
     attr_set = true;
   }
-  kern<<<grid, kThreads, Cfg<BN>::SMEM_BYTES, st>>>(tmA, tmB, tmB1, p);
+  kern<<<grid, kThreads, Cfg<BN>::SMEM_BYTES, st>>>(tmA, tmB, tmB1, om, p);
   return check_launch("gemm_tcgen05 launch");
 }
 
@@ -903,8 +1040,11 @@ extern "C" int wj_gemm_bf16(const wj_operand_t* A, const void* W, int64_t ldw, i
   fill_epilogue(p, epi);
   const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (block_n == 256) return launch<256, 0>(tmA, tmB, tmB, p, grid, st);
-  return launch<128, 0>(tmA, tmB, tmB, p, grid, st);
+  OutMaps om;
+  rc = setup_out_maps(p, om, N, L, batch);
+  if (rc) return rc;
+  if (block_n == 256) return launch<256, 0>(tmA, tmB, tmB, om, p, grid, st);
+  return launch<128, 0>(tmA, tmB, tmB, om, p, grid, st);
 }
 
 // dW[m, vc] (+)= sum_{b, t} dY(b, t; m) * X(vc; t, b)      fp32 output, reduce-add when splits > 1 or accumulate.
@@ -962,8 +1102,10 @@ extern "C" int wj_gemm_wgrad_bf16(const wj_operand_t* dY, const wj_operand_t* X,
   }
   const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (block_n == 256) return launch<256, 1>(tmA, tmB, tmB1, p, grid, st);
-  return launch<128, 1>(tmA, tmB, tmB1, p, grid, st);
+  OutMaps om;
+  memset(&om, 0, sizeof(om));
+  if (block_n == 256) return launch<256, 1>(tmA, tmB, tmB1, om, p, grid, st);
+  return launch<128, 1>(tmA, tmB, tmB1, om, p, grid, st);
 }
 
 // out[b*L + t, n] = epilogue( sum_{s, r} A(s*width + r; t, b) * W[r, col_off[s] + n] ),  W bf16 row-major [R, ldw]:
@@ -994,6 +1136,9 @@ extern "C" int wj_gemm_dgrad_bf16(const wj_operand_t* A, const void* W, int64_t 
   fill_epilogue(p, epi);
   const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (block_n == 256) return launch<256, 2>(tmA, tmB, tmB, p, grid, st);
-  return launch<128, 2>(tmA, tmB, tmB, p, grid, st);
+  OutMaps om;
+  rc = setup_out_maps(p, om, N, L, batch);
+  if (rc) return rc;
+  if (block_n == 256) return launch<256, 2>(tmA, tmB, tmB, om, p, grid, st);
+  return launch<128, 2>(tmA, tmB, tmB, om, p, grid, st);
 }
