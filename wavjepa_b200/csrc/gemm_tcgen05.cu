@@ -301,29 +301,32 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t t_ba
 // the per-element addressing, transposes and predicates of the generic path: tcgen05.ld.32x32b (row per lane) -> math
 // -> 4 x st.shared.v4 into a 64B-swizzled 32 x 32 staging tile (2 KB per warp) -> ONE TMA store per 32 x 32 chunk
 // (the hardware clips rows >= L and columns >= N).  ~5x fewer issued instructions per element than the generic path.
-template <int BN, typename Arrive>
+template <int BN, bool HEAVY, typename Arrive>
 __device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const OutMaps& om, uint32_t t_base, uint8_t* stg,
                                                   int lane, int lane_grp, int col_q, int n_blk, int b, int row_in_batch0,
                                                   Arrive arrive) {
   constexpr int CHUNKS = BN / 32 / 4;
   const int row0 = row_in_batch0 + lane_grp * 32;
+  uint8_t* srow = stg + lane * 64;          // staging row = lane (64 B); 16-byte chunk c lives at c ^ ((row >> 1) & 3)
+  const int sw = (lane >> 1) & 3;           // (CU_TENSOR_MAP_SWIZZLE_64B)
   uint32_t v[32];
   tmem_ld_32x32(t_base, v);
 #pragma unroll 1
   for (int ch = 0; ch < CHUNKS; ++ch) {
+    const int n0 = n_blk * BN + (col_q * CHUNKS + ch) * 32;
+    const bool live = n0 < p.N && row0 < p.L;   // warp-uniform
     tmem_ld_wait();
     float f[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
     if (ch + 1 < CHUNKS) {
-      tmem_ld_32x32(t_base + (ch + 1) * 32, v);
+      tmem_ld_32x32(t_base + (ch + 1) * 32, v);   // in flight during the math of this chunk
     } else {
       tc_fence_before();
       __syncwarp();
       if (lane == 0) arrive();
     }
-    const int n0 = n_blk * BN + (col_q * CHUNKS + ch) * 32;
-    if (n0 >= p.N || row0 >= p.L) continue;   // warp-uniform
+    if (!live) continue;
     if (p.bias != nullptr) {
 #pragma unroll
       for (int j = 0; j < 32; j += 4) {
@@ -333,10 +336,18 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const Out
         }
       }
     }
-    uint32_t w[16], w2[16];
-    if (p.act == 1) {
-      // autocast semantics: the linear/conv output is bf16 and GELU is evaluated on that bf16 value
-      if (p.out2 != nullptr) {
+    uint32_t w[16];
+    uint32_t w2[HEAVY ? 16 : 1];
+    if constexpr (!HEAVY) {
+      if (p.act == 1) {   // autocast semantics: the linear/conv output is bf16 and GELU is evaluated on that bf16 value
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) w[j >> 1] = pack_bf16x2(gelu_fast(bf16_round(f[j])), gelu_fast(bf16_round(f[j + 1])));
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) w[j >> 1] = pack_bf16x2(f[j], f[j + 1]);
+      }
+    } else {
+      if (p.act == 1) {
 #pragma unroll
         for (int j = 0; j < 32; j += 2) {
           float g0, d0, g1, d1;
@@ -347,15 +358,9 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const Out
         }
       } else {
 #pragma unroll
-        for (int j = 0; j < 32; j += 2) w[j >> 1] = pack_bf16x2(gelu_fast(bf16_round(f[j])), gelu_fast(bf16_round(f[j + 1])));
+        for (int j = 0; j < 32; j += 2) w[j >> 1] = pack_bf16x2(f[j], f[j + 1]);
       }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; j += 2) w[j >> 1] = pack_bf16x2(f[j], f[j + 1]);
     }
-    // staging row = lane (64 B), 16-byte chunk c stored at c ^ ((row >> 1) & 3)  (CU_TENSOR_MAP_SWIZZLE_64B)
-    uint8_t* srow = stg + lane * 64;
-    const int sw = (lane >> 1) & 3;
     if (lane == 0) bulk_wait_read0();   // the previous TMA store of this warp has finished reading the staging tile
     __syncwarp();
 #pragma unroll
@@ -367,24 +372,27 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const Out
       tma_store_3d(&om.o, stg, n0, row0, b);
       bulk_commit();
     }
-    if (p.act == 1 && p.out2 != nullptr) {
-      if (lane == 0) bulk_wait_read0();
-      __syncwarp();
+    if constexpr (HEAVY) {
+      if (p.act == 1 && p.out2 != nullptr) {
+        __syncwarp();
+        if (lane == 0) bulk_wait_read0();
+        __syncwarp();
 #pragma unroll
-      for (int c = 0; c < 4; ++c)
-        *reinterpret_cast<uint4*>(srow + ((c ^ sw) << 4)) = make_uint4(w2[4 * c], w2[4 * c + 1], w2[4 * c + 2], w2[4 * c + 3]);
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) {
-        tma_store_3d(&om.o2, stg, n0, row0, b);
-        bulk_commit();
+        for (int c = 0; c < 4; ++c)
+          *reinterpret_cast<uint4*>(srow + ((c ^ sw) << 4)) = make_uint4(w2[4 * c], w2[4 * c + 1], w2[4 * c + 2], w2[4 * c + 3]);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_3d(&om.o2, stg, n0, row0, b);
+          bulk_commit();
+        }
       }
     }
   }
 }
 
 // MODE 0: A K-major, B K-major (fwd)   MODE 1: A, B MN-major (wgrad)   MODE 2: A K-major, B MN-major (dgrad)
-template <int BN, int MODE>
+template <int BN, int MODE, bool HEAVY>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmB1, const __grid_constant__ OutMaps om, const GemmParams p) {
@@ -586,7 +594,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const uint32_t t_base = tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16) + acc * BN + col_q * (CHUNKS * 32);
       if constexpr (!WGRAD) {
         if (p.tma_store) {
-          epilogue_tile_tma<BN>(p, om, t_base, smem + C::STAGING_OFF + ew * 2048, lane, lane_grp, col_q, n_blk, b,
+          epilogue_tile_tma<BN, HEAVY>(p, om, t_base, smem + C::STAGING_OFF + ew * 2048, lane, lane_grp, col_q, n_blk, b,
                                 row_in_batch0, [&]() { mbar_arrive(&tempty_bar[acc]); });
           continue;
         }
@@ -956,11 +964,11 @@ static int setup_out_maps(GemmParams& p, OutMaps& om, int N, int L, int batch) {
 
 static int num_sms() { return sm_count(); }
 
-template <int BN, int MODE>
-static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmB1, const OutMaps& om,
-                  const GemmParams& p, int grid, cudaStream_t st) {
+template <int BN, int MODE, bool HEAVY>
+static int launch_variant(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmB1, const OutMaps& om,
+                          const GemmParams& p, int grid, cudaStream_t st) {
   static bool attr_set = false;
-  auto kern = gemm_kernel<BN, MODE>;
+  auto kern = gemm_kernel<BN, MODE, HEAVY>;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM_BYTES);
     if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return WJ_ERR_RUNTIME; }
@@ -983,6 +991,16 @@ static int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
   if (p.total_tiles < pairs) pairs = p.total_tiles;
   kern<<<2 * pairs, kThreads, CfgPair<BN>::SMEM_BYTES, st>>>(tmA, tmB, p);
   return check_launch("gemm_tcgen05 pair launch");
+}
+
+template <int BN, int MODE>
+static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmB1, const OutMaps& om,
+                  const GemmParams& p, int grid, cudaStream_t st) {
+  if constexpr (MODE != 1) {
+    // the two-output epilogue (GELU + saved GELU') has its own instantiation of the TMA-store path (register budget)
+    if (p.tma_store && p.out2 != nullptr) return launch_variant<BN, MODE, true>(tmA, tmB, tmB1, om, p, grid, st);
+  }
+  return launch_variant<BN, MODE, false>(tmA, tmB, tmB1, om, p, grid, st);
 }
 
 static void fill_seg(SegInfo& s, const wj_operand_t* op) {
