@@ -325,3 +325,10 @@ def hear_timestamp_embeddings(audio: torch.Tensor, sd, cfg: Cfg, sr: int = 16000
     step_ms = (L / sr) / n * 1000
     ts = torch.tensor([step_ms * i for i in range(n)]).unsqueeze(0).repeat(B, 1)
     return emb, ts
+
+
+def arch_get_embeddings(audio: torch.Tensor, sd, cfg: Cfg, sr: int = 16000) -> torch.Tensor:
+    """ARCH/configs/wavjepa_wrapper.py:67-110 for one clip [L]: loudness-normalise, pad, per-chunk normalise + encode with
+    the padded frames key-masked, keep the unmasked frames, mean over all kept frames -> [D]."""
+    emb, _ = hear_timestamp_embeddings(audio.reshape(1, -1), sd, cfg, sr)
+    return emb[0].mean(dim=0)

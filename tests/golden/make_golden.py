@@ -157,8 +157,69 @@ def golden_hear():
     np.savez_compressed(os.path.join(HERE, "hear.npz"), **out)
 
 
+def golden_interop():
+    """Rows of SURVEY.md 8(f)-3, executed on the unmodified reference: the ARCH wrapper (with a stub `arch_eval` base
+    class -- the vendored harness needs pyannote), the 7-layer wav2vec2 extractor HEAR model (process_seconds=4.02) and
+    the `size="large"` forward."""
+    import types
+    out = {}
+    # ---- ARCH/configs/wavjepa_wrapper.py: get_embeddings on one clip
+    stub = types.ModuleType("arch_eval")
+    stub.Model = type("Model", (), {"__init__": lambda self, model, **kw: None})
+    stub.ClassificationModel = stub.Model
+    sys.modules["arch_eval"] = stub
+    sys.path.insert(0, os.path.join(ref.root, "ARCH"))
+    import importlib
+    wrap = importlib.import_module("configs.wavjepa_wrapper")
+    cfg = jo.Cfg()
+    sd = jo.make_state_dict(cfg, seed=3)
+    m = build_ref(cfg, sd)
+    m.eval()
+    w = wrap.WavJEPAModelWrapper(m, "cpu", None)
+    for tag, n in (("a", 40000), ("b", 64318)):
+        audio = oi.hear_inputs(1, n, seed=21)[0]
+        out[f"arch_{tag}"] = w.get_embeddings(audio).numpy()
+        print("arch", tag, out[f"arch_{tag}"].shape)
+    # ---- hear_configs/WavJEPA_w2v2.py: 7-layer extractor, 4.02 s windows
+    import hear_api.feature_helper as fh
+    import hear_api.runtime as rt
+    fh.FeatureExtractor.forward = lambda self, x: self._wav2feature(x)  # the reference hard-codes .cuda() (:87)
+    w2v2 = [(512, 10, 5)] + [(512, 3, 2)] * 4 + [(512, 2, 2)] * 2
+    cfg2 = jo.Cfg(spec=w2v2, seconds=4.02)
+    sd2 = jo.make_state_dict(cfg2, seed=3)
+    ext = ref.ConvFeatureExtractor(conv_layers_spec=w2v2, in_channels=1)
+    model = rt.RuntimeJEPA(in_channels=1, weights={"state_dict": sd2}, is_spectrogram=False, process_seconds=4.02,
+                           extractor=ext, model_size="base", sr=16000)
+    audio = oi.hear_inputs(2, 100000, seed=12)
+    emb, ts = model.get_timestamp_embeddings(audio)
+    out["w2v2_emb"] = oi.subsample(emb)
+    out["w2v2_shape"] = np.asarray(emb.shape)
+    out["w2v2_ts"] = ts[0].numpy()
+    out["w2v2_l2"] = np.float64(emb.norm())
+    print("w2v2", tuple(emb.shape))
+    # ---- size="large": 24 x 1024 x 16 heads (jepa.py:113-118), forward + loss on 2 instances
+    cfgL = jo.Cfg(d_model=1024, nhead=16, layers=24)
+    sdL = jo.make_state_dict(cfgL, seed=3)
+    extL = ref.ConvFeatureExtractor(conv_layers_spec=cfgL.spec, in_channels=1)
+    mL = ref.JEPA(feature_extractor=extL, transformer_encoder_cfg=ref.TransformerEncoderCFG.create(),
+                  transformer_encoder_layers_cfg=ref.TransformerLayerCFG.create(),
+                  transformer_decoder_cfg=ref.TransformerEncoderCFG.create(),
+                  transformer_decoder_layers_cfg=ref.TransformerLayerCFG.create(d_model=384), resample_sr=16000,
+                  process_audio_seconds=2.01, nr_samples_per_audio=8, average_top_k_layers=8, compile_modules=False,
+                  size="large")
+    print("large load:", mL.load_state_dict(sdL, strict=True))
+    inp = oi.training_inputs(cfgL, 1, 2, seed=77, masker="audioset")
+    with torch.no_grad():
+        o = mL(inp["audio"], inp["ctx_masks"], inp["target_indices"], inp["ctx_and_target_masks"])
+    out["large_loss"] = np.float64(o["loss"].item())
+    out["large_local"] = oi.subsample(o["local_features"])
+    out["large_targets"] = oi.subsample(o["targets"])
+    print("large loss", out["large_loss"])
+    np.savez_compressed(os.path.join(HERE, "interop.npz"), **out)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["masks", "keys", "train", "nat", "hear"]
+    which = sys.argv[1:] or ["masks", "keys", "train", "nat", "hear", "interop"]
     if "masks" in which:
         golden_masks()
     if "keys" in which:
@@ -170,3 +231,5 @@ if __name__ == "__main__":
         golden_train("train_nat", jo.Cfg(in_channels=2, per_channel=True), n_clips=1, crops=2, seed=55)
     if "hear" in which:
         golden_hear()
+    if "interop" in which:
+        golden_interop()

@@ -260,3 +260,70 @@ def test_hear_against_live_oracle_with_silent_clip():
     assert rel(emb[0].cpu().numpy(), ref_emb[0].numpy()) < FEAT_TOL
     assert rel(emb[1].cpu().numpy(), ref_emb[1].numpy()) < FEAT_TOL
     assert torch.allclose(ts, ref_ts)
+
+
+# ------------------------------------------------------------------------------------------------- 8(f)-3 interop rows
+def test_arch_wrapper_matches_reference_goldens():
+    from wavjepa_b200.arch import WavJEPAModelWrapper
+
+    g = np.load(os.path.join(GOLD, "interop.npz"))
+    cfg = jo.Cfg()
+    model = build_model(cfg, jo.make_state_dict(cfg, seed=3))
+    wrap = WavJEPAModelWrapper(model, DEV, None)
+    assert wrap.get_sampling_rate() == 16000 and wrap.get_classification_embedding_size() == 768
+    for tag, n in (("a", 40000), ("b", 64318)):
+        v = wrap.get_embeddings(oi.hear_inputs(1, n, seed=21)[0])
+        assert v.shape == (768,)
+        assert rel(v.cpu().numpy(), g[f"arch_{tag}"]) < FEAT_TOL, tag
+    with pytest.raises(TypeError):
+        wrap.get_sequence_embeddings(torch.zeros(16000))
+
+
+def test_w2v2_extractor_hear_model_matches_reference_goldens():
+    g = np.load(os.path.join(GOLD, "interop.npz"))
+    cfg2 = jo.Cfg(spec=hear.W2V2_SPEC, seconds=4.02)
+    model = hear.load_model_w2v2({"state_dict": jo.make_state_dict(cfg2, seed=3)})
+    assert model.unit_frames == 64319 and model.output_steps == 200
+    emb, ts = model.get_timestamp_embeddings(oi.hear_inputs(2, 100000, seed=12).to(DEV))
+    assert list(emb.shape) == g["w2v2_shape"].tolist()
+    assert rel(oi.subsample(emb.cpu()), g["w2v2_emb"]) < FEAT_TOL
+    assert np.allclose(ts[0].numpy(), g["w2v2_ts"], rtol=1e-6, atol=1e-4)
+
+
+def test_large_model_forward_matches_reference_goldens():
+    g = np.load(os.path.join(GOLD, "interop.npz"))
+    cfgL = jo.Cfg(d_model=1024, nhead=16, layers=24)
+    ex = w.ConvFeatureExtractor(conv_layers_spec=cfgL.spec, in_channels=1)
+    model = w.JEPA(feature_extractor=ex, transformer_encoder_cfg=w.TransformerEncoderCFG.create(),
+                   transformer_encoder_layers_cfg=w.TransformerLayerCFG.create(),
+                   transformer_decoder_cfg=w.TransformerEncoderCFG.create(),
+                   transformer_decoder_layers_cfg=w.TransformerLayerCFG.create(d_model=384),
+                   process_audio_seconds=2.01, nr_samples_per_audio=8, average_top_k_layers=8, size="large")
+    assert model.encoder_embedding_dim == 1024 and len(model.encoder.layers) == 24
+    model.load_state_dict(jo.make_state_dict(cfgL, seed=3), strict=True)
+    model.to(DEV)
+    inp = oi.training_inputs(cfgL, 1, 2, seed=77, masker="audioset")
+    with torch.no_grad():
+        out = model(inp["audio"].to(DEV).bfloat16(), inp["ctx_masks"].to(DEV), inp["target_indices"].to(DEV),
+                    inp["ctx_and_target_masks"].to(DEV))
+    assert abs(out["loss"].item() - float(g["large_loss"])) / float(g["large_loss"]) < LOSS_TOL
+    assert rel(oi.subsample(out["local_features"].cpu()), g["large_local"]) < FEAT_TOL
+    assert rel(oi.subsample(out["targets"].cpu()), g["large_targets"]) < 1.5 * FEAT_TOL   # 24 layers of bf16 operands
+
+
+def test_checkpoint_round_trip(tmp_path):
+    """Lightning-style checkpoint with torch.compile's `_orig_mod` infix (hear_api/runtime.py:63-77) -> load_model(path);
+    and our state_dict written back has the reference's names."""
+    cfg = jo.Cfg()
+    sd = jo.make_state_dict(cfg, seed=9)
+    ck = {"state_dict": {(k.replace("extract_audio.", "extract_audio._orig_mod.", 1) if k.startswith("extract_audio.")
+                          else k.replace("decoder.", "decoder._orig_mod.", 1) if k.startswith("decoder.") else k): v
+                         for k, v in sd.items()}, "global_step": 123}
+    path = str(tmp_path / "step=123.ckpt")
+    torch.save(ck, path)
+    rt = hear.load_model(path)
+    back = rt.model.state_dict()
+    assert list(back.keys()) == list(sd.keys())
+    for k in ("extract_audio.cnn.3.0.weight", "decoder.layers.4.linear1.bias", "teacher_encoder.layers.7.norm2.weight",
+              "pos_encoding_decoder", "mask_token"):
+        assert torch.equal(back[k].cpu(), sd[k]), k

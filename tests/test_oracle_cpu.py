@@ -189,3 +189,30 @@ def test_c_abi_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/wavjepa_b200.h but not exported"
     assert lib.wj_version() >= 1
+
+
+def test_oracle_interop_rows_match_reference():
+    """SURVEY.md 8(f)-3 rows, pinned by the executed reference (tests/golden/interop.npz): ARCH wrapper embedding,
+    wav2vec2-extractor HEAR model (4.02 s windows), size="large" forward."""
+    torch.set_num_threads(os.cpu_count())
+    g = np.load(os.path.join(GOLD, "interop.npz"))
+    cfg = jo.Cfg()
+    sd = jo.make_state_dict(cfg, seed=3)
+    with torch.no_grad():
+        for tag, n in (("a", 40000), ("b", 64318)):
+            v = jo.arch_get_embeddings(oi.hear_inputs(1, n, seed=21)[0], sd, cfg)
+            assert v.shape == (768,) and rel(v.numpy(), g[f"arch_{tag}"]) < 2e-4, tag
+        w2v2 = [(512, 10, 5)] + [(512, 3, 2)] * 4 + [(512, 2, 2)] * 2
+        cfg2 = jo.Cfg(spec=w2v2, seconds=4.02)
+        assert cfg2.target_length == 64319 and cfg2.total_patches == 200
+        emb, ts = jo.hear_timestamp_embeddings(oi.hear_inputs(2, 100000, seed=12), jo.make_state_dict(cfg2, seed=3), cfg2)
+        assert list(emb.shape) == g["w2v2_shape"].tolist() == [2, 311, 768]
+        assert rel(oi.subsample(emb), g["w2v2_emb"]) < 2e-4
+        assert np.allclose(ts[0].numpy(), g["w2v2_ts"], rtol=1e-6, atol=1e-4)
+        cfgL = jo.Cfg(d_model=1024, nhead=16, layers=24)
+        inp = oi.training_inputs(cfgL, 1, 2, seed=77, masker="audioset")
+        o = jo.forward(inp["audio"], inp["ctx_masks"], inp["target_indices"], inp["ctx_and_target_masks"],
+                       jo.make_state_dict(cfgL, seed=3), cfgL)
+        assert abs(o["loss"].item() - float(g["large_loss"])) / float(g["large_loss"]) < 2e-5
+        assert rel(oi.subsample(o["local_features"]), g["large_local"]) < 2e-4
+        assert rel(oi.subsample(o["targets"]), g["large_targets"]) < 2e-4

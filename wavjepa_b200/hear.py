@@ -59,6 +59,25 @@ def get_timestamps(sample_rate: int, B: int, input_audio_len: int, n_frames: int
     return torch.tensor([step * i for i in range(n_frames)]).unsqueeze(0).repeat(B, 1)
 
 
+@torch.no_grad()
+def embed_chunks(model: JEPA, a: torch.Tensor, gain: Optional[torch.Tensor], unit: int, steps: int, sr: int):
+    """The chunk loop of hear_api/runtime.py:107-142 (and ARCH/configs/wavjepa_wrapper.py:67-110) as ONE batched pass:
+    a [B, C, L] fp32 on the device, gain [B] or None.  Chunk i of clip b = gain * a[b, :, i*unit:(i+1)*unit] (zeros past
+    L), normalised per chunk (mean / unbiased std including the zero padding, runtime.py:12-16); the frames that fall
+    into the padding are key-masked and cut off.  Returns (emb [B, cut_off, D] fp32, cut_off)."""
+    B, C, L = a.shape
+    pad, n_chunks, cut_off, total_steps = hear_geometry(L, unit, sr, steps)
+    dev = a.device
+    starts = (torch.arange(n_chunks, device=dev, dtype=torch.int32) * unit).repeat(B)
+    x16 = torch.empty(B * n_chunks, C, unit, device=dev, dtype=torch.bfloat16)
+    ops.crop_norm(a, starts, n_chunks, unit, x16, None, gain=gain)
+    mask = torch.zeros(B, max(total_steps, n_chunks * steps), dtype=torch.bool, device=dev)
+    mask[:, cut_off:total_steps] = True
+    mask = mask[:, :n_chunks * steps].reshape(B * n_chunks, steps)
+    emb = model.get_audio_representation(x16, mask)          # [B*n_chunks, steps, D] fp32
+    return emb.view(B, n_chunks * steps, -1)[:, :cut_off], cut_off
+
+
 class RuntimeJEPA(nn.Module):
     """reference hear_api/runtime.py:39-155."""
 
@@ -113,18 +132,7 @@ class RuntimeJEPA(nn.Module):
     def get_timestamp_embeddings(self, audio: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
         a, gain = self.to_feature(audio)
         B, _, L = a.shape
-        unit, steps = self.unit_frames, self.output_steps
-        pad, n_chunks, cut_off, total_steps = hear_geometry(L, unit, self.sample_rate, steps)
-        dev = a.device
-        # chunk i of clip b = gain * audio[b, :, i*unit:(i+1)*unit] (zeros past L), normalised per chunk
-        starts = (torch.arange(n_chunks, device=dev, dtype=torch.int32) * unit).repeat(B)
-        x16 = torch.empty(B * n_chunks, 1, unit, device=dev, dtype=torch.bfloat16)
-        ops.crop_norm(a, starts, n_chunks, unit, x16, None, gain=gain)
-        mask = torch.zeros(B, max(total_steps, n_chunks * steps), dtype=torch.bool, device=dev)
-        mask[:, cut_off:total_steps] = True
-        mask = mask[:, :n_chunks * steps].reshape(B * n_chunks, steps)
-        emb = self.model.get_audio_representation(x16, mask)          # [B*n_chunks, steps, D] fp32
-        emb = emb.view(B, n_chunks * steps, -1)[:, :cut_off]
+        emb, _ = embed_chunks(self.model, a, gain, self.unit_frames, self.output_steps, self.sample_rate)
         ts = get_timestamps(self.sample_rate, B, L, emb.shape[1])
         return emb, ts
 
