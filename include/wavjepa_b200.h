@@ -163,6 +163,19 @@ int wj_crop_norm(const float* audio, const int* starts, const float* gain, int n
 int wj_clip_gain(const float* audio, int n_clips, int channels, int64_t clip_len, float target_dbfs, float* gain,
                  void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * On-GPU input pipeline (data_modules/WebAudioDataModule.py:43-61, dataset_functions.py:92-114).
+ * wj_resample_sinc: y[n*new + p] = sum_k table_t[k, p] * xpad[n*orig + k] (torchaudio's polyphase Kaiser-sinc
+ *   resampler: conv1d with stride `orig` over x padded by (width, width + orig) zeros, K = 2*width + orig taps, `new`
+ *   phases; orig/new already divided by their gcd; table_t is [K, new] fp32).  Outputs t < out_cap are stored, the
+ *   rest of out[0:out_cap] is zero-filled (pad / crop to the fixed clip length); *sumsq (fp64, += ) receives the sum of
+ *   squares of ALL target_length = ceil(new*length/orig) outputs (the RMS is taken before the crop).
+ * wj_rms_gain_rows: clips[c, :] *= 10^((target_dbfs - 20 log10(sqrt(sumsq[c]/counts[c]))) / 20) (no-op when silent). */
+int wj_resample_sinc(const float* x, int64_t length, const float* table_t, int orig, int new_, int width,
+                     int64_t target_length, float* out, int64_t out_cap, double* sumsq, void* stream);
+int wj_rms_gain_rows(float* clips, const double* sumsq, const int64_t* counts, int n_clips, int64_t row_len,
+                     float target_dbfs, void* stream);
+
 /* targets (=|+=) scale * instance_norm(x) with statistics over all T*D values of each instance (biased var, eps);
  * rowsum [B*T, 2] comes from wj_layernorm_fwd.  JEPA._make_targets (wavjepa/jepa.py:230-253). */
 int wj_target_accum(const float* x, const float* rowsum, int B, int T, int D, float eps, float scale, int first,

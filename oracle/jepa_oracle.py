@@ -332,3 +332,25 @@ def arch_get_embeddings(audio: torch.Tensor, sd, cfg: Cfg, sr: int = 16000) -> t
     the padded frames key-masked, keep the unmasked frames, mean over all kept frames -> [D]."""
     emb, _ = hear_timestamp_embeddings(audio.reshape(1, -1), sd, cfg, sr)
     return emb[0].mean(dim=0)
+
+
+def data_pre_process(waveform: torch.Tensor, audio_sr: int, sr: int = 16000, seconds: int = 10) -> torch.Tensor:
+    """data_modules/WebAudioDataModule.py:43-61 + dataset_functions.py:92-114: first channel, torchaudio Kaiser-sinc
+    resampling (the reference's arguments), RMS normalisation to -14 dBFS over the whole resampled clip, zero-pad / crop
+    to `seconds` -> [1, sr*seconds] fp32.  torchaudio is the reference's own third-party resampler (requirements.txt)."""
+    import torchaudio
+
+    audio = waveform[0, :] if waveform.ndim > 1 else waveform
+    if audio_sr != sr:
+        audio = torchaudio.functional.resample(audio, audio_sr, sr, lowpass_filter_width=64, rolloff=0.9475937167399596,
+                                               resampling_method="sinc_interp_kaiser", beta=14.769656459379492)
+    rms = torch.sqrt(torch.mean(audio ** 2))
+    if rms != 0:
+        audio = audio * 10 ** ((-14.0 - 20 * torch.log10(rms)) / 20)
+    audio = audio.reshape(1, -1)
+    padding = sr * seconds - audio.shape[1]
+    if padding > 0:
+        audio = F.pad(audio, (0, padding), "constant", 0)
+    elif padding < 0:
+        audio = audio[:, : sr * seconds]
+    return audio

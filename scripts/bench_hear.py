@@ -29,6 +29,15 @@ def timed(fn, warmup=2, reps=5):
     return e0.elapsed_time(e1) / reps
 
 
+if "--pipeline" in sys.argv:
+    from wavjepa_b200.preprocess import GpuAudioPipeline
+    pipe = GpuAudioPipeline(device=dev)
+    for asr in (44100, 48000, 16000):
+        waves = [torch.randn(asr * 10, device=dev) * 0.1 for _ in range(64)]
+        ms = timed(lambda: pipe(waves, [asr] * 64))
+        print(json.dumps({"workload": f"8(f)-2 input pipeline: 64 clips x 10 s @ {asr} Hz -> [64, 1, 160000] (resample + RMS + pad)",
+                          "ms_per_batch": round(ms, 3), "clips_per_s": round(64 / ms * 1e3, 0)}))
+    sys.exit(0)
 if "--nat" in sys.argv:
     torch.manual_seed(0)
     ex = w.ConvChannelFeatureExtractor(conv_layers_spec=SPEC, in_channels=2, share_weights_over_channels=False)

@@ -327,3 +327,39 @@ def test_checkpoint_round_trip(tmp_path):
     for k in ("extract_audio.cnn.3.0.weight", "decoder.layers.4.linear1.bias", "teacher_encoder.layers.7.norm2.weight",
               "pos_encoding_decoder", "mask_token"):
         assert torch.equal(back[k].cpu(), sd[k]), k
+
+
+# ------------------------------------------------------------------------------------------------- 8(f)-2 input pipeline
+def test_gpu_input_pipeline_matches_reference_preprocessing():
+    """Resample (Kaiser sinc) -> -14 dBFS RMS -> pad / crop to 10 s on the GPU == the data module's CPU path
+    (WebAudioDataModule.py:43-61, dataset_functions.py:92-114) restated with the reference's own resampler."""
+    pytest.importorskip("torchaudio")
+    from wavjepa_b200.preprocess import GpuAudioPipeline
+
+    g = torch.Generator().manual_seed(3)
+    cases = [(48000, 5.0, 1), (44100, 12.3, 2), (16000, 10.0, 1), (22050, 3.7, 1), (32000, 10.0, 1), (8000, 2.0, 1),
+             (16000, 11.0, 1), (44100, 0.05, 1)]
+    waves, srs = [], []
+    for sr_, dur, ch in cases:
+        n = int(sr_ * dur)
+        wv = torch.randn(ch, n, generator=g) * 0.1 if ch > 1 else torch.randn(n, generator=g) * 0.1
+        waves.append(wv)
+        srs.append(sr_)
+    waves.append(torch.zeros(30000))          # silent clip: rms == 0 -> untouched
+    srs.append(48000)
+    pipe = GpuAudioPipeline(sr=16000, seconds=10, device=DEV)
+    clips = pipe(waves, srs)
+    assert clips.shape == (len(waves), 1, 160000) and clips.dtype == torch.float32
+    for i, (wv, sr_) in enumerate(zip(waves, srs)):
+        ref = jo.data_pre_process(wv, sr_)
+        got = clips[i].cpu()
+        scale = ref.abs().max().item() + 1e-12
+        assert (got - ref).abs().max().item() <= 2e-5 * scale + 1e-7, (i, sr_, (got - ref).abs().max().item(), scale)
+    assert clips[-1].abs().max().item() == 0.0
+    # feeds the training hook directly
+    model = build_model(jo.Cfg(), jo.make_state_dict(jo.Cfg(), seed=3))
+    mk = w.TimeInverseBlockMasker(4, 0.65, 10, 0.25, 10, 0.1, seed=1, row0=0)
+    n = clips.shape[0]
+    c_m, t_m, v_m = mk(batch_size=n * 8, n_times=200, in_channels=1)
+    x16, *_ = model.on_after_batch_transfer((clips, c_m.view(n, 8, -1), t_m.view(n, 8, 4, -1), v_m.view(n, 8, 4, -1)), 0)
+    assert x16.shape == (n * 8, 1, 32159) and torch.isfinite(x16.float()).all()

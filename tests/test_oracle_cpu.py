@@ -216,3 +216,19 @@ def test_oracle_interop_rows_match_reference():
         assert abs(o["loss"].item() - float(g["large_loss"])) / float(g["large_loss"]) < 2e-5
         assert rel(oi.subsample(o["local_features"]), g["large_local"]) < 2e-4
         assert rel(oi.subsample(o["targets"]), g["large_targets"]) < 2e-4
+
+
+def test_sinc_table_is_torchaudios():
+    """The host-side restatement of torchaudio's polyphase Kaiser-sinc table (the reference's resampler,
+    WebAudioDataModule.py:49-57) is bit-identical to the library's for the reference's arguments."""
+    taf = pytest.importorskip("torchaudio.functional.functional")
+    import math
+    from wavjepa_b200.preprocess import BETA, LOWPASS_FILTER_WIDTH, ROLLOFF, sinc_resample_table
+
+    for asr in (48000, 44100, 32000, 22050, 8000, 24000, 11025):
+        g = math.gcd(asr, 16000)
+        k_ref, w_ref = taf._get_sinc_resample_kernel(asr, 16000, g, LOWPASS_FILTER_WIDTH, ROLLOFF, "sinc_interp_kaiser", BETA,
+                                                     dtype=torch.float32)
+        k, w, o, n = sinc_resample_table(asr, 16000)
+        assert w == w_ref and (o, n) == (asr // g, 16000 // g)
+        assert torch.equal(k, k_ref[:, 0, :])

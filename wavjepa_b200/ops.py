@@ -430,3 +430,25 @@ def scale_bf16(x: torch.Tensor, scale_dev: torch.Tensor):
     lib = _lib.load()
     p = lambda t: C.c_void_p(_ptr(t))
     check(lib.wj_scale_bf16(p(x), p(scale_dev), C.c_int64(x.numel()), _stream()))
+
+
+# ----------------------------------------------------------------------------------------------------- input pipeline
+def resample_sinc(x: torch.Tensor, table_t: torch.Tensor, orig: int, new: int, width: int, target_length: int,
+                  out_row: torch.Tensor, sumsq_slot: torch.Tensor):
+    """x [L] fp32 -> out_row [cap] fp32 (resampled, zero-padded / cropped), sumsq_slot [1] fp64 += sum of squares."""
+    assert x.dtype == torch.float32 and x.is_contiguous() and out_row.dtype == torch.float32 and out_row.is_contiguous()
+    assert table_t.dtype == torch.float32 and table_t.is_contiguous() and table_t.shape == (2 * width + orig, new)
+    assert sumsq_slot.dtype == torch.float64
+    lib = _lib.load()
+    p = lambda t: C.c_void_p(_ptr(t))
+    check(lib.wj_resample_sinc(p(x), C.c_int64(x.numel()), p(table_t), orig, new, width, C.c_int64(target_length),
+                               p(out_row), C.c_int64(out_row.numel()), p(sumsq_slot), _stream()))
+
+
+def rms_gain_rows(clips: torch.Tensor, sumsq: torch.Tensor, counts: torch.Tensor, target_dbfs: float = -14.0):
+    assert clips.dtype == torch.float32 and clips.dim() == 2 and clips.is_contiguous()
+    assert sumsq.dtype == torch.float64 and counts.dtype == torch.int64
+    lib = _lib.load()
+    p = lambda t: C.c_void_p(_ptr(t))
+    check(lib.wj_rms_gain_rows(p(clips), p(sumsq), p(counts), clips.shape[0], C.c_int64(clips.shape[1]),
+                               C.c_float(target_dbfs), _stream()))
