@@ -13,7 +13,7 @@ ncu = "--ncu" in sys.argv
 torch.manual_seed(0)
 
 
-def run(name, M, N, K, *, act=0, f32=False, resid=False, out2=False, aux=False, bias=True, mode="fwd", reps=20, bn=0):
+def run(name, M, N, K, *, act=0, f32=False, resid=False, out2=False, aux=False, bias=True, mode="fwd", reps=20, bn=0, colsum=False):
     a = torch.randn(M, K, device=dev).bfloat16()
     w = (torch.randn(N, K, device=dev) * 0.05).bfloat16() if mode == "fwd" else (torch.randn(K, N, device=dev) * 0.05).bfloat16()
     outs = [torch.empty(M, N, device=dev, dtype=torch.float32 if f32 else torch.bfloat16) for _ in range(2)]
@@ -21,12 +21,13 @@ def run(name, M, N, K, *, act=0, f32=False, resid=False, out2=False, aux=False, 
     r = torch.randn(M, N, device=dev) if resid else None
     o2 = torch.empty(M, N, device=dev, dtype=torch.bfloat16) if out2 else None
     ax = torch.randn(M, N, device=dev).bfloat16() if aux else None
+    cs = torch.zeros(N, device=dev) if colsum else None
 
     def call(i):
         if mode == "fwd":
             ops.gemm(ops.plain_operand(a), w, M, 1, outs[i % 2], bias=b, act=act, resid=r, out2=o2, aux=ax, block_n=bn)
         else:
-            ops.gemm_dgrad(ops.plain_operand(a), w, M, 1, outs[i % 2], K=K, N=N, act=act, aux=ax, resid=r)
+            ops.gemm_dgrad(ops.plain_operand(a), w, M, 1, outs[i % 2], K=K, N=N, act=act, aux=ax, resid=r, colsum=cs)
 
     if ncu:
         call(0)
@@ -102,6 +103,7 @@ run("pred fc1 plain", 172433, 1536, 384)
 run("pred fc2 resid f32", 172433, 384, 1536, act=3, f32=True, resid=True)
 run("pred outproj resid f32", 172433, 384, 384, act=3, f32=True, resid=True)
 run("pred dgrad fc2 x aux", 172433, 1536, 384, act=2, aux=True, bias=False, mode="dgrad")
+run("pred dgrad fc2 x aux + colsum", 172433, 1536, 384, act=2, aux=True, bias=False, mode="dgrad", colsum=True)
 run("pred dgrad plain", 172433, 1536, 384, bias=False, mode="dgrad")
 run("teacher fc1 gelu", 102400, 3072, 768, act=1)
 run("teacher fc1 plain", 102400, 3072, 768)
