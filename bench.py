@@ -167,6 +167,7 @@ def run_native(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     model = build_model(dev)
+    model.reserve_workspace(80 << 30)   # setup: the activation pool of a 512-instance step (53-66 GB) exists up front
     model.global_step = 1000          # lr(0) == 0 (warm-up from 0): start inside the warm-up so AdamW moves weights
     if world > 1:
         model.attach_data_parallel(BucketedAllReduce())

@@ -676,6 +676,19 @@ class JEPA(nn.Module):
         ops.cast_bf16(self._flat_t, self._flat_t16)
 
     # ------------------------------------------------------------------------------------------- fused train step
+    def reserve_workspace(self, n_bytes: int) -> int:
+        """Pre-sizes PyTorch's caching allocator pool on this device: the activation buffers of a step are allocated
+        through it, their sizes follow the masks (token counts differ from step to step), and a pool that is still
+        growing makes some rank call into the driver (cudaMalloc / cuMemMap, synchronising) in the middle of a step --
+        at N GPUs every such stall is paid by all ranks at the next all-reduce.  Returns the bytes reserved."""
+        dev = self.device
+        free, _ = torch.cuda.mem_get_info(dev)
+        n = int(min(n_bytes, 0.8 * free))
+        if n > 0:
+            block = torch.empty(n, dtype=torch.uint8, device=dev)
+            del block
+        return n
+
     def attach_data_parallel(self, reducer) -> None:
         """reducer: wavjepa_b200.dist.BucketedAllReduce (or None)."""
         self._ddp = reducer
