@@ -136,12 +136,15 @@ int wj_mask_indices(const uint8_t* ctx_hidden, const uint8_t* tgt, const uint8_t
 int wj_conv0_moment_count(int Cin);
 int wj_conv0_gn_gelu_fwd(const void* x_bf16, const float* w, const float* gamma, const float* beta, int B, int Cin,
                          int L, int C, int k, int stride, float eps, double* moments, float* stats, void* out_bf16,
-                         void* stream);
-/* Backward of the block above given dY (bf16 [B, L_out, C]); accumulates into dw [C, Cin, 10], dgamma, dbeta (fp32).
- * red_scratch: [B, 2 + Cin*10, C] fp32 workspace. */
+                         void* dgelu_bf16, void* stream);
+/* Backward of the block above given dY (bf16 [B, L_out, C]) and the GELU' saved by the forward (dgelu_bf16, same layout;
+ * NULL in the forward = inference, nothing saved); accumulates into dw [C, Cin, 10], dgamma, dbeta (fp32).
+ * red_scratch: [B, 2 + Cin*10, C] fp32 workspace.  The convolution itself runs on mma.sync tensor-core tiles in both
+ * directions (C must be 512). */
 int wj_conv0_gn_gelu_bwd(const void* x_bf16, const float* w, const float* gamma, const float* beta, int B, int Cin,
                          int L, int C, int k, int stride, float eps, const double* moments, const float* stats,
-                         const void* dy_bf16, float* red_scratch, float* dw, float* dgamma, float* dbeta, void* stream);
+                         const void* dy_bf16, const void* dgelu_bf16, float* red_scratch, float* dw, float* dgamma,
+                         float* dbeta, void* stream);
 
 /* LayerNorm over the last dim (D in {128,256,384,512,768,1024}), biased variance, one warp per row.
  * Writes any of: out_f32, out_bf16, stats [M,2] = (mean, rstd), rowsum [M,2] = (sum, sum of squares of the OUTPUT row).

@@ -105,144 +105,243 @@ __global__ void conv0_stats_kernel(Conv0Args a, const double* __restrict__ mom, 
 }
 
 // ------------------------------------------------------------------------------------------------ main passes
-// Loads the input window of outputs [t0, t0 + kC0TT) into smem as fp32 (zero past the end of the signal).
+// Both passes run the 10-tap convolution on the legacy tensor-core path (mma.sync.m16n8k16, bf16 in / fp32 out): the
+// A operand is the [16 outputs x 16 taps] window matrix A[t][k] = x[ci, 5t + k] (taps 10..15 are zero), read straight
+// from the bf16 input window in shared memory; B is the [16 taps x 8 channels] slice of the (bf16-rounded) weights.
+// What is left on the CUDA cores is the epilogue: ~20 instructions per output in the forward (bf16 round, affine,
+// GELU + GELU', pack, store), ~12 in the backward.
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t movmatrix_trans(uint32_t a) {
+  uint32_t d;
+  asm volatile("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;" : "=r"(d) : "r"(a));
+  return d;
+}
+__device__ __forceinline__ uint32_t pack2(bf16 lo, bf16 hi) {
+  return static_cast<uint32_t>(__bfloat16_as_ushort(lo)) | (static_cast<uint32_t>(__bfloat16_as_ushort(hi)) << 16);
+}
+
+constexpr int kC0WinB = kC0Win + 3;   // bf16 window per input channel (odd pad keeps rows apart; zero-filled tail)
+
+// Loads the bf16 input window of outputs [t0, t0 + kC0TT) (zero past the end of the signal).
 template <int CIN>
-__device__ __forceinline__ void load_window(const Conv0Args& a, int b, int t0, float* s_x) {
+__device__ __forceinline__ void load_window_bf16(const Conv0Args& a, int b, int t0, bf16* s_x) {
   for (int ci = 0; ci < CIN; ++ci) {
     const bf16* src = a.x + (static_cast<size_t>(b) * CIN + ci) * a.L;
-    for (int i = threadIdx.x; i < kC0WinPad; i += blockDim.x) {
-      const int p = t0 * kC0S + i;
-      s_x[ci * kC0WinPad + i] = (i < kC0Win && p < a.L) ? __bfloat162float(src[p]) : 0.f;
+    for (int i = threadIdx.x; i < kC0WinB; i += blockDim.x) {
+      const long long p = static_cast<long long>(t0) * kC0S + i;
+      s_x[ci * kC0WinB + i] = (i < kC0Win && p < a.L) ? src[p] : __float2bfloat16_rn(0.f);
     }
   }
 }
 
-template <int CIN>
-__device__ __forceinline__ void load_weights(const Conv0Args& a, int c, float (&w)[CIN * kC0K]) {
-#pragma unroll
-  for (int i = 0; i < CIN * kC0K; ++i) w[i] = bf16_round(a.w[static_cast<size_t>(c) * CIN * kC0K + i]);
+// A fragment of the conv window matrix for outputs tl0 .. tl0+15 of the tile: A[t][k] = x[5 (tl0 + t) + k], k < 10
+__device__ __forceinline__ void conv_a_frag(const bf16* sx, int tl0, int g, int tg, uint32_t (&a)[4]) {
+  const bf16* r0 = sx + (tl0 + g) * kC0S + 2 * tg;
+  const bf16* r1 = r0 + 8 * kC0S;
+  a[0] = pack2(r0[0], r0[1]);
+  a[1] = pack2(r1[0], r1[1]);
+  a[2] = tg == 0 ? pack2(r0[8], r0[9]) : 0u;
+  a[3] = tg == 0 ? pack2(r1[8], r1[9]) : 0u;
 }
 
-// The 25 input samples (per input channel) feeding outputs tl .. tl+3 (tl a multiple of 4): 7 aligned float4 loads.
-template <int CIN>
-__device__ __forceinline__ void load_x4(const float* s_x, int tl, float (&xw)[CIN][28]) {
-#pragma unroll
-  for (int ci = 0; ci < CIN; ++ci) {
-    const float4* p = reinterpret_cast<const float4*>(s_x + ci * kC0WinPad + tl * kC0S);
-#pragma unroll
-    for (int i = 0; i < 7; ++i) {
-      const float4 v = p[i];
-      xw[ci][4 * i] = v.x; xw[ci][4 * i + 1] = v.y; xw[ci][4 * i + 2] = v.z; xw[ci][4 * i + 3] = v.w;
-    }
-  }
+// A fragment of the TRANSPOSED window matrix: A[j][t] = x[5 (tl0 + t) + j]  (rows = taps, k = outputs), taps >= 10 zero
+__device__ __forceinline__ void conv_at_frag(const bf16* sx, int tl0, int g, int tg, uint32_t (&a)[4]) {
+  const bf16* c0 = sx + (tl0 + 2 * tg) * kC0S + g;          // t = 2tg, 2tg+1 ; j = g
+  const bf16* c1 = c0 + 8 * kC0S;                            // t + 8
+  a[0] = pack2(c0[0], c0[kC0S]);
+  a[2] = pack2(c1[0], c1[kC0S]);
+  a[1] = g < 2 ? pack2(c0[8], c0[kC0S + 8]) : 0u;           // j = g + 8 (taps 8, 9)
+  a[3] = g < 2 ? pack2(c1[8], c1[kC0S + 8]) : 0u;
 }
 
-template <int CIN>
-__device__ __forceinline__ float conv_at(const float (&xw)[CIN][28], const float (&w)[CIN * kC0K], int u) {
-  float acc = 0.f;
-#pragma unroll
-  for (int ci = 0; ci < CIN; ++ci)
-#pragma unroll
-    for (int j = 0; j < kC0K; ++j) acc = fmaf(xw[ci][u * kC0S + j], w[ci * kC0K + j], acc);
-  return bf16_round(acc);  // conv1d output is bf16 under autocast
-}
-
-// grid (ceil(chunks / chunks_per_block), B), block C/2 threads: thread owns channels 2*tid, 2*tid+1
+// grid (ceil(chunks / chunks_per_block), B), block C/2 threads = C/64 warps... the forward gives every warp one block of
+// 16 outputs of the 128-output tile and ALL channels (8 warps x 16 = 128 outputs).
 template <int CIN>
 __global__ void __launch_bounds__(256) conv0_fwd_kernel(Conv0Args a, const float* __restrict__ stats,
                                                         const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, bf16* __restrict__ out,
-                                                        int chunks_per_block) {
-  __shared__ __align__(16) float s_x[CIN * kC0WinPad];
+                                                        bf16* __restrict__ dgelu, int chunks_per_block) {
+  extern __shared__ __align__(16) uint8_t smem_c0[];
+  bf16* s_w = reinterpret_cast<bf16*>(smem_c0);                       // [CIN][C][16] taps (10..15 zero)
+  float4* s_p = reinterpret_cast<float4*>(s_w + CIN * a.C * 16);      // [C/2] (scale0, shift0, scale1, shift1)
+  bf16* s_x = reinterpret_cast<bf16*>(s_p + a.C / 2);                 // [CIN][kC0WinB]
   const int b = blockIdx.y;
-  const int c0 = threadIdx.x * 2;
-  float w0[CIN * kC0K], w1[CIN * kC0K];
-  load_weights<CIN>(a, c0, w0);
-  load_weights<CIN>(a, c0 + 1, w1);
-  const float4 st = *reinterpret_cast<const float4*>(stats + (static_cast<size_t>(b) * a.C + c0) * 2);  // m0 r0 m1 r1
-  const float g0 = gamma[c0] * st.y, g1 = gamma[c0 + 1] * st.w;
-  const float b0 = beta[c0] - st.x * g0, b1 = beta[c0 + 1] - st.z * g1;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tg = lane & 3;
+  for (int i = threadIdx.x; i < CIN * a.C * 16; i += blockDim.x) {
+    const int k = i & 15, c = (i >> 4) % a.C, ci = (i >> 4) / a.C;
+    s_w[i] = __float2bfloat16_rn(k < kC0K ? a.w[(static_cast<size_t>(c) * CIN + ci) * kC0K + k] : 0.f);
+  }
+  for (int i = threadIdx.x; i < a.C / 2; i += blockDim.x) {
+    const float4 st = *reinterpret_cast<const float4*>(stats + (static_cast<size_t>(b) * a.C + 2 * i) * 2);  // m0 r0 m1 r1
+    const float g0 = gamma[2 * i] * st.y, g1 = gamma[2 * i + 1] * st.w;
+    s_p[i] = make_float4(g0, beta[2 * i] - st.x * g0, g1, beta[2 * i + 1] - st.z * g1);
+  }
+  const int n_tiles = a.C / 8;
   for (int ch = 0; ch < chunks_per_block; ++ch) {
     const int t0 = (blockIdx.x * chunks_per_block + ch) * kC0TT;
     if (t0 >= a.L_out) break;
     __syncthreads();
-    load_window<CIN>(a, b, t0, s_x);
+    load_window_bf16<CIN>(a, b, t0, s_x);
     __syncthreads();
-    const int nt = min(kC0TT, a.L_out - t0);
-    bf16* o = out + (static_cast<size_t>(b) * a.L_out + t0) * a.C + c0;
-    for (int tl = 0; tl < nt; tl += 4) {
-      float xw[CIN][28];
-      load_x4<CIN>(s_x, tl, xw);
+    const int tl0 = warp * 16;
+    if (t0 + tl0 >= a.L_out) continue;
+    uint32_t af[CIN][4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        if (tl + u < nt) {
-          const float h0 = conv_at<CIN>(xw, w0, u), h1 = conv_at<CIN>(xw, w1, u);
-          const float y0 = gelu_fast(fmaf(h0, g0, b0)), y1 = gelu_fast(fmaf(h1, g1, b1));
-          *reinterpret_cast<uint32_t*>(o + static_cast<size_t>(tl + u) * a.C) = pack_bf16x2(y0, y1);
+    for (int ci = 0; ci < CIN; ++ci) conv_a_frag(s_x + ci * kC0WinB, tl0, g, tg, af[ci]);
+    const int ta = t0 + tl0 + g, tb = ta + 8;
+    const bool va = ta < a.L_out, vb = tb < a.L_out;
+    // lanes with even tg store tile nt, lanes with odd tg store tile nt+1 (4 consecutive channels = 8 bytes each)
+    const int ccol = ((tg & 1) ? 8 : 0) + (tg >> 1) * 4;
+    for (int nt = 0; nt < n_tiles; nt += 2) {
+      uint32_t y[2][2], d[2][2];   // [tile][row]
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        float c[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int ci = 0; ci < CIN; ++ci) {
+          const uint32_t* wp = reinterpret_cast<const uint32_t*>(s_w + (static_cast<size_t>(ci) * a.C + (nt + u) * 8 + g) * 16) + tg;
+          mma16816(c, af[ci], wp[0], wp[4]);
+        }
+        const float4 pr = s_p[(nt + u) * 4 + tg];
+        float y0, y1, y2, y3, d0, d1, d2, d3;
+        gelu_fast2(fmaf(bf16_round(c[0]), pr.x, pr.y), y0, d0);
+        gelu_fast2(fmaf(bf16_round(c[1]), pr.z, pr.w), y1, d1);
+        gelu_fast2(fmaf(bf16_round(c[2]), pr.x, pr.y), y2, d2);
+        gelu_fast2(fmaf(bf16_round(c[3]), pr.z, pr.w), y3, d3);
+        y[u][0] = pack_bf16x2(y0, y1); y[u][1] = pack_bf16x2(y2, y3);
+        d[u][0] = pack_bf16x2(d0, d1); d[u][1] = pack_bf16x2(d2, d3);
+      }
+      // pair exchange inside the quad: even tg keeps tile 0 and receives the neighbour's tile-0 pair; odd tg likewise
+      // for tile 1 -> every lane owns 4 consecutive channels of one row
+      const bool odd = tg & 1;
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const uint32_t ys = odd ? y[0][r] : y[1][r], ds = odd ? d[0][r] : d[1][r];
+        const uint32_t yr = __shfl_xor_sync(0xffffffffu, ys, 1), dr = __shfl_xor_sync(0xffffffffu, ds, 1);
+        const uint2 yo = odd ? make_uint2(yr, y[1][r]) : make_uint2(y[0][r], yr);
+        const uint2 dd = odd ? make_uint2(dr, d[1][r]) : make_uint2(d[0][r], dr);
+        const int t = r == 0 ? ta : tb;
+        if (r == 0 ? va : vb) {
+          const size_t o = (static_cast<size_t>(b) * a.L_out + t) * a.C + nt * 8 + ccol;
+          *reinterpret_cast<uint2*>(out + o) = yo;
+          if (dgelu != nullptr) *reinterpret_cast<uint2*>(dgelu + o) = dd;
         }
       }
     }
   }
 }
 
-// Backward, the one pass over dY: red[b, 0, c] += S1, red[b, 1, c] += S2, red[b, 2 + a, c] += P[a]
+// Backward, the one pass over dY: red[b, 0, c] += S1, red[b, 1, c] += S2, red[b, 2 + a, c] += P[a].
+// Warp w owns channels [64 w, 64 w + 64) (8 n-tiles) and walks every 16-output block of the CTA's time range:
+// conv (mma) -> hhat; dz = dY * saved GELU'; S1 += dz, S2 += dz hhat; P^T[tap][ch] += X^T[tap][t] dz[t][ch] (mma, dz
+// rounded to bf16 like autograd's bf16 conv weight gradient, transposed into a B fragment with movmatrix).
 template <int CIN>
-__global__ void __launch_bounds__(256) conv0_bwd_kernel(Conv0Args a, const float* __restrict__ stats,
-                                                        const float* __restrict__ gamma,
-                                                        const float* __restrict__ beta, const bf16* __restrict__ dy,
-                                                        float* __restrict__ red, int chunks_per_block) {
+__global__ void __launch_bounds__(256, 2) conv0_bwd_kernel(Conv0Args a, const float* __restrict__ stats,
+                                                           const bf16* __restrict__ dy, const bf16* __restrict__ dgelu,
+                                                           float* __restrict__ red, int chunks_per_block) {
   constexpr int NA = CIN * kC0K;
-  __shared__ __align__(16) float s_x[CIN * kC0WinPad];
+  __shared__ __align__(16) bf16 s_x[CIN * kC0WinB];
+  __shared__ float4 s_mr[256];   // (mean0, rstd0, mean1, rstd1) of channel pair i (C = 512)
   const int b = blockIdx.y;
-  const int c0 = threadIdx.x * 2;
-  float w0[NA], w1[NA];
-  load_weights<CIN>(a, c0, w0);
-  load_weights<CIN>(a, c0 + 1, w1);
-  const float4 st = *reinterpret_cast<const float4*>(stats + (static_cast<size_t>(b) * a.C + c0) * 2);  // m0 r0 m1 r1
-  const float ga0 = gamma[c0], ga1 = gamma[c0 + 1], be0 = beta[c0], be1 = beta[c0 + 1];
-  float s10 = 0.f, s20 = 0.f, s11 = 0.f, s21 = 0.f;
-  float p0[NA], p1[NA];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tg = lane & 3;
+  const int c_base = warp * 64;
+  // weights of this warp's 8 n-tiles as B fragments (bf16-rounded), (mean, rstd) of its channel pairs
+  uint32_t wb[CIN][8][2];
+  for (int i = threadIdx.x; i < a.C / 2; i += blockDim.x)
+    s_mr[i] = *reinterpret_cast<const float4*>(stats + (static_cast<size_t>(b) * a.C + 2 * i) * 2);
 #pragma unroll
-  for (int i = 0; i < NA; ++i) { p0[i] = 0.f; p1[i] = 0.f; }
+  for (int nt = 0; nt < 8; ++nt) {
+    const int c = c_base + nt * 8 + g;
+#pragma unroll
+    for (int ci = 0; ci < CIN; ++ci) {
+      const float* wr = a.w + (static_cast<size_t>(c) * CIN + ci) * kC0K;
+      wb[ci][nt][0] = pack_bf16x2(wr[2 * tg], wr[2 * tg + 1]);
+      wb[ci][nt][1] = tg == 0 ? pack_bf16x2(wr[8], wr[9]) : 0u;
+    }
+  }
+  float s1[8][2], s2[8][2], pt[CIN][8][4];
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    s1[nt][0] = s1[nt][1] = s2[nt][0] = s2[nt][1] = 0.f;
+#pragma unroll
+    for (int ci = 0; ci < CIN; ++ci) pt[ci][nt][0] = pt[ci][nt][1] = pt[ci][nt][2] = pt[ci][nt][3] = 0.f;
+  }
   for (int ch = 0; ch < chunks_per_block; ++ch) {
     const int t0 = (blockIdx.x * chunks_per_block + ch) * kC0TT;
     if (t0 >= a.L_out) break;
     __syncthreads();
-    load_window<CIN>(a, b, t0, s_x);
+    load_window_bf16<CIN>(a, b, t0, s_x);
     __syncthreads();
-    const int nt = min(kC0TT, a.L_out - t0);
-    const bf16* d = dy + (static_cast<size_t>(b) * a.L_out + t0) * a.C + c0;
-    for (int tl = 0; tl < nt; tl += 4) {
-      float xw[CIN][28];
-      load_x4<CIN>(s_x, tl, xw);
-      uint32_t dv[4];
+    const int nblk = min(kC0TT, a.L_out - t0);
+    for (int tl0 = 0; tl0 < nblk; tl0 += 16) {
+      uint32_t af[CIN][4], atf[CIN][4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u)
-        dv[u] = (tl + u < nt) ? *reinterpret_cast<const uint32_t*>(d + static_cast<size_t>(tl + u) * a.C) : 0u;
+      for (int ci = 0; ci < CIN; ++ci) {
+        conv_a_frag(s_x + ci * kC0WinB, tl0, g, tg, af[ci]);
+        conv_at_frag(s_x + ci * kC0WinB, tl0, g, tg, atf[ci]);
+      }
+      const int ta = t0 + tl0 + g, tb = ta + 8;
+      const bool va = ta < a.L_out, vb = tb < a.L_out;
+      const size_t oa = (static_cast<size_t>(b) * a.L_out + ta) * a.C + c_base + 2 * tg;
+      const size_t ob = oa + static_cast<size_t>(8) * a.C;
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const float hh0 = (conv_at<CIN>(xw, w0, u) - st.x) * st.y, hh1 = (conv_at<CIN>(xw, w1, u) - st.z) * st.w;
-        const float2 dd = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&dv[u]));   // 0 past the end
-        const float dz0 = dd.x * gelu_fast_grad(fmaf(hh0, ga0, be0)), dz1 = dd.y * gelu_fast_grad(fmaf(hh1, ga1, be1));
-        s10 += dz0; s20 = fmaf(dz0, hh0, s20); s11 += dz1; s21 = fmaf(dz1, hh1, s21);
+      for (int nt = 0; nt < 8; ++nt) {
+        float c[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int ci = 0; ci < CIN; ++ci)
+        for (int ci = 0; ci < CIN; ++ci) mma16816(c, af[ci], wb[ci][nt][0], wb[ci][nt][1]);
+        const uint32_t dya = va ? *reinterpret_cast<const uint32_t*>(dy + oa + nt * 8) : 0u;
+        const uint32_t dyb = vb ? *reinterpret_cast<const uint32_t*>(dy + ob + nt * 8) : 0u;
+        const uint32_t dga = va ? *reinterpret_cast<const uint32_t*>(dgelu + oa + nt * 8) : 0u;
+        const uint32_t dgb = vb ? *reinterpret_cast<const uint32_t*>(dgelu + ob + nt * 8) : 0u;
+        const float2 ya = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&dya));
+        const float2 yb = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&dyb));
+        const float2 ga = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&dga));
+        const float2 gb = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&dgb));
+        const float z0 = ya.x * ga.x, z1 = ya.y * ga.y, z2 = yb.x * gb.x, z3 = yb.y * gb.y;   // dz (0 past the end)
+        const float4 mr = s_mr[(c_base >> 1) + nt * 4 + tg];
+        const float h0 = (bf16_round(c[0]) - mr.x) * mr.y, h1 = (bf16_round(c[1]) - mr.z) * mr.w;
+        const float h2 = (bf16_round(c[2]) - mr.x) * mr.y, h3 = (bf16_round(c[3]) - mr.z) * mr.w;
+        s1[nt][0] += z0 + z2; s1[nt][1] += z1 + z3;
+        s2[nt][0] = fmaf(z0, h0, fmaf(z2, h2, s2[nt][0]));
+        s2[nt][1] = fmaf(z1, h1, fmaf(z3, h3, s2[nt][1]));
+        const uint32_t b0 = movmatrix_trans(pack_bf16x2(z0, z1)), b1 = movmatrix_trans(pack_bf16x2(z2, z3));
 #pragma unroll
-          for (int j = 0; j < kC0K; ++j) {
-            const float xv = xw[ci][u * kC0S + j];
-            p0[ci * kC0K + j] = fmaf(dz0, xv, p0[ci * kC0K + j]);
-            p1[ci * kC0K + j] = fmaf(dz1, xv, p1[ci * kC0K + j]);
-          }
+        for (int ci = 0; ci < CIN; ++ci) mma16816(pt[ci][nt], atf[ci], b0, b1);
       }
     }
   }
-  float* r = red + static_cast<size_t>(b) * (2 + NA) * a.C + c0;
-  atomicAdd(r, s10); atomicAdd(r + 1, s11);
-  atomicAdd(r + a.C, s20); atomicAdd(r + a.C + 1, s21);
+  // S1 / S2: sum over the 8 lanes (g) that share a channel pair; P^T: fragments already hold sums over outputs
+  float* r = red + static_cast<size_t>(b) * (2 + NA) * a.C + c_base;
 #pragma unroll
-  for (int i = 0; i < NA; ++i) {
-    atomicAdd(r + static_cast<size_t>(2 + i) * a.C, p0[i]);
-    atomicAdd(r + static_cast<size_t>(2 + i) * a.C + 1, p1[i]);
+  for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      float v1 = s1[nt][e], v2 = s2[nt][e];
+#pragma unroll
+      for (int o = 4; o < 32; o <<= 1) {
+        v1 += __shfl_xor_sync(0xffffffffu, v1, o);
+        v2 += __shfl_xor_sync(0xffffffffu, v2, o);
+      }
+      if (g == 0) {
+        atomicAdd(r + nt * 8 + 2 * tg + e, v1);
+        atomicAdd(r + a.C + nt * 8 + 2 * tg + e, v2);
+      }
+    }
+#pragma unroll
+    for (int ci = 0; ci < CIN; ++ci) {
+      float* rp = r + static_cast<size_t>(2 + ci * kC0K) * a.C + nt * 8 + 2 * tg;
+      atomicAdd(rp + static_cast<size_t>(g) * a.C, pt[ci][nt][0]);
+      atomicAdd(rp + static_cast<size_t>(g) * a.C + 1, pt[ci][nt][1]);
+      if (g < 2) {
+        atomicAdd(rp + static_cast<size_t>(g + 8) * a.C, pt[ci][nt][2]);
+        atomicAdd(rp + static_cast<size_t>(g + 8) * a.C + 1, pt[ci][nt][3]);
+      }
+    }
   }
 }
 
@@ -310,7 +409,7 @@ __global__ void __launch_bounds__(256) conv0_bwd_finalize_kernel(Conv0Args a, co
 static int check_conv0(int Cin, int C, int k, int stride) {
   if (k != kC0K || stride != kC0S) { set_error("conv0: only k=10, stride=5 is built (got k=%d s=%d)", k, stride); return WJ_ERR_ARG; }
   if (Cin < 1 || Cin > kC0MaxCin) { set_error("conv0: Cin must be 1 or 2"); return WJ_ERR_ARG; }
-  if (C % 2 != 0 || C / 2 > 256 || C / 2 < 32) { set_error("conv0: C must be even, 64..512"); return WJ_ERR_ARG; }
+  if (C != 512) { set_error("conv0: the tensor-core kernels are built for C = 512 channels (8 warps x 64); got %d", C); return WJ_ERR_ARG; }
   return WJ_OK;
 }
 
@@ -322,7 +421,7 @@ extern "C" int wj_conv0_moment_count(int Cin) { return conv0_moment_count(Cin); 
 
 extern "C" int wj_conv0_gn_gelu_fwd(const void* x_bf16, const float* w, const float* gamma, const float* beta, int B,
                                     int Cin, int L, int C, int k, int stride, float eps, double* moments, float* stats,
-                                    void* out_bf16, void* stream) {
+                                    void* out_bf16, void* dgelu_bf16, void* stream) {
   if (B <= 0) return WJ_OK;
   int rc = check_conv0(Cin, C, k, stride);
   if (rc) return rc;
@@ -334,26 +433,29 @@ extern "C" int wj_conv0_gn_gelu_fwd(const void* x_bf16, const float* w, const fl
   const int cpb = 4;
   dim3 grid((chunks + cpb - 1) / cpb, B);
   bf16* out = reinterpret_cast<bf16*>(out_bf16);
+  bf16* dg = reinterpret_cast<bf16*>(dgelu_bf16);
+  const size_t smem = static_cast<size_t>(Cin) * C * 16 * 2 + static_cast<size_t>(C / 2) * 16 + static_cast<size_t>(Cin) * kC0WinB * 2 + 16;
   if (Cin == 1) {
     conv0_moments_kernel<1><<<B, 512, 0, st>>>(a, moments);
     conv0_stats_kernel<1><<<B, C, 0, st>>>(a, moments, eps, stats);
-    conv0_fwd_kernel<1><<<grid, C / 2, 0, st>>>(a, stats, gamma, beta, out, cpb);
+    conv0_fwd_kernel<1><<<grid, 256, smem, st>>>(a, stats, gamma, beta, out, dg, cpb);
   } else {
     conv0_moments_kernel<2><<<B, 512, 0, st>>>(a, moments);
     conv0_stats_kernel<2><<<B, C, 0, st>>>(a, moments, eps, stats);
-    conv0_fwd_kernel<2><<<grid, C / 2, 0, st>>>(a, stats, gamma, beta, out, cpb);
+    conv0_fwd_kernel<2><<<grid, 256, smem, st>>>(a, stats, gamma, beta, out, dg, cpb);
   }
   return check_launch("conv0_gn_gelu_fwd", 3);
 }
 
 extern "C" int wj_conv0_gn_gelu_bwd(const void* x_bf16, const float* w, const float* gamma, const float* beta, int B,
                                     int Cin, int L, int C, int k, int stride, float eps, const double* moments,
-                                    const float* stats, const void* dy_bf16, float* red_scratch, float* dw,
-                                    float* dgamma, float* dbeta, void* stream) {
+                                    const float* stats, const void* dy_bf16, const void* dgelu_bf16, float* red_scratch,
+                                    float* dw, float* dgamma, float* dbeta, void* stream) {
   if (B <= 0) return WJ_OK;
   int rc = check_conv0(Cin, C, k, stride);
   if (rc) return rc;
-  (void)eps;
+  if (dgelu_bf16 == nullptr) { set_error("conv0 backward needs the GELU' saved by the forward"); return WJ_ERR_ARG; }
+  (void)eps; (void)beta;
   cudaStream_t st = WJ_STREAM(stream);
   Conv0Args a;
   a.x = reinterpret_cast<const bf16*>(x_bf16); a.w = w; a.B = B; a.Cin = Cin; a.L = L; a.C = C;
@@ -361,15 +463,16 @@ extern "C" int wj_conv0_gn_gelu_bwd(const void* x_bf16, const float* w, const fl
   const int na = Cin * kC0K;
   cudaMemsetAsync(red_scratch, 0, static_cast<size_t>(B) * (2 + na) * C * sizeof(float), st);
   const int chunks = (a.L_out + kC0TT - 1) / kC0TT;
-  const int cpb = 13;   // 2*(2+na) atomics per thread at the end: few, long blocks (4 per 2 s instance)
+  const int cpb = 13;   // 2 + na accumulators per channel flushed with atomics at the end: few, long blocks
   dim3 grid((chunks + cpb - 1) / cpb, B);
   const bf16* dy = reinterpret_cast<const bf16*>(dy_bf16);
+  const bf16* dg = reinterpret_cast<const bf16*>(dgelu_bf16);
   dim3 fgrid((C + 31) / 32), fblock(32, 8);
   if (Cin == 1) {
-    conv0_bwd_kernel<1><<<grid, C / 2, 0, st>>>(a, stats, gamma, beta, dy, red_scratch, cpb);
+    conv0_bwd_kernel<1><<<grid, C / 2, 0, st>>>(a, stats, dy, dg, red_scratch, cpb);
     conv0_bwd_finalize_kernel<1><<<fgrid, fblock, 0, st>>>(a, moments, stats, gamma, red_scratch, dw, dgamma, dbeta);
   } else {
-    conv0_bwd_kernel<2><<<grid, C / 2, 0, st>>>(a, stats, gamma, beta, dy, red_scratch, cpb);
+    conv0_bwd_kernel<2><<<grid, C / 2, 0, st>>>(a, stats, dy, dg, red_scratch, cpb);
     conv0_bwd_finalize_kernel<2><<<fgrid, fblock, 0, st>>>(a, moments, stats, gamma, red_scratch, dw, dgamma, dbeta);
   }
   return check_launch("conv0_gn_gelu_bwd", 2);

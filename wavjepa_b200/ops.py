@@ -256,7 +256,9 @@ def conv0_workspaces(B: int, Cin: int, C: int, device, backward: bool = False):
 
 
 def conv0_fwd(x: torch.Tensor, w: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, out: torch.Tensor,
-              moments: torch.Tensor, stats: torch.Tensor, k: int = 10, stride: int = 5, eps: float = 1e-5) -> None:
+              moments: torch.Tensor, stats: torch.Tensor, dgelu: Optional[torch.Tensor] = None, k: int = 10,
+              stride: int = 5, eps: float = 1e-5) -> None:
+    """dgelu (bf16, same shape as out): receives GELU'(z) for the backward; None = inference."""
     B, Cin, L = x.shape
     assert x.dtype == torch.bfloat16 and x.is_contiguous() and w.dtype == torch.float32
     assert moments.dtype == torch.float64 and stats.dtype == torch.float32
@@ -264,17 +266,19 @@ def conv0_fwd(x: torch.Tensor, w: torch.Tensor, gamma: torch.Tensor, beta: torch
     check(lib.wj_conv0_gn_gelu_fwd(C.c_void_p(_ptr(x)), C.c_void_p(_ptr(w)), C.c_void_p(_ptr(gamma)),
                                    C.c_void_p(_ptr(beta)), B, Cin, L, w.shape[0], k, stride, C.c_float(eps),
                                    C.c_void_p(_ptr(moments)), C.c_void_p(_ptr(stats)), C.c_void_p(_ptr(out)),
-                                   _stream()))
+                                   C.c_void_p(_ptr(dgelu)), _stream()))
 
 
-def conv0_bwd(x, w, gamma, beta, moments, stats, dy, red_scratch, dw, dgamma, dbeta, k: int = 10, stride: int = 5,
+def conv0_bwd(x, w, gamma, beta, moments, stats, dy, dgelu, red_scratch, dw, dgamma, dbeta, k: int = 10, stride: int = 5,
               eps: float = 1e-5) -> None:
     B, Cin, L = x.shape
     assert red_scratch.dtype == torch.float32 and red_scratch.numel() >= B * (2 + Cin * 10) * w.shape[0]
+    assert dgelu.dtype == torch.bfloat16 and dgelu.shape == dy.shape and dgelu.is_contiguous() and dy.is_contiguous()
     lib = _lib.load()
     p = lambda t: C.c_void_p(_ptr(t))
     check(lib.wj_conv0_gn_gelu_bwd(p(x), p(w), p(gamma), p(beta), B, Cin, L, w.shape[0], k, stride, C.c_float(eps),
-                                   p(moments), p(stats), p(dy), p(red_scratch), p(dw), p(dgamma), p(dbeta), _stream()))
+                                   p(moments), p(stats), p(dy), p(dgelu), p(red_scratch), p(dw), p(dgamma), p(dbeta),
+                                   _stream()))
 
 
 # ----------------------------------------------------------------------------------------------------- norms
