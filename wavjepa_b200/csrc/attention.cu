@@ -205,12 +205,12 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(const bf16* __restrict__ 
 // One CTA per (sequence, head); Q, K, V, dO of the whole sequence live in smem (NPAD rows each).
 //   phase A: warps own 16-query blocks -> dQ;  phase B: warps own 16-key blocks -> dK, dV.  No atomics.
 template <int DH>
-__global__ void __launch_bounds__(128, (DH == 32 ? 4 : 2)) attn_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ out,
+__global__ void __launch_bounds__(128, (DH == 32 ? 4 : 3)) attn_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ out,
                                                        const bf16* __restrict__ dout, const float* __restrict__ lse2,
                                                        const int* __restrict__ cu, int D, int H, int NPAD, float scale,
                                                        float scale_log2, bf16* __restrict__ dqkv) {
   constexpr int PITCH = DH + 8;
-  constexpr int NT = (DH == 32) ? 4 : 8;   // 8-wide tiles per inner block: 32-wide blocks keep the DH=32 kernel at
+  constexpr int NT = 4;                    // 8-wide tiles per inner block: 32-wide blocks keep the DH=32 kernel at
   constexpr int KB = NT * 8;               // <= 128 registers (4 CTAs / SM); the lse / delta arrays stay padded to 64
   extern __shared__ __align__(16) uint8_t smem_attn[];
   bf16* sQ = reinterpret_cast<bf16*>(smem_attn);
