@@ -187,9 +187,11 @@ int wj_target_accum(const float* x, const float* rowsum, int B, int T, int D, fl
 /* Variable-length multi-head attention over packed tokens: qkv bf16 [tokens, 3*D] (q|k|v), sequences given by
  * cu_seqlens [n_seqs+1], softmax(q k^T / sqrt(D/H)) v, head dim 32 or 64.  out bf16 [tokens, D];
  * lse2 fp32 [tokens, H] = log2-sum-exp2 of the scaled logits (saved for the backward; may be NULL).
+ * total_tokens = rows of qkv.  Sequences of <= 128 tokens run on tcgen05 (S = Q K^T and O = P V as UMMAs with TMEM
+ * accumulators, softmax one query row per thread); longer ones on the mma.sync kernel.
  * Reference: F.scaled_dot_product_attention with key_padding_mask inside nn.MultiheadAttention. */
-int wj_attn_varlen_fwd(const void* qkv_bf16, const int* cu_seqlens, int n_seqs, int max_len, int D, int H,
-                       void* out_bf16, float* lse2, void* stream);
+int wj_attn_varlen_fwd(const void* qkv_bf16, const int* cu_seqlens, int n_seqs, int max_len, int64_t total_tokens, int D,
+                       int H, void* out_bf16, float* lse2, void* stream);
 int wj_attn_varlen_bwd(const void* qkv_bf16, const void* out_bf16, const void* dout_bf16, const float* lse2,
                        const int* cu_seqlens, int n_seqs, int max_len, int D, int H, void* dqkv_bf16, void* stream);
 

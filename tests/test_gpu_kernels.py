@@ -340,6 +340,8 @@ def _attn_ref(qkv, cu, D, H):
     for s in range(len(cu) - 1):
         x = qkv[cu[s]:cu[s + 1]]
         n = x.shape[0]
+        if n == 0:
+            continue
         q, k, v = (x[:, i * D:(i + 1) * D].reshape(n, H, dh).transpose(0, 1) for i in range(3))
         o = F.scaled_dot_product_attention(q, k, v)
         outs.append(o.transpose(0, 1).reshape(n, D))
@@ -347,7 +349,8 @@ def _attn_ref(qkv, cu, D, H):
 
 
 @pytest.mark.parametrize("D,H,lens", [(768, 12, [39, 72, 20, 1, 64, 65]), (384, 12, [85, 122, 128, 17]),
-                                      (768, 12, [200, 200, 200]), (384, 12, [250, 3])])
+                                      (768, 12, [200, 200, 200]), (384, 12, [250, 3]), (384, 12, [5, 0, 128, 0, 33]),
+                                      (768, 12, [128] * 40 + [7])])
 def test_attention_fwd_bwd(D, H, lens):
     cu_l = [0]
     for n in lens:

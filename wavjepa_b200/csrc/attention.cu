@@ -355,11 +355,21 @@ __global__ void __launch_bounds__(128, (DH == 32 ? 4 : 3)) attn_bwd_kernel(const
 
 using namespace wj;
 
-extern "C" int wj_attn_varlen_fwd(const void* qkv_bf16, const int* cu_seqlens, int n_seqs, int max_len, int D, int H,
-                                  void* out_bf16, float* lse2, void* stream) {
+namespace wj {
+int attn_fwd_tc_launch(const void* qkv, const int* cu, int n_seqs, int max_len, long long total_tokens, int D, int H,
+                       void* out, float* lse2, cudaStream_t st);
+}
+
+extern "C" int wj_attn_varlen_fwd(const void* qkv_bf16, const int* cu_seqlens, int n_seqs, int max_len, int64_t total_tokens,
+                                  int D, int H, void* out_bf16, float* lse2, void* stream) {
   if (n_seqs <= 0 || max_len <= 0) return WJ_OK;
   const int dh = D / H;
   if (D % H != 0 || (dh != 32 && dh != 64)) { set_error("wj_attn_varlen_fwd: head dim must be 32 or 64 (D=%d H=%d)", D, H); return WJ_ERR_ARG; }
+  {
+    // sequences of <= 128 tokens: tcgen05 kernel (attention_tc.cu); longer ones: the mma.sync kernel below
+    const int rc = wj::attn_fwd_tc_launch(qkv_bf16, cu_seqlens, n_seqs, max_len, total_tokens, D, H, out_bf16, lse2, WJ_STREAM(stream));
+    if (rc <= 0) return rc;
+  }
   const int npad = (max_len + 15) & ~15;
   const size_t smem = static_cast<size_t>(3) * npad * (dh + 8) * 2;
   if (smem > 227 * 1024) { set_error("wj_attn_varlen_fwd: sequence of %d tokens (head dim %d) exceeds the shared-memory resident design", max_len, dh); return WJ_ERR_ARG; }

@@ -1,0 +1,301 @@
+// tcgen05 forward attention for short packed sequences (<= 128 tokens: the student's visible context sets and the
+// predictor's context + target sets of wavjepa/jepa.py:397,438).  One work item = one (sequence, head):
+//
+//   TMA      Q, K, V tiles [128 tokens x dh] (128B swizzle for dh 64, 64B for dh 32) straight out of qkv [tokens, 3D],
+//            double-buffered for dh 32 so that the next item's tiles land while this item's softmax runs
+//   UMMA #1  S = Q K^T        128 x n16 x dh    (tcgen05.mma, fp32 accumulator in TMEM columns [0, 128))
+//   softmax  4 warps, one query row per thread: tcgen05.ld of its S row in 32-column chunks, masked max, then
+//            exp2 / sum; P (bf16 pairs) goes straight back to TMEM with tcgen05.st over the S columns already consumed
+//            (P chunk c lands on columns [16c, 16c+16), S chunk c lives on [32c, 32c+32))
+//   UMMA #2  O = P V          128 x dh x n16    (A = P from TMEM, B = V MN-major from smem; TMEM columns [64, 64+dh))
+//   epilogue O row / sum -> bf16 -> out[token, head*dh ...], lse2[token, head]
+//
+// 128 TMEM columns and 48 KB of smem per CTA: four CTAs (160 threads each) share an SM and fill each other's latency
+// gaps; the single-KV-block structure needs no online softmax.  Rows / keys past the end of the sequence are other
+// sequences' (finite) tokens or TMA zero fill: keys >= n are masked, query rows >= n are never stored.
+#include "common.cuh"
+
+namespace wj {
+
+constexpr int kAtQ = 128;   // query rows per tile = TMEM lanes
+constexpr int kAtK = 128;   // keys per tile
+
+struct AttnTcParams {
+  const int* cu;
+  int n_seqs, D, H, items;
+  float scale_log2;
+  bf16* out;
+  float* lse2;
+};
+
+template <int DH> struct AttnTcCfg {
+  static constexpr int TILE = kAtQ * DH * 2;                 // bytes of one [128 x DH] bf16 tile
+  static constexpr int STAGES = DH == 32 ? 2 : 1;            // 48 KB either way
+  static constexpr int BAR_OFF = STAGES * 3 * TILE;
+  static constexpr int SMEM = BAR_OFF + 128 + 1024;          // + alignment slack
+  static constexpr uint32_t SWZ = DH == 64 ? 2u : 4u;        // UMMA layout type: 128B / 64B swizzle
+  static constexpr uint32_t SBO = DH == 64 ? 1024u : 512u;   // 8 rows x row pitch
+  static constexpr uint32_t P_COL = 0, O_COL = 64;           // TMEM columns of P (bf16 pairs) and O inside the S block
+};
+
+__device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(layout) << 61;
+  return d;
+}
+// D[tmem] (+)= A[tmem] * B[smem]: the A operand (bf16, row = lane, two K elements per 32-bit column) read from TMEM
+__device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x32_x16(uint32_t taddr, const uint32_t (&w)[16]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+               ::"r"(taddr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]), "r"(w[8]),
+               "r"(w[9]), "r"(w[10]), "r"(w[11]), "r"(w[12]), "r"(w[13]), "r"(w[14]), "r"(w[15])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+template <int DH>
+__global__ void __launch_bounds__(160, 4) attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const AttnTcParams p) {
+  using Cfg = AttnTcCfg<DH>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bar_load = reinterpret_cast<uint64_t*>(smem + Cfg::BAR_OFF);   // [STAGES]
+  uint64_t* bar_s = bar_load + 2;                 // S accumulator complete (MMA commit)
+  uint64_t* bar_p = bar_load + 3;                 // P written by the 4 softmax warps (S fully read)
+  uint64_t* bar_o = bar_load + 4;                 // O accumulator complete (MMA commit)
+  uint64_t* bar_done = bar_load + 5;              // O read by the 4 epilogue warps: TMEM (and this stage's smem) reusable
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_load + 6);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tmQ);
+      mbar_init(bar_load, 1);
+      mbar_init(bar_load + 1, 1);
+      mbar_init(bar_s, 1);
+      mbar_init(bar_p, 4);
+      mbar_init(bar_o, 1);
+      mbar_init(bar_done, 4);
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, 128);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tS = tmem_base, tP = tmem_base + Cfg::P_COL, tO = tmem_base + Cfg::O_COL;
+
+  if (warp == 4) {
+    // ================================================================================ control: TMA + MMA issue
+    if (lane == 0) {
+      constexpr uint32_t idesc_o = umma_idesc_bf16(kAtQ, DH, false, true);
+      auto issue_loads = [&](int item, int stage) {
+        const int s = item / p.H, head = item - s * p.H;
+        const int start = p.cu[s];
+        uint8_t* base = smem + stage * 3 * Cfg::TILE;
+        mbar_arrive_expect_tx(bar_load + stage, 3 * Cfg::TILE);
+        tma_load_2d(base, &tmQ, bar_load + stage, head * DH, start);
+        tma_load_2d(base + Cfg::TILE, &tmQ, bar_load + stage, p.D + head * DH, start);
+        tma_load_2d(base + 2 * Cfg::TILE, &tmQ, bar_load + stage, 2 * p.D + head * DH, start);
+      };
+      uint32_t ph_load[2] = {0, 0}, ph_p = 0, ph_done = 0;
+      int it = 0;
+      if (STAGES == 2 && blockIdx.x < p.items) issue_loads(blockIdx.x, 0);
+      for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
+        const int stage = STAGES == 2 ? (it & 1) : 0;
+        const int s = item / p.H;
+        const int n = p.cu[s + 1] - p.cu[s];
+        const int n16 = (n + 15) & ~15;
+        const uint32_t idesc_s = umma_idesc_bf16(kAtQ, n16 > 0 ? n16 : 16, false, false);
+        if (it > 0) {   // the previous item's O has been read: its MMAs are complete, TMEM and its smem stage are free
+          mbar_wait(bar_done, ph_done);
+          ph_done ^= 1;
+        }
+        if (STAGES == 1) issue_loads(item, 0);
+        mbar_wait(bar_load + stage, ph_load[stage]);
+        ph_load[stage] ^= 1;
+        tc_fence_after();
+        const uint32_t sQ = smem_u32(smem + stage * 3 * Cfg::TILE), sK = sQ + Cfg::TILE, sV = sK + Cfg::TILE;
+#pragma unroll
+        for (int ks = 0; ks < DH / 16; ++ks)
+          umma_bf16(tS, umma_smem_desc(sQ + ks * 32, 0, Cfg::SBO, Cfg::SWZ), umma_smem_desc(sK + ks * 32, 0, Cfg::SBO, Cfg::SWZ),
+                    idesc_s, ks > 0 ? 1u : 0u);
+        umma_commit(bar_s);
+        if (STAGES == 2 && item + gridDim.x < p.items) issue_loads(item + gridDim.x, stage ^ 1);   // lands during the softmax
+        mbar_wait(bar_p, ph_p);
+        ph_p ^= 1;
+        tc_fence_after();
+        // O = P V over the 16-key steps that hold valid keys (at least one, so that bar_o always completes)
+        const uint64_t vdesc = umma_smem_desc(sV, Cfg::TILE, Cfg::SBO, Cfg::SWZ);
+        const int steps = n16 > 0 ? n16 / 16 : 1;
+        for (int kk = 0; kk < steps; ++kk)
+          umma_bf16_ts(tO, tP + kk * 8, vdesc + static_cast<uint64_t>((kk * 16 * DH * 2) >> 4), idesc_o, kk > 0 ? 1u : 0u);
+        umma_commit(bar_o);
+      }
+    }
+  } else {
+    // ================================================================================ softmax + epilogue (4 warps)
+    const int row = warp * 32 + lane;                       // query row of the tile = TMEM lane
+    const uint32_t lane_addr = static_cast<uint32_t>(warp * 32) << 16;
+    uint32_t ph_s = 0, ph_o = 0;
+    int nstart = 0, nn = 0;
+    if (blockIdx.x < p.items) {
+      const int s = blockIdx.x / p.H;
+      nstart = p.cu[s];
+      nn = p.cu[s + 1] - nstart;
+    }
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+      const int head = item % p.H;
+      const int start = nstart, n = nn;
+      if (item + gridDim.x < p.items) {   // next item's bounds: the load latency hides behind this item
+        const int s = (item + gridDim.x) / p.H;
+        nstart = p.cu[s];
+        nn = p.cu[s + 1] - nstart;
+      }
+      mbar_wait(bar_s, ph_s);
+      ph_s ^= 1;
+      tc_fence_after();
+      // pass 1: row maximum over the valid keys
+      float m = -INFINITY;
+#pragma unroll 1
+      for (int c0 = 0; c0 < n; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(tS + lane_addr + c0, v);
+        tmem_ld_wait();
+        if (c0 + 32 <= n) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) m = fmaxf(m, __uint_as_float(v[j]));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (c0 + j < n) m = fmaxf(m, __uint_as_float(v[j]));
+        }
+      }
+      const float ms = m * p.scale_log2;
+      // pass 2: p = exp2(s * scale - m * scale), row sum; P (bf16 pairs) -> TMEM columns [16 c, 16 c + 16)
+      float l = 0.f;
+#pragma unroll 1
+      for (int c0 = 0; c0 < n; c0 += 32) {
+        uint32_t v[32], w[16];
+        tmem_ld_32x32(tS + lane_addr + c0, v);
+        tmem_ld_wait();
+        if (c0 + 32 <= n) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            const float p0 = ex2_approx(fmaf(__uint_as_float(v[j]), p.scale_log2, -ms));
+            const float p1 = ex2_approx(fmaf(__uint_as_float(v[j + 1]), p.scale_log2, -ms));
+            l += p0 + p1;
+            w[j >> 1] = pack_bf16x2(p0, p1);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            const float p0 = c0 + j < n ? ex2_approx(fmaf(__uint_as_float(v[j]), p.scale_log2, -ms)) : 0.f;
+            const float p1 = c0 + j + 1 < n ? ex2_approx(fmaf(__uint_as_float(v[j + 1]), p.scale_log2, -ms)) : 0.f;
+            l += p0 + p1;
+            w[j >> 1] = pack_bf16x2(p0, p1);
+          }
+        }
+        tmem_st_32x32_x16(tP + lane_addr + (c0 >> 1), w);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_p);
+      // epilogue: O row / l
+      mbar_wait(bar_o, ph_o);
+      ph_o ^= 1;
+      tc_fence_after();
+      const float inv = 1.0f / l;
+      bf16* op = p.out + static_cast<long long>(start + row) * p.D + head * DH;
+      uint32_t o[DH / 32][32];
+#pragma unroll
+      for (int c = 0; c < DH / 32; ++c) tmem_ld_32x32(tO + lane_addr + c * 32, o[c]);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_done);
+      if (row < n) {
+#pragma unroll
+        for (int c = 0; c < DH / 32; ++c)
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            uint4 w;
+            w.x = pack_bf16x2(__uint_as_float(o[c][j]) * inv, __uint_as_float(o[c][j + 1]) * inv);
+            w.y = pack_bf16x2(__uint_as_float(o[c][j + 2]) * inv, __uint_as_float(o[c][j + 3]) * inv);
+            w.z = pack_bf16x2(__uint_as_float(o[c][j + 4]) * inv, __uint_as_float(o[c][j + 5]) * inv);
+            w.w = pack_bf16x2(__uint_as_float(o[c][j + 6]) * inv, __uint_as_float(o[c][j + 7]) * inv);
+            *reinterpret_cast<uint4*>(op + c * 32 + j) = w;
+          }
+        if (p.lse2 != nullptr) p.lse2[static_cast<long long>(start + row) * p.H + head] = ms + log2f(l);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 128);
+  }
+}
+
+typedef CUresult (*PFN_encodeTiledA)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// Returns WJ_OK and launches when the problem fits this kernel; 1 when the caller should use the mma.sync kernel.
+int attn_fwd_tc_launch(const void* qkv, const int* cu, int n_seqs, int max_len, long long total_tokens, int D, int H,
+                       void* out, float* lse2, cudaStream_t st) {
+  const int dh = D / H;
+  if (max_len > kAtK || D % 64 != 0 || (dh != 32 && dh != 64) || total_tokens <= 0) return 1;
+  static PFN_encodeTiledA enc = nullptr;
+  if (enc == nullptr) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+      return 1;
+    enc = reinterpret_cast<PFN_encodeTiledA>(sym);
+  }
+  CUtensorMap tm;
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(3) * D, static_cast<cuuint64_t>(total_tokens)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(3) * D * 2};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(dh), kAtQ}, es[2] = {1, 1};
+  if (enc(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(qkv), dims, strides, box, es,
+          CU_TENSOR_MAP_INTERLEAVE_NONE, dh == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+          CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return 1;
+  AttnTcParams p;
+  p.cu = cu; p.n_seqs = n_seqs; p.D = D; p.H = H; p.items = n_seqs * H;
+  p.scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(dh));
+  p.out = reinterpret_cast<bf16*>(out); p.lse2 = lse2;
+  int grid = 4 * sm_count();
+  if (grid > p.items) grid = p.items;
+  cudaError_t e;
+  if (dh == 64) {
+    e = cudaFuncSetAttribute(attn_fwd_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnTcCfg<64>::SMEM);
+    if (e != cudaSuccess) { set_error("attn_fwd_tc attr: %s", cudaGetErrorString(e)); return WJ_ERR_RUNTIME; }
+    attn_fwd_tc_kernel<64><<<grid, 160, AttnTcCfg<64>::SMEM, st>>>(tm, p);
+  } else {
+    e = cudaFuncSetAttribute(attn_fwd_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnTcCfg<32>::SMEM);
+    if (e != cudaSuccess) { set_error("attn_fwd_tc attr: %s", cudaGetErrorString(e)); return WJ_ERR_RUNTIME; }
+    attn_fwd_tc_kernel<32><<<grid, 160, AttnTcCfg<32>::SMEM, st>>>(tm, p);
+  }
+  return check_launch("attn_fwd_tc");
+}
+
+}  // namespace wj

@@ -347,7 +347,7 @@ def attn_fwd(qkv: torch.Tensor, cu: torch.Tensor, n_seqs: int, max_len: int, D: 
     p = lambda t: C.c_void_p(_ptr(t))
     if _lib._profile is not None:
         _lib._profile.meta = (0.0, n_seqs, max_len, D, H, qkv.shape[0])
-    check(lib.wj_attn_varlen_fwd(p(qkv), p(cu), n_seqs, max_len, D, H, p(out), p(lse2), _stream()))
+    check(lib.wj_attn_varlen_fwd(p(qkv), p(cu), n_seqs, max_len, C.c_int64(qkv.shape[0]), D, H, p(out), p(lse2), _stream()))
 
 
 def attn_bwd(qkv, out, dout, lse2, cu, n_seqs: int, max_len: int, D: int, H: int, dqkv):
