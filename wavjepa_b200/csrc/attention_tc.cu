@@ -28,14 +28,18 @@ struct AttnTcParams {
   float* lse2;
 };
 
-template <int DH> struct AttnTcCfg {
+// KT = keys per item (128 or 256 = TMEM columns of S); sequences of 129..256 tokens run as two query tiles.
+template <int DH, int KT> struct AttnTcCfg {
   static constexpr int TILE = kAtQ * DH * 2;                 // bytes of one [128 x DH] bf16 tile
-  static constexpr int STAGES = DH == 32 ? 2 : 1;            // 48 KB either way
-  static constexpr int BAR_OFF = STAGES * 3 * TILE;
+  static constexpr int KTILES = KT / 128;
+  static constexpr int STAGE = (1 + 2 * KTILES) * TILE;      // Q | K | V
+  static constexpr int STAGES = DH == 32 ? 2 : 1;            // 48 KB (KT 128) / 80 KB (KT 256) either way
+  static constexpr int BAR_OFF = STAGES * STAGE;
   static constexpr int SMEM = BAR_OFF + 128 + 1024;          // + alignment slack
+  static constexpr int CTAS = 512 / KT;                      // per SM, by TMEM columns
   static constexpr uint32_t SWZ = DH == 64 ? 2u : 4u;        // UMMA layout type: 128B / 64B swizzle
   static constexpr uint32_t SBO = DH == 64 ? 1024u : 512u;   // 8 rows x row pitch
-  static constexpr uint32_t P_COL = 0, O_COL = 64;           // TMEM columns of P (bf16 pairs) and O inside the S block
+  static constexpr uint32_t P_COL = 0, O_COL = KT / 2;       // TMEM columns of P (bf16 pairs) and O inside the S block
 };
 
 __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
@@ -65,9 +69,10 @@ __device__ __forceinline__ void tmem_st_32x32_x16(uint32_t taddr, const uint32_t
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-template <int DH>
-__global__ void __launch_bounds__(160, 4) attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const AttnTcParams p) {
-  using Cfg = AttnTcCfg<DH>;
+template <int DH, int KT>
+__global__ void __launch_bounds__(160, 512 / KT) attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const AttnTcParams p) {
+  using Cfg = AttnTcCfg<DH, KT>;
+  constexpr int QT = Cfg::KTILES;                   // query tiles per (sequence, head); item = (seq * H + head) * QT + qt
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -91,7 +96,7 @@ __global__ void __launch_bounds__(160, 4) attn_fwd_tc_kernel(const __grid_consta
       fence_mbar_init();
     }
     __syncwarp();
-    tmem_alloc(tmem_slot, 128);
+    tmem_alloc(tmem_slot, KT);
   }
   tc_fence_before();
   __syncthreads();
@@ -104,21 +109,27 @@ __global__ void __launch_bounds__(160, 4) attn_fwd_tc_kernel(const __grid_consta
     if (lane == 0) {
       constexpr uint32_t idesc_o = umma_idesc_bf16(kAtQ, DH, false, true);
       auto issue_loads = [&](int item, int stage) {
-        const int s = item / p.H, head = item - s * p.H;
+        const int sh = item / QT, qt = item - sh * QT;
+        const int s = sh / p.H, head = sh - s * p.H;
         const int start = p.cu[s];
-        uint8_t* base = smem + stage * 3 * Cfg::TILE;
-        mbar_arrive_expect_tx(bar_load + stage, 3 * Cfg::TILE);
-        tma_load_2d(base, &tmQ, bar_load + stage, head * DH, start);
-        tma_load_2d(base + Cfg::TILE, &tmQ, bar_load + stage, p.D + head * DH, start);
-        tma_load_2d(base + 2 * Cfg::TILE, &tmQ, bar_load + stage, 2 * p.D + head * DH, start);
+        const int halves = (QT == 2 && p.cu[s + 1] - start > 128) ? 2 : 1;   // key tiles that hold valid keys
+        uint8_t* base = smem + stage * Cfg::STAGE;
+        mbar_arrive_expect_tx(bar_load + stage, (1 + 2 * halves) * Cfg::TILE);
+        tma_load_2d(base, &tmQ, bar_load + stage, head * DH, start + qt * 128);
+        for (int h = 0; h < halves; ++h) {
+          tma_load_2d(base + (1 + h) * Cfg::TILE, &tmQ, bar_load + stage, p.D + head * DH, start + h * 128);
+          tma_load_2d(base + (1 + QT + h) * Cfg::TILE, &tmQ, bar_load + stage, 2 * p.D + head * DH, start + h * 128);
+        }
       };
       uint32_t ph_load[2] = {0, 0}, ph_p = 0, ph_done = 0;
       int it = 0;
       if (STAGES == 2 && blockIdx.x < p.items) issue_loads(blockIdx.x, 0);
       for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
         const int stage = STAGES == 2 ? (it & 1) : 0;
-        const int s = item / p.H;
-        const int n = p.cu[s + 1] - p.cu[s];
+        const int sh = item / QT, qt = item - sh * QT;
+        const int s = sh / p.H;
+        int n = p.cu[s + 1] - p.cu[s];
+        if (qt * 128 >= n) n = 0;                   // no valid query row in this tile: minimal MMAs, nothing stored
         const int n16 = (n + 15) & ~15;
         const uint32_t idesc_s = umma_idesc_bf16(kAtQ, n16 > 0 ? n16 : 16, false, false);
         if (it > 0) {   // the previous item's O has been read: its MMAs are complete, TMEM and its smem stage are free
@@ -129,7 +140,7 @@ __global__ void __launch_bounds__(160, 4) attn_fwd_tc_kernel(const __grid_consta
         mbar_wait(bar_load + stage, ph_load[stage]);
         ph_load[stage] ^= 1;
         tc_fence_after();
-        const uint32_t sQ = smem_u32(smem + stage * 3 * Cfg::TILE), sK = sQ + Cfg::TILE, sV = sK + Cfg::TILE;
+        const uint32_t sQ = smem_u32(smem + stage * Cfg::STAGE), sK = sQ + Cfg::TILE, sV = sK + QT * Cfg::TILE;
 #pragma unroll
         for (int ks = 0; ks < DH / 16; ++ks)
           umma_bf16(tS, umma_smem_desc(sQ + ks * 32, 0, Cfg::SBO, Cfg::SWZ), umma_smem_desc(sK + ks * 32, 0, Cfg::SBO, Cfg::SWZ),
@@ -154,15 +165,18 @@ __global__ void __launch_bounds__(160, 4) attn_fwd_tc_kernel(const __grid_consta
     uint32_t ph_s = 0, ph_o = 0;
     int nstart = 0, nn = 0;
     if (blockIdx.x < p.items) {
-      const int s = blockIdx.x / p.H;
+      const int s = blockIdx.x / (QT * p.H);
       nstart = p.cu[s];
       nn = p.cu[s + 1] - nstart;
     }
     for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
-      const int head = item % p.H;
-      const int start = nstart, n = nn;
+      const int sh = item / QT, qt = item - sh * QT;
+      const int head = sh % p.H;
+      const int start = nstart + qt * 128;          // first token of this query tile
+      const int n = qt * 128 < nn ? nn : 0;         // keys (0: no valid query row in this tile)
+      const int nq = n - qt * 128;                  // valid query rows of the tile (<= 0: none)
       if (item + gridDim.x < p.items) {   // next item's bounds: the load latency hides behind this item
-        const int s = (item + gridDim.x) / p.H;
+        const int s = (item + gridDim.x) / (QT * p.H);
         nstart = p.cu[s];
         nn = p.cu[s + 1] - nstart;
       }
@@ -229,7 +243,7 @@ __global__ void __launch_bounds__(160, 4) attn_fwd_tc_kernel(const __grid_consta
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_done);
-      if (row < n) {
+      if (row < nq) {
 #pragma unroll
         for (int c = 0; c < DH / 32; ++c)
 #pragma unroll
@@ -249,7 +263,7 @@ __global__ void __launch_bounds__(160, 4) attn_fwd_tc_kernel(const __grid_consta
   __syncthreads();
   if (warp == 4) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 128);
+    tmem_dealloc(tmem_base, KT);
   }
 }
 
@@ -261,7 +275,7 @@ typedef CUresult (*PFN_encodeTiledA)(CUtensorMap*, CUtensorMapDataType, cuuint32
 int attn_fwd_tc_launch(const void* qkv, const int* cu, int n_seqs, int max_len, long long total_tokens, int D, int H,
                        void* out, float* lse2, cudaStream_t st) {
   const int dh = D / H;
-  if (max_len > kAtK || D % 64 != 0 || (dh != 32 && dh != 64) || total_tokens <= 0) return 1;
+  if (max_len > 256 || D % 64 != 0 || (dh != 32 && dh != 64) || total_tokens <= 0) return 1;
   static PFN_encodeTiledA enc = nullptr;
   if (enc == nullptr) {
     void* sym = nullptr;
@@ -280,22 +294,22 @@ int attn_fwd_tc_launch(const void* qkv, const int* cu, int n_seqs, int max_len, 
           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
     return 1;
   AttnTcParams p;
-  p.cu = cu; p.n_seqs = n_seqs; p.D = D; p.H = H; p.items = n_seqs * H;
+  const int qt = max_len > 128 ? 2 : 1;
+  p.cu = cu; p.n_seqs = n_seqs; p.D = D; p.H = H; p.items = n_seqs * H * qt;
   p.scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(dh));
   p.out = reinterpret_cast<bf16*>(out); p.lse2 = lse2;
-  int grid = 4 * sm_count();
-  if (grid > p.items) grid = p.items;
-  cudaError_t e;
-  if (dh == 64) {
-    e = cudaFuncSetAttribute(attn_fwd_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnTcCfg<64>::SMEM);
+  auto go = [&](auto kernel, int smem, int ctas) -> int {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) { set_error("attn_fwd_tc attr: %s", cudaGetErrorString(e)); return WJ_ERR_RUNTIME; }
-    attn_fwd_tc_kernel<64><<<grid, 160, AttnTcCfg<64>::SMEM, st>>>(tm, p);
-  } else {
-    e = cudaFuncSetAttribute(attn_fwd_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnTcCfg<32>::SMEM);
-    if (e != cudaSuccess) { set_error("attn_fwd_tc attr: %s", cudaGetErrorString(e)); return WJ_ERR_RUNTIME; }
-    attn_fwd_tc_kernel<32><<<grid, 160, AttnTcCfg<32>::SMEM, st>>>(tm, p);
-  }
-  return check_launch("attn_fwd_tc");
+    int grid = ctas * sm_count();
+    if (grid > p.items) grid = p.items;
+    kernel<<<grid, 160, smem, st>>>(tm, p);
+    return check_launch("attn_fwd_tc");
+  };
+  if (dh == 64 && qt == 1) return go(attn_fwd_tc_kernel<64, 128>, AttnTcCfg<64, 128>::SMEM, AttnTcCfg<64, 128>::CTAS);
+  if (dh == 64) return go(attn_fwd_tc_kernel<64, 256>, AttnTcCfg<64, 256>::SMEM, AttnTcCfg<64, 256>::CTAS);
+  if (qt == 1) return go(attn_fwd_tc_kernel<32, 128>, AttnTcCfg<32, 128>::SMEM, AttnTcCfg<32, 128>::CTAS);
+  return go(attn_fwd_tc_kernel<32, 256>, AttnTcCfg<32, 256>::SMEM, AttnTcCfg<32, 256>::CTAS);
 }
 
 }  // namespace wj
