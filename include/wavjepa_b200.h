@@ -193,7 +193,8 @@ int wj_target_accum(const float* x, const float* rowsum, int B, int T, int D, fl
 int wj_attn_varlen_fwd(const void* qkv_bf16, const int* cu_seqlens, int n_seqs, int max_len, int64_t total_tokens, int D,
                        int H, void* out_bf16, float* lse2, void* stream);
 int wj_attn_varlen_bwd(const void* qkv_bf16, const void* out_bf16, const void* dout_bf16, const float* lse2,
-                       const int* cu_seqlens, int n_seqs, int max_len, int D, int H, void* dqkv_bf16, void* stream);
+                       const int* cu_seqlens, int n_seqs, int max_len, int64_t total_tokens, int D, int H,
+                       void* dqkv_bf16, void* stream);
 
 /* Row gather: out[i, :] = src[idx[i], :] (idx NULL = identity, i.e. a cast); fp32 and/or bf16 outputs.
  * contextual_features[~ctx_masks] (wavjepa/jepa.py:399). */

@@ -391,12 +391,23 @@ extern "C" int wj_attn_varlen_fwd(const void* qkv_bf16, const int* cu_seqlens, i
   return check_launch("attn_varlen_fwd");
 }
 
+namespace wj {
+int attn_bwd_tc_launch(const void* qkv, const void* out, const void* dout, const float* lse2, const int* cu, int n_seqs,
+                       int max_len, long long total_tokens, int D, int H, void* dqkv, cudaStream_t st);
+}
+
 extern "C" int wj_attn_varlen_bwd(const void* qkv_bf16, const void* out_bf16, const void* dout_bf16, const float* lse2,
-                                  const int* cu_seqlens, int n_seqs, int max_len, int D, int H, void* dqkv_bf16,
-                                  void* stream) {
+                                  const int* cu_seqlens, int n_seqs, int max_len, int64_t total_tokens, int D, int H,
+                                  void* dqkv_bf16, void* stream) {
   if (n_seqs <= 0 || max_len <= 0) return WJ_OK;
   const int dh = D / H;
   if (D % H != 0 || (dh != 32 && dh != 64)) { set_error("wj_attn_varlen_bwd: head dim must be 32 or 64"); return WJ_ERR_ARG; }
+  {
+    // head dim 32, <= 128 tokens: tcgen05 kernel (attention_tc.cu); everything else: the mma.sync kernel below
+    const int rc = wj::attn_bwd_tc_launch(qkv_bf16, out_bf16, dout_bf16, lse2, cu_seqlens, n_seqs, max_len, total_tokens, D, H,
+                                          dqkv_bf16, WJ_STREAM(stream));
+    if (rc <= 0) return rc;
+  }
   const int npad = (max_len + 15) & ~15;
   const size_t smem = static_cast<size_t>(4) * npad * (dh + 8) * 2 + static_cast<size_t>(2) * ((npad + 63) & ~63) * 4;
   if (smem > 227 * 1024) { set_error("wj_attn_varlen_bwd: sequence of %d tokens (head dim %d) exceeds the shared-memory resident design", max_len, dh); return WJ_ERR_ARG; }

@@ -267,6 +267,265 @@ __global__ void __launch_bounds__(160, 512 / KT) attn_fwd_tc_kernel(const __grid
   }
 }
 
+// ------------------------------------------------------------------------------------------------------- backward
+// One work item = one (sequence, head) of <= 128 tokens, head dim 32 (the predictor; the student's dim-64 heads stay
+// on the mma.sync kernel).  All five products of the attention backward are UMMAs:
+//
+//   S  = Q K^T, dP = dO V^T        TMEM columns [0,128) and [128,256)
+//   gradient warps (8: two per TMEM lane quadrant, splitting the key chunks; one query row per thread):
+//        P = exp2(S*scale - lse), dS = P * (dP - delta), both bf16 -> smem [128 queries][128 keys], 128B swizzle
+//   dV = P^T dO, dK = dS^T Q       A = the smem tiles read MN-major (M = keys), B = dO / Q read MN-major
+//   dQ = dS K                      A = the dS tile read K-major, B = K read MN-major
+//        (TMEM columns [0,32), [32,64), [64,96) over the consumed S block)
+//   epilogue: rows < n of dQ*scale, dK*scale, dV -> dqkv[token, {0, D, 2D} + head*32 ...], transposed through the
+//        warp's own (consumed) corner of the P tile so that four lanes store one 64-byte row
+//   delta: the O tile rides along with the TMA loads; every gradient thread reduces its own row of O * dO out of
+//        smem while the S / dP products run.  lse is fetched one item ahead into a register.
+//
+// Query rows >= n are written as zeros into P / dS (they are K-dimension rows of the dV / dK products); key columns
+// >= n are masked to zero.  104 KB smem + 256 TMEM columns: two CTAs per SM.
+struct AttnBwdParams {
+  const int* cu;
+  int D, H, items;
+  float scale, scale_log2;
+  const bf16* out;
+  const bf16* dout;
+  const float* lse2;
+  bf16* dqkv;
+};
+
+constexpr int kBwdTile = kAtQ * 32 * 2;                  // 8 KB: [128 x 32] bf16, 64B swizzle
+constexpr int kBwdPs = 2 * kAtQ * 128;                   // 32 KB: [2 key blocks][128 queries][64 keys] bf16, 128B swizzle
+constexpr int kBwdBarOff = 5 * kBwdTile + 2 * kBwdPs;    // Q | K | V | dO | O | P | dS | barriers
+constexpr int kBwdSmem = kBwdBarOff + 128 + 1024;
+
+__global__ void __launch_bounds__(288, 2) attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
+                                                             const __grid_constant__ CUtensorMap tmDO,
+                                                             const __grid_constant__ CUtensorMap tmO, const AttnBwdParams p) {
+  constexpr int DH = 32;
+  constexpr uint32_t SWZ = 4u, SBO = 512u;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sP = smem + 5 * kBwdTile;
+  uint8_t* sDS = sP + kBwdPs;
+  uint64_t* bar_load = reinterpret_cast<uint64_t*>(smem + kBwdBarOff);
+  uint64_t* bar_s = bar_load + 1;      // S and dP complete
+  uint64_t* bar_p = bar_load + 2;      // P / dS written (8 warps)
+  uint64_t* bar_g = bar_load + 3;      // dV, dK, dQ complete
+  uint64_t* bar_done = bar_load + 4;   // gradients read out of TMEM (8 warps)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_load + 5);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 8) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tmQ);
+      tma_prefetch_desc(&tmDO);
+      tma_prefetch_desc(&tmO);
+      mbar_init(bar_load, 1);
+      mbar_init(bar_s, 1);
+      mbar_init(bar_p, 8);
+      mbar_init(bar_g, 1);
+      mbar_init(bar_done, 8);
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, 256);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tS = tmem_base, tDP = tmem_base + 128, tDV = tmem_base, tDK = tmem_base + 32, tDQ = tmem_base + 64;
+
+  if (warp == 8) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_g = umma_idesc_bf16(kAtQ, DH, true, true);    // dV, dK: A and B MN-major
+      constexpr uint32_t idesc_q = umma_idesc_bf16(kAtQ, DH, false, true);   // dQ: A K-major, B MN-major
+      const uint32_t sQ = smem_u32(smem), sK = sQ + kBwdTile, sV = sK + kBwdTile, sDO = sV + kBwdTile;
+      uint32_t ph_load = 0, ph_p = 0, ph_g = 0, ph_done = 0;
+      int it = 0;
+      for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
+        const int s = item / p.H, head = item - s * p.H;
+        const int start = p.cu[s], n = p.cu[s + 1] - start;
+        const int n16 = n > 0 ? (n + 15) & ~15 : 16;
+        const uint32_t idesc_s = umma_idesc_bf16(kAtQ, n16, false, false);
+        if (it > 0) {   // the previous item's last MMAs are complete: every smem tile may be overwritten
+          mbar_wait(bar_g, ph_g);
+          ph_g ^= 1;
+        }
+        mbar_arrive_expect_tx(bar_load, 5 * kBwdTile);
+        tma_load_2d(smem, &tmQ, bar_load, head * DH, start);
+        tma_load_2d(smem + kBwdTile, &tmQ, bar_load, p.D + head * DH, start);
+        tma_load_2d(smem + 2 * kBwdTile, &tmQ, bar_load, 2 * p.D + head * DH, start);
+        tma_load_2d(smem + 3 * kBwdTile, &tmDO, bar_load, head * DH, start);
+        tma_load_2d(smem + 4 * kBwdTile, &tmO, bar_load, head * DH, start);
+        mbar_wait(bar_load, ph_load);
+        ph_load ^= 1;
+        if (it > 0) {   // the previous item's gradients have been read out of TMEM
+          mbar_wait(bar_done, ph_done);
+          ph_done ^= 1;
+        }
+        tc_fence_after();
+#pragma unroll
+        for (int ks = 0; ks < DH / 16; ++ks)
+          umma_bf16(tS, umma_smem_desc(sQ + ks * 32, 0, SBO, SWZ), umma_smem_desc(sK + ks * 32, 0, SBO, SWZ), idesc_s, ks > 0 ? 1u : 0u);
+#pragma unroll
+        for (int ks = 0; ks < DH / 16; ++ks)
+          umma_bf16(tDP, umma_smem_desc(sDO + ks * 32, 0, SBO, SWZ), umma_smem_desc(sV + ks * 32, 0, SBO, SWZ), idesc_s, ks > 0 ? 1u : 0u);
+        umma_commit(bar_s);
+        mbar_wait(bar_p, ph_p);
+        ph_p ^= 1;
+        tc_fence_after();
+        const int steps = n16 / 16;
+        const uint64_t dP_mn = umma_smem_desc(smem_u32(sP), kAtQ * 128, 1024, 2u);     // A = P^T  (M = keys, K = queries)
+        const uint64_t dS_mn = umma_smem_desc(smem_u32(sDS), kAtQ * 128, 1024, 2u);    // A = dS^T
+        const uint64_t bDO = umma_smem_desc(sDO, kBwdTile, SBO, SWZ), bQ = umma_smem_desc(sQ, kBwdTile, SBO, SWZ),
+                       bK = umma_smem_desc(sK, kBwdTile, SBO, SWZ);
+        for (int kk = 0; kk < steps; ++kk)    // 16 queries per step: 16 rows of the P tile (2 KB) and of dO (1 KB)
+          umma_bf16(tDV, dP_mn + static_cast<uint64_t>((kk * 2048) >> 4), bDO + static_cast<uint64_t>((kk * 1024) >> 4), idesc_g, kk > 0 ? 1u : 0u);
+        for (int kk = 0; kk < steps; ++kk)
+          umma_bf16(tDK, dS_mn + static_cast<uint64_t>((kk * 2048) >> 4), bQ + static_cast<uint64_t>((kk * 1024) >> 4), idesc_g, kk > 0 ? 1u : 0u);
+        for (int kk = 0; kk < steps; ++kk) {  // 16 keys per step
+          const uint32_t a = smem_u32(sDS) + (kk >> 2) * (kAtQ * 128) + (kk & 3) * 32;
+          umma_bf16(tDQ, umma_smem_desc(a, 0, 1024, 2u), bK + static_cast<uint64_t>((kk * 1024) >> 4), idesc_q, kk > 0 ? 1u : 0u);
+        }
+        umma_commit(bar_g);
+      }
+    }
+  } else {
+    // ================================================================================ gradient warps
+    const int quad = warp & 3, half = warp >> 2;
+    const int row = quad * 32 + lane;
+    const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
+    // this warp's private 4 KB of the P tile (its 32 query rows x its 64 keys): staging for the coalesced stores
+    uint8_t* stage = sP + half * (kAtQ * 128) + quad * 32 * 128;
+    uint32_t ph_s = 0, ph_g = 0, ph_l = 0;
+    int nstart = 0, nn = 0;
+    float nlse = 0.f;
+    if (blockIdx.x < p.items) {
+      const int s = blockIdx.x / p.H;
+      nstart = p.cu[s];
+      nn = p.cu[s + 1] - nstart;
+      if (row < nn) nlse = p.lse2[static_cast<long long>(nstart + row) * p.H + blockIdx.x % p.H];
+    }
+    const uint8_t* sOrow = smem + 4 * kBwdTile + row * 64;
+    const uint8_t* sDOrow = smem + 3 * kBwdTile + row * 64;
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+      const int head = item % p.H;
+      const int start = nstart, n = nn;
+      const float lse = nlse;
+      if (item + gridDim.x < p.items) {   // next item's bounds and this row's lse: the latency hides behind this item
+        const int nitem = item + gridDim.x, s = nitem / p.H;
+        nstart = p.cu[s];
+        nn = p.cu[s + 1] - nstart;
+        nlse = row < nn ? p.lse2[static_cast<long long>(nstart + row) * p.H + (nitem - s * p.H)] : 0.f;
+      }
+      const bool live = row < n;
+      // delta = sum(O * dO) of this thread's row out of the TMA tiles (64B swizzle), while the S / dP products run
+      mbar_wait(bar_load, ph_l);
+      ph_l ^= 1;
+      float delta = 0.f;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int o = (c ^ ((row >> 1) & 3)) << 4;
+        const uint4 a = *reinterpret_cast<const uint4*>(sOrow + o);
+        const uint4 b = *reinterpret_cast<const uint4*>(sDOrow + o);
+        const __nv_bfloat162* a2 = reinterpret_cast<const __nv_bfloat162*>(&a);
+        const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&b);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const float2 x = __bfloat1622float2(a2[t]), y = __bfloat1622float2(b2[t]);
+          delta += x.x * y.x + x.y * y.y;
+        }
+      }
+      mbar_wait(bar_s, ph_s);
+      ph_s ^= 1;
+      tc_fence_after();
+#pragma unroll 1
+      for (int c0 = half * 64; c0 < half * 64 + 64 && c0 < n; c0 += 32) {
+        uint32_t sv[32], dv[32];
+        tmem_ld_32x32(tS + lane_addr + c0, sv);
+        tmem_ld_32x32(tDP + lane_addr + c0, dv);
+        tmem_ld_wait();
+        const int off = (c0 >> 6) * (kAtQ * 128) + row * 128;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint32_t wp[4], wd[4];
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const int j = q * 8 + 2 * t;
+            // selects, not multiplies: TMEM columns >= n16 and rows >= n hold stale bits
+            const bool k0 = live && c0 + j < n, k1 = live && c0 + j + 1 < n;
+            const float p0 = k0 ? ex2_approx(fmaf(__uint_as_float(sv[j]), p.scale_log2, -lse)) : 0.f;
+            const float p1 = k1 ? ex2_approx(fmaf(__uint_as_float(sv[j + 1]), p.scale_log2, -lse)) : 0.f;
+            wp[t] = pack_bf16x2(p0, p1);
+            wd[t] = pack_bf16x2(k0 ? p0 * (__uint_as_float(dv[j]) - delta) : 0.f, k1 ? p1 * (__uint_as_float(dv[j + 1]) - delta) : 0.f);
+          }
+          const int chunk = ((c0 & 63) >> 3) + q;
+          const int o = off + ((chunk ^ (row & 7)) << 4);
+          *reinterpret_cast<uint4*>(sP + o) = make_uint4(wp[0], wp[1], wp[2], wp[3]);
+          *reinterpret_cast<uint4*>(sDS + o) = make_uint4(wd[0], wd[1], wd[2], wd[3]);
+        }
+      }
+      tc_fence_before();
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_p);
+      mbar_wait(bar_g, ph_g);
+      ph_g ^= 1;
+      tc_fence_after();
+      // warps 0-3: dQ and dV rows; warps 4-7: dK rows.  TMEM -> registers -> bf16 rows in this warp's staging corner
+      // (16-byte pieces XOR-swizzled by the row pair) -> four lanes per 64-byte row to global memory
+      const int ntile = half == 0 ? 2 : 1;
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        if (t < ntile) {
+          uint32_t g[32];
+          tmem_ld_32x32((half == 0 ? (t == 0 ? tDQ : tDV) : tDK) + lane_addr, g);
+          tmem_ld_wait();
+          const float sc = (half == 0 && t == 1) ? 1.0f : p.scale;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            uint4 w;
+            w.x = pack_bf16x2(__uint_as_float(g[8 * q]) * sc, __uint_as_float(g[8 * q + 1]) * sc);
+            w.y = pack_bf16x2(__uint_as_float(g[8 * q + 2]) * sc, __uint_as_float(g[8 * q + 3]) * sc);
+            w.z = pack_bf16x2(__uint_as_float(g[8 * q + 4]) * sc, __uint_as_float(g[8 * q + 5]) * sc);
+            w.w = pack_bf16x2(__uint_as_float(g[8 * q + 6]) * sc, __uint_as_float(g[8 * q + 7]) * sc);
+            *reinterpret_cast<uint4*>(stage + t * 2048 + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4)) = w;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_done);
+      {
+        const int rsub = lane >> 2, piece = lane & 3;
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          if (t < ntile) {
+            const int col = half == 0 ? (t == 0 ? 0 : 2 * p.D) : p.D;
+#pragma unroll
+            for (int r0 = 0; r0 < 32; r0 += 8) {
+              const int lr = r0 + rsub, r = quad * 32 + lr;
+              if (r < n) {
+                const uint4 w = *reinterpret_cast<const uint4*>(stage + t * 2048 + lr * 64 + ((piece ^ ((lr >> 1) & 3)) << 4));
+                *reinterpret_cast<uint4*>(p.dqkv + static_cast<long long>(start + r) * (3LL * p.D) + col + head * DH + piece * 8) = w;
+              }
+            }
+          }
+        }
+      }
+      __syncwarp();   // the staging corner is rewritten by this warp's next P / dS chunk
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
 typedef CUresult (*PFN_encodeTiledA)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                      const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                      CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -310,6 +569,54 @@ int attn_fwd_tc_launch(const void* qkv, const int* cu, int n_seqs, int max_len, 
   if (dh == 64) return go(attn_fwd_tc_kernel<64, 256>, AttnTcCfg<64, 256>::SMEM, AttnTcCfg<64, 256>::CTAS);
   if (qt == 1) return go(attn_fwd_tc_kernel<32, 128>, AttnTcCfg<32, 128>::SMEM, AttnTcCfg<32, 128>::CTAS);
   return go(attn_fwd_tc_kernel<32, 256>, AttnTcCfg<32, 256>::SMEM, AttnTcCfg<32, 256>::CTAS);
+}
+
+
+// Returns WJ_OK and launches when the problem fits (head dim 32, <= 128 tokens); 1 -> caller uses the mma.sync kernel.
+int attn_bwd_tc_launch(const void* qkv, const void* out, const void* dout, const float* lse2, const int* cu, int n_seqs,
+                       int max_len, long long total_tokens, int D, int H, void* dqkv, cudaStream_t st) {
+  const int dh = D / H;
+  if (max_len > 128 || dh != 32 || D % 8 != 0 || total_tokens <= 0) return 1;
+  static PFN_encodeTiledA enc = nullptr;
+  if (enc == nullptr) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+      return 1;
+    enc = reinterpret_cast<PFN_encodeTiledA>(sym);
+  }
+  CUtensorMap tq, tdo, to;
+  cuuint32_t box[2] = {32, kAtQ}, es[2] = {1, 1};
+  {
+    cuuint64_t dims[2] = {static_cast<cuuint64_t>(3) * D, static_cast<cuuint64_t>(total_tokens)};
+    cuuint64_t strides[1] = {static_cast<cuuint64_t>(3) * D * 2};
+    if (enc(&tq, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(qkv), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return 1;
+  }
+  {
+    cuuint64_t dims[2] = {static_cast<cuuint64_t>(D), static_cast<cuuint64_t>(total_tokens)};
+    cuuint64_t strides[1] = {static_cast<cuuint64_t>(D) * 2};
+    if (enc(&tdo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(dout), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return 1;
+    if (enc(&to, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(out), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return 1;
+  }
+  AttnBwdParams p;
+  p.cu = cu; p.D = D; p.H = H; p.items = n_seqs * H;
+  p.scale = 1.0f / sqrtf(static_cast<float>(dh));
+  p.scale_log2 = p.scale * 1.4426950408889634f;
+  p.out = reinterpret_cast<const bf16*>(out); p.dout = reinterpret_cast<const bf16*>(dout); p.lse2 = lse2;
+  p.dqkv = reinterpret_cast<bf16*>(dqkv);
+  cudaError_t e = cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem);
+  if (e != cudaSuccess) { set_error("attn_bwd_tc attr: %s", cudaGetErrorString(e)); return WJ_ERR_RUNTIME; }
+  int grid = 2 * sm_count();
+  if (grid > p.items) grid = p.items;
+  attn_bwd_tc_kernel<<<grid, 288, kBwdSmem, st>>>(tq, tdo, to, p);
+  return check_launch("attn_bwd_tc");
 }
 
 }  // namespace wj

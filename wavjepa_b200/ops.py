@@ -355,7 +355,8 @@ def attn_bwd(qkv, out, dout, lse2, cu, n_seqs: int, max_len: int, D: int, H: int
     p = lambda t: C.c_void_p(_ptr(t))
     if _lib._profile is not None:
         _lib._profile.meta = (0.0, n_seqs, max_len, D, H, qkv.shape[0])
-    check(lib.wj_attn_varlen_bwd(p(qkv), p(out), p(dout), p(lse2), p(cu), n_seqs, max_len, D, H, p(dqkv), _stream()))
+    check(lib.wj_attn_varlen_bwd(p(qkv), p(out), p(dout), p(lse2), p(cu), n_seqs, max_len, C.c_int64(qkv.shape[0]), D, H,
+                                 p(dqkv), _stream()))
 
 
 # ----------------------------------------------------------------------------------------------------- misc
