@@ -28,18 +28,23 @@ struct AttnTcParams {
   float* lse2;
 };
 
-// KT = keys per item (128 or 256 = TMEM columns of S); sequences of 129..256 tokens run as two query tiles.
+// KT = keys per item (128 or 256 = TMEM columns of S); sequences of 129..256 tokens run as two query tiles.  With
+// KT = 256 the keys are split into two 128-key halves, each with its own 4 softmax warps (own max / sum, own P and O
+// blocks in TMEM); the epilogue merges the two partial results (flash-decoding style) from (max, sum) pairs in smem.
 template <int DH, int KT> struct AttnTcCfg {
   static constexpr int TILE = kAtQ * DH * 2;                 // bytes of one [128 x DH] bf16 tile
-  static constexpr int KTILES = KT / 128;
-  static constexpr int STAGE = (1 + 2 * KTILES) * TILE;      // Q | K | V
-  static constexpr int STAGES = DH == 32 ? 2 : 1;            // 48 KB (KT 128) / 80 KB (KT 256) either way
+  static constexpr int HALVES = KT / 128;
+  static constexpr int NW = 4 * HALVES;                      // softmax warps; warp NW = control
+  static constexpr int THREADS = (NW + 1) * 32;
+  static constexpr int STAGE = 3 * HALVES * TILE;            // Q tile(s) | K | V of one (sequence, head)
+  static constexpr int STAGES = DH == 32 ? 2 : 1;            // 48 KB (KT 128) / 96 KB (KT 256) either way
   static constexpr int BAR_OFF = STAGES * STAGE;
-  static constexpr int SMEM = BAR_OFF + 128 + 1024;          // + alignment slack
+  static constexpr int ML_OFF = BAR_OFF + 128;               // (max, sum) [2 item parities][2 halves][128 rows] float2
+  static constexpr int SMEM = ML_OFF + (HALVES == 2 ? 4096 : 0) + 1024;   // + alignment slack
   static constexpr int CTAS = 512 / KT;                      // per SM, by TMEM columns
   static constexpr uint32_t SWZ = DH == 64 ? 2u : 4u;        // UMMA layout type: 128B / 64B swizzle
   static constexpr uint32_t SBO = DH == 64 ? 1024u : 512u;   // 8 rows x row pitch
-  static constexpr uint32_t P_COL = 0, O_COL = KT / 2;       // TMEM columns of P (bf16 pairs) and O inside the S block
+  static constexpr uint32_t O_COL = 64;                      // inside a half's 128-column block: P at [0,64), O at [64,64+DH)
 };
 
 __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
@@ -68,31 +73,50 @@ __device__ __forceinline__ void tmem_st_32x32_x16(uint32_t taddr, const uint32_t
                : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+// EC (16 / 32 / 64) consecutive fp32 columns of this thread's TMEM lane
+template <int EC> __device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t* v) {
+  if constexpr (EC == 16) {
+    tmem_ld_32x16(taddr, v);
+  } else {
+#pragma unroll
+    for (int c = 0; c < EC / 32; ++c) tmem_ld_32x32(taddr + c * 32, *reinterpret_cast<uint32_t(*)[32]>(v + c * 32));
+  }
+}
 
 template <int DH, int KT>
-__global__ void __launch_bounds__(160, 512 / KT) attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const AttnTcParams p) {
+__global__ void __launch_bounds__(AttnTcCfg<DH, KT>::THREADS, 512 / KT)
+attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const AttnTcParams p) {
   using Cfg = AttnTcCfg<DH, KT>;
-  constexpr int QT = Cfg::KTILES;                   // query tiles per (sequence, head); item = (seq * H + head) * QT + qt
-  constexpr int STAGES = Cfg::STAGES;
+  constexpr int STAGES = Cfg::STAGES, HALVES = Cfg::HALVES, NW = Cfg::NW;
+  constexpr int QT = HALVES;                        // query tiles per unit = (sequence, head); K / V are loaded once per unit
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bar_load = reinterpret_cast<uint64_t*>(smem + Cfg::BAR_OFF);   // [STAGES]
   uint64_t* bar_s = bar_load + 2;                 // S accumulator complete (MMA commit)
-  uint64_t* bar_p = bar_load + 3;                 // P written by the 4 softmax warps (S fully read)
-  uint64_t* bar_o = bar_load + 4;                 // O accumulator complete (MMA commit)
-  uint64_t* bar_done = bar_load + 5;              // O read by the 4 epilogue warps: TMEM (and this stage's smem) reusable
+  uint64_t* bar_p = bar_load + 3;                 // P written by the softmax warps (S fully read)
+  uint64_t* bar_o = bar_load + 4;                 // O accumulator(s) complete (MMA commit)
+  uint64_t* bar_done = bar_load + 5;              // O read by the epilogue warps: TMEM (and this stage's smem) reusable
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_load + 6);
+  float2* sML = reinterpret_cast<float2*>(smem + Cfg::ML_OFF);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  if (warp == 4) {
+  if (warp == NW) {
     if (lane == 0) {
       tma_prefetch_desc(&tmQ);
       mbar_init(bar_load, 1);
       mbar_init(bar_load + 1, 1);
       mbar_init(bar_s, 1);
-      mbar_init(bar_p, 4);
+      mbar_init(bar_p, NW);
       mbar_init(bar_o, 1);
-      mbar_init(bar_done, 4);
+      mbar_init(bar_done, NW);
       fence_mbar_init();
     }
     __syncwarp();
@@ -102,112 +126,126 @@ __global__ void __launch_bounds__(160, 512 / KT) attn_fwd_tc_kernel(const __grid
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tS = tmem_base, tP = tmem_base + Cfg::P_COL, tO = tmem_base + Cfg::O_COL;
 
-  if (warp == 4) {
+  if (warp == NW) {
     // ================================================================================ control: TMA + MMA issue
     if (lane == 0) {
       constexpr uint32_t idesc_o = umma_idesc_bf16(kAtQ, DH, false, true);
-      auto issue_loads = [&](int item, int stage) {
-        const int sh = item / QT, qt = item - sh * QT;
-        const int s = sh / p.H, head = sh - s * p.H;
+      auto issue_loads = [&](int unit, int stage) {
+        const int s = unit / p.H, head = unit - s * p.H;
         const int start = p.cu[s];
-        const int halves = (QT == 2 && p.cu[s + 1] - start > 128) ? 2 : 1;   // key tiles that hold valid keys
+        const int halves = (QT == 2 && p.cu[s + 1] - start > 128) ? 2 : 1;   // 128-token tiles that hold valid tokens
         uint8_t* base = smem + stage * Cfg::STAGE;
-        mbar_arrive_expect_tx(bar_load + stage, (1 + 2 * halves) * Cfg::TILE);
-        tma_load_2d(base, &tmQ, bar_load + stage, head * DH, start + qt * 128);
+        mbar_arrive_expect_tx(bar_load + stage, 3 * halves * Cfg::TILE);
         for (int h = 0; h < halves; ++h) {
-          tma_load_2d(base + (1 + h) * Cfg::TILE, &tmQ, bar_load + stage, p.D + head * DH, start + h * 128);
-          tma_load_2d(base + (1 + QT + h) * Cfg::TILE, &tmQ, bar_load + stage, 2 * p.D + head * DH, start + h * 128);
+          tma_load_2d(base + h * Cfg::TILE, &tmQ, bar_load + stage, head * DH, start + h * 128);
+          tma_load_2d(base + (QT + h) * Cfg::TILE, &tmQ, bar_load + stage, p.D + head * DH, start + h * 128);
+          tma_load_2d(base + (2 * QT + h) * Cfg::TILE, &tmQ, bar_load + stage, 2 * p.D + head * DH, start + h * 128);
         }
       };
       uint32_t ph_load[2] = {0, 0}, ph_p = 0, ph_done = 0;
-      int it = 0;
+      int iu = 0, it = 0;
       if (STAGES == 2 && blockIdx.x < p.items) issue_loads(blockIdx.x, 0);
-      for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
-        const int stage = STAGES == 2 ? (it & 1) : 0;
-        const int sh = item / QT, qt = item - sh * QT;
-        const int s = sh / p.H;
-        int n = p.cu[s + 1] - p.cu[s];
-        if (qt * 128 >= n) n = 0;                   // no valid query row in this tile: minimal MMAs, nothing stored
+      for (int unit = blockIdx.x; unit < p.items; unit += gridDim.x, ++iu) {
+        const int stage = STAGES == 2 ? (iu & 1) : 0;
+        const int s = unit / p.H;
+        const int n = p.cu[s + 1] - p.cu[s];
         const int n16 = (n + 15) & ~15;
         const uint32_t idesc_s = umma_idesc_bf16(kAtQ, n16 > 0 ? n16 : 16, false, false);
-        if (it > 0) {   // the previous item's O has been read: its MMAs are complete, TMEM and its smem stage are free
-          mbar_wait(bar_done, ph_done);
-          ph_done ^= 1;
-        }
-        if (STAGES == 1) issue_loads(item, 0);
-        mbar_wait(bar_load + stage, ph_load[stage]);
-        ph_load[stage] ^= 1;
-        tc_fence_after();
-        const uint32_t sQ = smem_u32(smem + stage * Cfg::STAGE), sK = sQ + Cfg::TILE, sV = sK + QT * Cfg::TILE;
-#pragma unroll
-        for (int ks = 0; ks < DH / 16; ++ks)
-          umma_bf16(tS, umma_smem_desc(sQ + ks * 32, 0, Cfg::SBO, Cfg::SWZ), umma_smem_desc(sK + ks * 32, 0, Cfg::SBO, Cfg::SWZ),
-                    idesc_s, ks > 0 ? 1u : 0u);
-        umma_commit(bar_s);
-        if (STAGES == 2 && item + gridDim.x < p.items) issue_loads(item + gridDim.x, stage ^ 1);   // lands during the softmax
-        mbar_wait(bar_p, ph_p);
-        ph_p ^= 1;
-        tc_fence_after();
-        // O = P V over the 16-key steps that hold valid keys (at least one, so that bar_o always completes)
+        const uint32_t sQ = smem_u32(smem + stage * Cfg::STAGE), sK = sQ + QT * Cfg::TILE, sV = sK + QT * Cfg::TILE;
         const uint64_t vdesc = umma_smem_desc(sV, Cfg::TILE, Cfg::SBO, Cfg::SWZ);
-        const int steps = n16 > 0 ? n16 / 16 : 1;
-        for (int kk = 0; kk < steps; ++kk)
-          umma_bf16_ts(tO, tP + kk * 8, vdesc + static_cast<uint64_t>((kk * 16 * DH * 2) >> 4), idesc_o, kk > 0 ? 1u : 0u);
-        umma_commit(bar_o);
+#pragma unroll 1
+        for (int qt = 0; qt < QT; ++qt) {
+          if (qt > 0 && qt * 128 >= n) break;     // no valid query row in this tile (every warp skips it alike)
+          if (it > 0) {   // the previous tile's O has been read: its MMAs are complete, TMEM (and its smem stage) are free
+            mbar_wait(bar_done, ph_done);
+            ph_done ^= 1;
+          }
+          if (qt == 0) {
+            if (STAGES == 1) issue_loads(unit, 0);
+            mbar_wait(bar_load + stage, ph_load[stage]);
+            ph_load[stage] ^= 1;
+          }
+          tc_fence_after();
+#pragma unroll
+          for (int ks = 0; ks < DH / 16; ++ks)
+            umma_bf16(tmem_base, umma_smem_desc(sQ + qt * Cfg::TILE + ks * 32, 0, Cfg::SBO, Cfg::SWZ),
+                      umma_smem_desc(sK + ks * 32, 0, Cfg::SBO, Cfg::SWZ), idesc_s, ks > 0 ? 1u : 0u);
+          umma_commit(bar_s);
+          if (STAGES == 2 && qt == 0 && unit + gridDim.x < p.items) issue_loads(unit + gridDim.x, stage ^ 1);   // lands during the softmax
+          mbar_wait(bar_p, ph_p);
+          ph_p ^= 1;
+          tc_fence_after();
+          // O_h = P_h V_h per 128-key half, over the 16-key steps that hold valid keys (at least one step of half 0,
+          // so that bar_o always completes)
+#pragma unroll
+          for (int h = 0; h < HALVES; ++h) {
+            int steps = (min(n16, 128 * (h + 1)) - 128 * h) / 16;
+            if (h == 0 && steps < 1) steps = 1;
+            const uint32_t tPh = tmem_base + h * 128, tOh = tPh + Cfg::O_COL;
+            for (int kk = 0; kk < steps; ++kk)
+              umma_bf16_ts(tOh, tPh + kk * 8, vdesc + static_cast<uint64_t>(((h * 128 + kk * 16) * DH * 2) >> 4), idesc_o, kk > 0 ? 1u : 0u);
+          }
+          umma_commit(bar_o);
+          ++it;
+        }
       }
     }
   } else {
-    // ================================================================================ softmax + epilogue (4 warps)
-    const int row = warp * 32 + lane;                       // query row of the tile = TMEM lane
-    const uint32_t lane_addr = static_cast<uint32_t>(warp * 32) << 16;
+    // ================================================================================ softmax + epilogue warps
+    const int quad = warp & 3, half = warp >> 2;
+    const int row = quad * 32 + lane;                       // query row of the tile = TMEM lane
+    const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
+    const uint32_t tSh = tmem_base + half * 128 + lane_addr;   // this half's S block (P over its first 64 columns)
     uint32_t ph_s = 0, ph_o = 0;
-    int nstart = 0, nn = 0;
+    int nstart = 0, nn = 0, it = 0;
     if (blockIdx.x < p.items) {
-      const int s = blockIdx.x / (QT * p.H);
+      const int s = blockIdx.x / p.H;
       nstart = p.cu[s];
       nn = p.cu[s + 1] - nstart;
     }
-    for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
-      const int sh = item / QT, qt = item - sh * QT;
-      const int head = sh % p.H;
-      const int start = nstart + qt * 128;          // first token of this query tile
-      const int n = qt * 128 < nn ? nn : 0;         // keys (0: no valid query row in this tile)
-      const int nq = n - qt * 128;                  // valid query rows of the tile (<= 0: none)
-      if (item + gridDim.x < p.items) {   // next item's bounds: the load latency hides behind this item
-        const int s = (item + gridDim.x) / (QT * p.H);
+    for (int unit = blockIdx.x; unit < p.items; unit += gridDim.x) {
+      const int head = unit % p.H;
+      const int ustart = nstart, n = nn;            // tokens (= keys) of this sequence
+      if (unit + gridDim.x < p.items) {   // next unit's bounds: the load latency hides behind this unit
+        const int s = (unit + gridDim.x) / p.H;
         nstart = p.cu[s];
         nn = p.cu[s + 1] - nstart;
       }
+      const int nk = min(n - half * 128, 128);      // keys of this warp's half (<= 0: none)
+#pragma unroll 1
+      for (int qt = 0; qt < QT; ++qt, ++it) {
+      if (qt > 0 && qt * 128 >= n) break;           // (same rule as the control warp)
+      const int start = ustart + qt * 128;          // first token of this query tile
+      const int nq = n - qt * 128;                  // valid query rows of the tile (<= 0: none)
       mbar_wait(bar_s, ph_s);
       ph_s ^= 1;
       tc_fence_after();
       // pass 1: row maximum over the valid keys
       float m = -INFINITY;
 #pragma unroll 1
-      for (int c0 = 0; c0 < n; c0 += 32) {
+      for (int c0 = 0; c0 < nk; c0 += 32) {
         uint32_t v[32];
-        tmem_ld_32x32(tS + lane_addr + c0, v);
+        tmem_ld_32x32(tSh + c0, v);
         tmem_ld_wait();
-        if (c0 + 32 <= n) {
+        if (c0 + 32 <= nk) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) m = fmaxf(m, __uint_as_float(v[j]));
         } else {
 #pragma unroll
           for (int j = 0; j < 32; ++j)
-            if (c0 + j < n) m = fmaxf(m, __uint_as_float(v[j]));
+            if (c0 + j < nk) m = fmaxf(m, __uint_as_float(v[j]));
         }
       }
       const float ms = m * p.scale_log2;
-      // pass 2: p = exp2(s * scale - m * scale), row sum; P (bf16 pairs) -> TMEM columns [16 c, 16 c + 16)
+      // pass 2: p = exp2(s * scale - m * scale), row sum; P (bf16 pairs) -> TMEM columns [16 c, 16 c + 16) of the block
       float l = 0.f;
 #pragma unroll 1
-      for (int c0 = 0; c0 < n; c0 += 32) {
+      for (int c0 = 0; c0 < nk; c0 += 32) {
         uint32_t v[32], w[16];
-        tmem_ld_32x32(tS + lane_addr + c0, v);
+        tmem_ld_32x32(tSh + c0, v);
         tmem_ld_wait();
-        if (c0 + 32 <= n) {
+        if (c0 + 32 <= nk) {
 #pragma unroll
           for (int j = 0; j < 32; j += 2) {
             const float p0 = ex2_approx(fmaf(__uint_as_float(v[j]), p.scale_log2, -ms));
@@ -218,50 +256,71 @@ __global__ void __launch_bounds__(160, 512 / KT) attn_fwd_tc_kernel(const __grid
         } else {
 #pragma unroll
           for (int j = 0; j < 32; j += 2) {
-            const float p0 = c0 + j < n ? ex2_approx(fmaf(__uint_as_float(v[j]), p.scale_log2, -ms)) : 0.f;
-            const float p1 = c0 + j + 1 < n ? ex2_approx(fmaf(__uint_as_float(v[j + 1]), p.scale_log2, -ms)) : 0.f;
+            const float p0 = c0 + j < nk ? ex2_approx(fmaf(__uint_as_float(v[j]), p.scale_log2, -ms)) : 0.f;
+            const float p1 = c0 + j + 1 < nk ? ex2_approx(fmaf(__uint_as_float(v[j + 1]), p.scale_log2, -ms)) : 0.f;
             l += p0 + p1;
             w[j >> 1] = pack_bf16x2(p0, p1);
           }
         }
-        tmem_st_32x32_x16(tP + lane_addr + (c0 >> 1), w);
+        tmem_st_32x32_x16(tSh + (c0 >> 1), w);
       }
+      if constexpr (HALVES == 2) sML[((it & 1) * 2 + half) * kAtQ + row] = make_float2(ms, l);
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_p);
-      // epilogue: O row / l
+      // epilogue: this warp's EC output columns of its rows
       mbar_wait(bar_o, ph_o);
       ph_o ^= 1;
       tc_fence_after();
-      const float inv = 1.0f / l;
-      bf16* op = p.out + static_cast<long long>(start + row) * p.D + head * DH;
-      uint32_t o[DH / 32][32];
+      constexpr int EC = DH / HALVES;
+      uint32_t o[EC];
+      float fa = 1.f, lsum = l, mtot = ms;
+      if constexpr (HALVES == 1) {
+        tmem_ld_cols<EC>(tmem_base + lane_addr + Cfg::O_COL, o);
+        tmem_ld_wait();
+      } else {
+        const float2 a = sML[((it & 1) * 2 + 0) * kAtQ + row], b = sML[((it & 1) * 2 + 1) * kAtQ + row];
+        const bool hasb = n > 128;                   // warp-uniform
+        mtot = hasb ? fmaxf(a.x, b.x) : a.x;
+        fa = ex2_approx(a.x - mtot);
+        const float fb = hasb ? ex2_approx(b.x - mtot) : 0.f;
+        lsum = a.y * fa + (hasb ? b.y * fb : 0.f);
+        tmem_ld_cols<EC>(tmem_base + lane_addr + Cfg::O_COL + half * EC, o);
+        if (hasb) {
+          uint32_t ob[EC];
+          tmem_ld_cols<EC>(tmem_base + 128 + lane_addr + Cfg::O_COL + half * EC, ob);
+          tmem_ld_wait();
 #pragma unroll
-      for (int c = 0; c < DH / 32; ++c) tmem_ld_32x32(tO + lane_addr + c * 32, o[c]);
-      tmem_ld_wait();
+          for (int j = 0; j < EC; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) * fa + __uint_as_float(ob[j]) * fb);
+          fa = 1.f;
+        } else {
+          tmem_ld_wait();
+        }
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_done);
       if (row < nq) {
+        const float inv = fa / lsum;
+        bf16* op = p.out + static_cast<long long>(start + row) * p.D + head * DH + (HALVES == 2 ? half * EC : 0);
 #pragma unroll
-        for (int c = 0; c < DH / 32; ++c)
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            uint4 w;
-            w.x = pack_bf16x2(__uint_as_float(o[c][j]) * inv, __uint_as_float(o[c][j + 1]) * inv);
-            w.y = pack_bf16x2(__uint_as_float(o[c][j + 2]) * inv, __uint_as_float(o[c][j + 3]) * inv);
-            w.z = pack_bf16x2(__uint_as_float(o[c][j + 4]) * inv, __uint_as_float(o[c][j + 5]) * inv);
-            w.w = pack_bf16x2(__uint_as_float(o[c][j + 6]) * inv, __uint_as_float(o[c][j + 7]) * inv);
-            *reinterpret_cast<uint4*>(op + c * 32 + j) = w;
-          }
-        if (p.lse2 != nullptr) p.lse2[static_cast<long long>(start + row) * p.H + head] = ms + log2f(l);
+        for (int j = 0; j < EC; j += 8) {
+          uint4 w;
+          w.x = pack_bf16x2(__uint_as_float(o[j]) * inv, __uint_as_float(o[j + 1]) * inv);
+          w.y = pack_bf16x2(__uint_as_float(o[j + 2]) * inv, __uint_as_float(o[j + 3]) * inv);
+          w.z = pack_bf16x2(__uint_as_float(o[j + 4]) * inv, __uint_as_float(o[j + 5]) * inv);
+          w.w = pack_bf16x2(__uint_as_float(o[j + 6]) * inv, __uint_as_float(o[j + 7]) * inv);
+          *reinterpret_cast<uint4*>(op + j) = w;
+        }
+        if (p.lse2 != nullptr && half == 0) p.lse2[static_cast<long long>(start + row) * p.H + head] = mtot + log2f(lsum);
+      }
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == NW) {
     tc_fence_after();
     tmem_dealloc(tmem_base, KT);
   }
@@ -400,7 +459,8 @@ __global__ void __launch_bounds__(288, 2) attn_bwd_tc_kernel(const __grid_consta
     // this warp's private 4 KB of the P tile (its 32 query rows x its 64 keys): staging for the coalesced stores
     uint8_t* stage = sP + half * (kAtQ * 128) + quad * 32 * 128;
     uint32_t ph_s = 0, ph_g = 0, ph_l = 0;
-    int nstart = 0, nn = 0;
+    // software pipeline of the per-item scalars: sequence bounds two items ahead, this row's lse one item ahead
+    int nstart = 0, nn = 0, n2start = 0, n2n = 0;
     float nlse = 0.f;
     if (blockIdx.x < p.items) {
       const int s = blockIdx.x / p.H;
@@ -408,17 +468,25 @@ __global__ void __launch_bounds__(288, 2) attn_bwd_tc_kernel(const __grid_consta
       nn = p.cu[s + 1] - nstart;
       if (row < nn) nlse = p.lse2[static_cast<long long>(nstart + row) * p.H + blockIdx.x % p.H];
     }
+    if (blockIdx.x + gridDim.x < p.items) {
+      const int s = (blockIdx.x + gridDim.x) / p.H;
+      n2start = p.cu[s];
+      n2n = p.cu[s + 1] - n2start;
+    }
     const uint8_t* sOrow = smem + 4 * kBwdTile + row * 64;
     const uint8_t* sDOrow = smem + 3 * kBwdTile + row * 64;
     for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
       const int head = item % p.H;
       const int start = nstart, n = nn;
       const float lse = nlse;
-      if (item + gridDim.x < p.items) {   // next item's bounds and this row's lse: the latency hides behind this item
-        const int nitem = item + gridDim.x, s = nitem / p.H;
-        nstart = p.cu[s];
-        nn = p.cu[s + 1] - nstart;
-        nlse = row < nn ? p.lse2[static_cast<long long>(nstart + row) * p.H + (nitem - s * p.H)] : 0.f;
+      nstart = n2start;
+      nn = n2n;
+      if (item + gridDim.x < p.items)     // (addresses known: the loads' latency hides behind this item)
+        nlse = row < nn ? p.lse2[static_cast<long long>(nstart + row) * p.H + (item + gridDim.x) % p.H] : 0.f;
+      if (item + 2 * gridDim.x < p.items) {
+        const int s = (item + 2 * gridDim.x) / p.H;
+        n2start = p.cu[s];
+        n2n = p.cu[s + 1] - n2start;
       }
       const bool live = row < n;
       // delta = sum(O * dO) of this thread's row out of the TMA tiles (64B swizzle), while the S / dP products run
@@ -554,21 +622,21 @@ int attn_fwd_tc_launch(const void* qkv, const int* cu, int n_seqs, int max_len, 
     return 1;
   AttnTcParams p;
   const int qt = max_len > 128 ? 2 : 1;
-  p.cu = cu; p.n_seqs = n_seqs; p.D = D; p.H = H; p.items = n_seqs * H * qt;
+  p.cu = cu; p.n_seqs = n_seqs; p.D = D; p.H = H; p.items = n_seqs * H;   // units = (sequence, head)
   p.scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(dh));
   p.out = reinterpret_cast<bf16*>(out); p.lse2 = lse2;
-  auto go = [&](auto kernel, int smem, int ctas) -> int {
+  auto go = [&](auto kernel, int smem, int ctas, int threads) -> int {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) { set_error("attn_fwd_tc attr: %s", cudaGetErrorString(e)); return WJ_ERR_RUNTIME; }
     int grid = ctas * sm_count();
     if (grid > p.items) grid = p.items;
-    kernel<<<grid, 160, smem, st>>>(tm, p);
+    kernel<<<grid, threads, smem, st>>>(tm, p);
     return check_launch("attn_fwd_tc");
   };
-  if (dh == 64 && qt == 1) return go(attn_fwd_tc_kernel<64, 128>, AttnTcCfg<64, 128>::SMEM, AttnTcCfg<64, 128>::CTAS);
-  if (dh == 64) return go(attn_fwd_tc_kernel<64, 256>, AttnTcCfg<64, 256>::SMEM, AttnTcCfg<64, 256>::CTAS);
-  if (qt == 1) return go(attn_fwd_tc_kernel<32, 128>, AttnTcCfg<32, 128>::SMEM, AttnTcCfg<32, 128>::CTAS);
-  return go(attn_fwd_tc_kernel<32, 256>, AttnTcCfg<32, 256>::SMEM, AttnTcCfg<32, 256>::CTAS);
+  if (dh == 64 && qt == 1) return go(attn_fwd_tc_kernel<64, 128>, AttnTcCfg<64, 128>::SMEM, AttnTcCfg<64, 128>::CTAS, AttnTcCfg<64, 128>::THREADS);
+  if (dh == 64) return go(attn_fwd_tc_kernel<64, 256>, AttnTcCfg<64, 256>::SMEM, AttnTcCfg<64, 256>::CTAS, AttnTcCfg<64, 256>::THREADS);
+  if (qt == 1) return go(attn_fwd_tc_kernel<32, 128>, AttnTcCfg<32, 128>::SMEM, AttnTcCfg<32, 128>::CTAS, AttnTcCfg<32, 128>::THREADS);
+  return go(attn_fwd_tc_kernel<32, 256>, AttnTcCfg<32, 256>::SMEM, AttnTcCfg<32, 256>::CTAS, AttnTcCfg<32, 256>::THREADS);
 }
 
 
