@@ -212,12 +212,12 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t t_ba
       if (p.act == 3) {
         // the Linear output is bf16 under autocast before it meets the fp32 residual / positional table
 #pragma unroll
-        for (int c = 0; c < 8; ++c) x[c] = bf16_round(x[c]);
+        for (int c = 0; c < 8; c += 2) bf16_round2(x[c], x[c + 1]);
       } else if (p.act == 1) {
         // autocast semantics: the linear/conv output is bf16 and GELU is evaluated on that bf16 value; out2
         // receives GELU'(h) (bf16), which is all the backward needs of the pre-activation
 #pragma unroll
-        for (int c = 0; c < 8; ++c) x[c] = bf16_round(x[c]);
+        for (int c = 0; c < 8; c += 2) bf16_round2(x[c], x[c + 1]);
         if (p.out2 != nullptr) {
           float d[8];
 #pragma unroll
@@ -341,7 +341,11 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const Out
     if constexpr (!HEAVY) {
       if (p.act == 1) {   // autocast semantics: the linear/conv output is bf16 and GELU is evaluated on that bf16 value
 #pragma unroll
-        for (int j = 0; j < 32; j += 2) w[j >> 1] = pack_bf16x2(gelu_fast(bf16_round(f[j])), gelu_fast(bf16_round(f[j + 1])));
+        for (int j = 0; j < 32; j += 2) {
+          float x0 = f[j], x1 = f[j + 1];
+          bf16_round2(x0, x1);
+          w[j >> 1] = pack_bf16x2(gelu_fast(x0), gelu_fast(x1));
+        }
       } else {
 #pragma unroll
         for (int j = 0; j < 32; j += 2) w[j >> 1] = pack_bf16x2(f[j], f[j + 1]);
@@ -351,8 +355,10 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const Out
 #pragma unroll
         for (int j = 0; j < 32; j += 2) {
           float g0, d0, g1, d1;
-          gelu_fast2(bf16_round(f[j]), g0, d0);
-          gelu_fast2(bf16_round(f[j + 1]), g1, d1);
+          float x0 = f[j], x1 = f[j + 1];
+          bf16_round2(x0, x1);
+          gelu_fast2(x0, g0, d0);
+          gelu_fast2(x1, g1, d1);
           w[j >> 1] = pack_bf16x2(g0, g1);
           w2[j >> 1] = pack_bf16x2(d0, d1);
         }
@@ -463,7 +469,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           const int row0 = (m_blk - b * p.mb_per_batch) * BM;
           const int nkb = p.K / BK;
           for (int kb = 0; kb < nkb; ++kb) {
-            mbar_wait(&empty_bar[stage], phase ^ 1);
+            mbar_wait_relaxed(&empty_bar[stage], phase ^ 1);
             uint8_t* sa = smem + stage * C::STAGE_BYTES;
             uint8_t* sb = sa + C::A_BYTES;
             int c0, q, po;
@@ -495,7 +501,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           for (int kb = lo; kb < hi; ++kb) {
             const int b = kb / p.kb_per_batch;
             const int row0 = (kb - b * p.kb_per_batch) * BK;
-            mbar_wait(&empty_bar[stage], phase ^ 1);
+            mbar_wait_relaxed(&empty_bar[stage], phase ^ 1);
             uint8_t* sa = smem + stage * C::STAGE_BYTES;
             uint8_t* sb = sa + C::A_BYTES;
             mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
@@ -531,7 +537,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
         const int nkb = num_kb(tile);
-        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        mbar_wait_relaxed(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
         for (int kb = 0; kb < nkb; ++kb) {

@@ -42,6 +42,26 @@ __device__ __forceinline__ void fence_mbar_init() {
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
+// Wait for roles that are usually far ahead of the barrier (the TMA producer on a full ring, the MMA warp on an
+// accumulator the epilogue still reads): after a failed probe the warp sleeps instead of re-issuing the probe every
+// ~16 cycles, which would take issue slots from the epilogue warps of the same scheduler.
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+  uint32_t addr = static_cast<uint32_t>(__cvta_generic_to_shared(bar));
+  uint32_t ok;
+  for (;;) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (ok) break;
+    __nanosleep(64);
+  }
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t addr = smem_u32(bar);
   uint32_t ok;
@@ -329,6 +349,13 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+// Two values rounded to bf16 (round-to-nearest-even) and widened again with ONE pack (F2FP) + two integer ops instead
+// of two F2F conversions: F2F shares the quarter-rate XU pipe with MUFU, which the GELU epilogues saturate.
+__device__ __forceinline__ void bf16_round2(float& a, float& b) {
+  const uint32_t w = pack_bf16x2(a, b);
+  a = __uint_as_float(w << 16);
+  b = __uint_as_float(w & 0xffff0000u);
+}
 
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
