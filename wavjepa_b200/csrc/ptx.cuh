@@ -45,6 +45,7 @@ __device__ __forceinline__ void fence_proxy_async_smem() {
 // Wait for roles that are usually far ahead of the barrier (the TMA producer on a full ring, the MMA warp on an
 // accumulator the epilogue still reads): after a failed probe the warp sleeps instead of re-issuing the probe every
 // ~16 cycles, which would take issue slots from the epilogue warps of the same scheduler.
+template <int NS = 64>
 __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
   uint32_t addr = static_cast<uint32_t>(__cvta_generic_to_shared(bar));
   uint32_t ok;
@@ -59,7 +60,7 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity
         : "r"(addr), "r"(parity)
         : "memory");
     if (ok) break;
-    __nanosleep(64);
+    __nanosleep(NS);
   }
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
