@@ -209,10 +209,12 @@ __global__ void __launch_bounds__(256) conv0_fwd_kernel(Conv0Args a, const float
         }
         const float4 pr = s_p[(nt + u) * 4 + tg];
         float y0, y1, y2, y3, d0, d1, d2, d3;
-        gelu_fast2(fmaf(bf16_round(c[0]), pr.x, pr.y), y0, d0);
-        gelu_fast2(fmaf(bf16_round(c[1]), pr.z, pr.w), y1, d1);
-        gelu_fast2(fmaf(bf16_round(c[2]), pr.x, pr.y), y2, d2);
-        gelu_fast2(fmaf(bf16_round(c[3]), pr.z, pr.w), y3, d3);
+        bf16_round2(c[0], c[1]);   // (one F2FP per pair instead of two XU-pipe F2F: the GELU already saturates the XU)
+        bf16_round2(c[2], c[3]);
+        gelu_fast2(fmaf(c[0], pr.x, pr.y), y0, d0);
+        gelu_fast2(fmaf(c[1], pr.z, pr.w), y1, d1);
+        gelu_fast2(fmaf(c[2], pr.x, pr.y), y2, d2);
+        gelu_fast2(fmaf(c[3], pr.z, pr.w), y3, d3);
         y[u][0] = pack_bf16x2(y0, y1); y[u][1] = pack_bf16x2(y2, y3);
         d[u][0] = pack_bf16x2(d0, d1); d[u][1] = pack_bf16x2(d2, d3);
       }
@@ -304,8 +306,10 @@ __global__ void __launch_bounds__(256, 2) conv0_bwd_kernel(Conv0Args a, const fl
         const float2 gb = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&dgb));
         const float z0 = ya.x * ga.x, z1 = ya.y * ga.y, z2 = yb.x * gb.x, z3 = yb.y * gb.y;   // dz (0 past the end)
         const float4 mr = s_mr[(c_base >> 1) + nt * 4 + tg];
-        const float h0 = (bf16_round(c[0]) - mr.x) * mr.y, h1 = (bf16_round(c[1]) - mr.z) * mr.w;
-        const float h2 = (bf16_round(c[2]) - mr.x) * mr.y, h3 = (bf16_round(c[3]) - mr.z) * mr.w;
+        bf16_round2(c[0], c[1]);
+        bf16_round2(c[2], c[3]);
+        const float h0 = (c[0] - mr.x) * mr.y, h1 = (c[1] - mr.z) * mr.w;
+        const float h2 = (c[2] - mr.x) * mr.y, h3 = (c[3] - mr.z) * mr.w;
         s1[nt][0] += z0 + z2; s1[nt][1] += z1 + z3;
         s2[nt][0] = fmaf(z0, h0, fmaf(z2, h2, s2[nt][0]));
         s2[nt][1] = fmaf(z1, h1, fmaf(z3, h3, s2[nt][1]));

@@ -232,12 +232,10 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t t_ba
         }
       } else if (p.act == 2) {
         const uint4 w = pre_aux ? pre[hr][0] : *reinterpret_cast<const uint4*>(p.aux + orow * p.ld_aux + n0);
-        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&w);
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          const float2 hh = __bfloat1622float2(h2[t]);
-          x[2 * t] *= hh.x; x[2 * t + 1] *= hh.y;
-        }
+        x[0] *= __uint_as_float(w.x << 16); x[1] *= __uint_as_float(w.x & 0xffff0000u);
+        x[2] *= __uint_as_float(w.y << 16); x[3] *= __uint_as_float(w.y & 0xffff0000u);
+        x[4] *= __uint_as_float(w.z << 16); x[5] *= __uint_as_float(w.z & 0xffff0000u);
+        x[6] *= __uint_as_float(w.w << 16); x[7] *= __uint_as_float(w.w & 0xffff0000u);
       }
       if (p.resid != nullptr) {
         if (p.resid_f32) {
@@ -264,17 +262,14 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t t_ba
           *reinterpret_cast<float4*>(op + 4) = make_float4(x[4], x[5], x[6], x[7]);
         }
       } else {
-        uint4 w;
-        w.x = pack_bf16x2(x[0], x[1]); w.y = pack_bf16x2(x[2], x[3]);
-        w.z = pack_bf16x2(x[4], x[5]); w.w = pack_bf16x2(x[6], x[7]);
-        *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + orow * p.ld_out + n0) = w;
+        const uint32_t w0 = pack_bf16x2(x[0], x[1]), w1 = pack_bf16x2(x[2], x[3]), w2 = pack_bf16x2(x[4], x[5]),
+                       w3 = pack_bf16x2(x[6], x[7]);
+        *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + orow * p.ld_out + n0) = make_uint4(w0, w1, w2, w3);
         if (p.colsum != nullptr) {   // sums of the values as stored (bf16), like autograd's bias gradient
-          const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&w);
-#pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            const float2 hh = __bfloat1622float2(h2[t]);
-            x[2 * t] = hh.x; x[2 * t + 1] = hh.y;
-          }
+          x[0] = __uint_as_float(w0 << 16); x[1] = __uint_as_float(w0 & 0xffff0000u);
+          x[2] = __uint_as_float(w1 << 16); x[3] = __uint_as_float(w1 & 0xffff0000u);
+          x[4] = __uint_as_float(w2 << 16); x[5] = __uint_as_float(w2 & 0xffff0000u);
+          x[6] = __uint_as_float(w3 << 16); x[7] = __uint_as_float(w3 & 0xffff0000u);
         }
       }
       if (p.colsum != nullptr) {
