@@ -187,8 +187,9 @@ int wj_target_accum(const float* x, const float* rowsum, int B, int T, int D, fl
 /* Variable-length multi-head attention over packed tokens: qkv bf16 [tokens, 3*D] (q|k|v), sequences given by
  * cu_seqlens [n_seqs+1], softmax(q k^T / sqrt(D/H)) v, head dim 32 or 64.  out bf16 [tokens, D];
  * lse2 fp32 [tokens, H] = log2-sum-exp2 of the scaled logits (saved for the backward; may be NULL).
- * total_tokens = rows of qkv.  Sequences of <= 128 tokens run on tcgen05 (S = Q K^T and O = P V as UMMAs with TMEM
- * accumulators, softmax one query row per thread); longer ones on the mma.sync kernel.
+ * total_tokens = rows of qkv.  Forward: sequences of <= 256 tokens run on tcgen05 (S = Q K^T and O = P V as UMMAs with
+ * TMEM accumulators, P handed back through TMEM, softmax one query row per thread); longer ones on the mma.sync kernel.
+ * Backward: head dim 32 with <= 128 tokens runs on tcgen05 (S, dP, dV, dK, dQ as UMMAs); everything else on mma.sync.
  * Reference: F.scaled_dot_product_attention with key_padding_mask inside nn.MultiheadAttention. */
 int wj_attn_varlen_fwd(const void* qkv_bf16, const int* cu_seqlens, int n_seqs, int max_len, int64_t total_tokens, int D,
                        int H, void* out_bf16, float* lse2, void* stream);
@@ -218,6 +219,18 @@ int wj_predictor_assemble_bwd(const float* dx0, const int* vis_src, int N, int D
  * JEPA.masked_loss (wavjepa/jepa.py:335-362) restricted to the target rows (all other rows have zero weight). */
 int wj_masked_mse(const void* pred_bf16, const float* targets, const int* tgt_rows, int Nt, int D, float* loss,
                   void* dpred_bf16, void* stream);
+
+/* Denoiser losses (wavjepa/denoiser.py:352-356): pred fp32 [2, M] = student features of the (clean, generated) halves,
+ * target fp32 [M] = frozen-teacher features of the clean audio.  sums[h] (fp64, caller-zeroed) += sum (pred[h]-target)^2,
+ * i.e. loss_clean = sums[0] / M, loss_denoise_dereverb = sums[1] / M; dpred (optional, fp32 [2, M]) = gradient of
+ * alpha * loss_clean + (1 - alpha) * loss_denoise_dereverb. */
+int wj_mse_pair(const float* pred, const float* target, int64_t M, float alpha, double* sums, float* dpred, void* stream);
+
+/* Segmental-SNR mixing (data_modules/scene_module/generate_scenes_batch.py:107-146 add_noise): rows b of source / noise
+ * [B, T] fp32; energies over the window [start_b, start_b + length_b); out = source + a_b * noise with
+ * a_b = sqrt(E_source / (E_noise + 1e-9) * 10^(-snr_b / 10)).  energy: fp64 [B, 2] workspace. */
+int wj_snr_mix(const float* source, const float* noise, const int* start, const int* length, const float* snr, int B,
+               int64_t T, double* energy, float* out, void* stream);
 
 /* teacher = teacher * decay + (1 - decay) * student, fp32, rounding exactly like
  * teacher.mul_(r).add_((1 - r) * student) (JEPA._step_teacher, wavjepa/jepa.py:193-198). */

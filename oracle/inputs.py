@@ -43,3 +43,24 @@ def training_inputs(cfg: jo.Cfg, n_clips: int, crops: int, seed: int = 1234, cli
 def hear_inputs(n_clips: int, n_samples: int, seed: int = 1234) -> torch.Tensor:
     g = torch.Generator().manual_seed(seed)
     return torch.rand(n_clips, n_samples, generator=g) * 2 - 1
+
+
+def denoiser_batch(B: int = 2, T32: int = 80000, rir_len: int = 4000, n_noise: int = 2, seed: int = 5):
+    """Synthetic batch with the tuple layout of Denoiser.on_after_batch_transfer (wavjepa/denoiser.py:229-237):
+    (audio [B, T32] @ 32 kHz, source_rir [B, 2, R], noise [B, T32], noise_length [B], noise_start_idx [B],
+    noise_rirs [B, S, 2, R], snr [B]).  RIRs are exponentially decaying noise with a unit direct path."""
+    g = torch.Generator().manual_seed(seed)
+    audio = torch.rand(B, T32, generator=g) * 2 - 1
+    decay = torch.exp(-torch.arange(rir_len) / (rir_len / 6.0))
+    source_rir = torch.randn(B, 2, rir_len, generator=g) * decay * 0.1
+    source_rir[..., 0] = 1.0
+    noise_rirs = torch.randn(B, n_noise, 2, rir_len, generator=g) * decay * 0.1
+    noise_rirs[..., 0] = 0.7
+    noise_start = torch.randint(0, T32 // 4, (B,), generator=g)
+    noise_len = torch.randint(T32 // 4, T32 // 2, (B,), generator=g)
+    noise = torch.zeros(B, T32)
+    for b in range(B):   # the loader places (and fades) the noise inside its window; zeros elsewhere
+        seg = torch.randn(int(noise_len[b]), generator=g) * 0.3
+        noise[b, int(noise_start[b]):int(noise_start[b]) + int(noise_len[b])] = seg
+    snr = torch.tensor([5.0, 15.0, 0.0, 25.0])[:B].clone() if B <= 4 else torch.rand(B, generator=g) * 30 - 5
+    return audio, source_rir, noise, noise_len, noise_start, noise_rirs, snr

@@ -354,3 +354,77 @@ def data_pre_process(waveform: torch.Tensor, audio_sr: int, sr: int = 16000, sec
     elif padding < 0:
         audio = audio[:, : sr * seconds]
     return audio
+
+
+# ------------------------------------------------------------------------------------------------- denoiser stage
+def student_features(audio, sd, cfg: Cfg):
+    """extractor -> LayerNorm -> mapper -> + positions -> encoder incl. final norm on full sequences, no mask
+    (wavjepa/denoiser.py:338-346 `_forward_features`; also JEPA.get_audio_representation, jepa.py:456-467)."""
+    return run_stack(local_features(audio, sd, cfg), sd, "encoder", cfg.layers, cfg.nhead, None)
+
+
+def denoiser_forward(generated, clean, sd_student, sd_teacher, cfg: Cfg, alpha: float) -> Dict[str, torch.Tensor]:
+    """Denoiser.forward (wavjepa/denoiser.py:308-364): the student on the clean and on the generated scene, a frozen
+    WavJEPA teacher on the clean scene, two dense MSE losses mixed by alpha."""
+    f_clean = student_features(clean, sd_student, cfg)
+    f_gen = student_features(generated, sd_student, cfg)
+    with torch.no_grad():
+        targets = student_features(clean, sd_teacher, Cfg()).clone()     # the teacher is always WavJEPA-base (:160-171)
+    loss_clean = F.mse_loss(f_clean, targets)
+    loss_dd = F.mse_loss(f_gen, targets)
+    return dict(loss=alpha * loss_clean + (1 - alpha) * loss_dd, loss_clean=loss_clean, loss_denoise_dereverb=loss_dd,
+                features_clean=f_clean, features_generated=f_gen, targets=targets)
+
+
+def fftconvolve_full(x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+    """torchaudio.functional.fftconvolve(mode="full") (third-party, pinned torchaudio 2.7): rfft of both inputs at
+    n = len(x) + len(y) - 1, product, irfft."""
+    n = x.shape[-1] + y.shape[-1] - 1
+    return torch.fft.irfft(torch.fft.rfft(x, n=n) * torch.fft.rfft(y, n=n), n=n)
+
+
+def scene_convolve_with_rir(waveform: torch.Tensor, rir: torch.Tensor) -> torch.Tensor:
+    """generate_scenes_batch.py:12-45: waveform [B, T], rir [B, C, R] -> [B, C, T] (full convolution cut to T)."""
+    T = waveform.shape[-1]
+    return torch.stack([torch.stack([fftconvolve_full(waveform[b], rir[b, c]) for c in range(rir.shape[1])])
+                        for b in range(waveform.shape[0])])[..., :T]
+
+
+def scene_add_noise(source, noise, snr, start_idx, real_noise_length):
+    """generate_scenes_batch.py:107-146: a = sqrt(||x_active||^2 / (||n_active||^2 + 1e-9) * 10^(-snr/10)) over the
+    window [start, start + length); source + a * noise.  source, noise [B, 1, T]."""
+    B, _, T = source.shape
+    t = torch.arange(T).view(1, 1, -1)
+    mask = (t >= start_idx.view(B, 1, 1)) & (t < (start_idx + real_noise_length).view(B, 1, 1))
+    nx = torch.linalg.vector_norm(source * mask, ord=2, dim=-1, keepdim=True)
+    nn_ = torch.linalg.vector_norm(noise * mask, ord=2, dim=-1, keepdim=True)
+    a = torch.sqrt(nx ** 2 / (nn_ ** 2 + 1e-9) * 10 ** (-snr.view(B, 1, 1) / 10.0))
+    return source + a * noise
+
+
+def generate_scene(source_rir, noise_rirs, source, noise, real_noise_length, noise_start_idx, snr):
+    """generate_scenes_batch.py:148-188, case 1 (source RIR and noise present): first RIR channel only."""
+    T = source.shape[-1]
+    conv = scene_convolve_with_rir(source, source_rir[:, [0], :])
+    agg = torch.zeros(source.shape[0], 1, T)
+    for i in range(noise_rirs.shape[1]):
+        agg = agg + scene_convolve_with_rir(noise, noise_rirs[:, i, [0], :])
+    return scene_add_noise(conv, agg[:, :, :T], snr, noise_start_idx, real_noise_length)
+
+
+def denoiser_batch(batch, starts: torch.Tensor, perm: torch.Tensor, sr: int = 16000, target_length: int = 32159):
+    """Denoiser.on_after_batch_transfer (wavjepa/denoiser.py:215-290) with the random crop starts [B, nr] and the
+    shuffle permutation given: scene at 32 kHz, torchaudio Kaiser-sinc resampling of scene and clean audio, identical
+    crops, per-crop normalisation -> (generated, clean) [B*nr, 1, target_length] fp32 (the caller casts to bf16)."""
+    import torchaudio
+
+    audio, source_rir, noise, noise_length, noise_start_idx, noise_rirs, snr = batch
+    scene = generate_scene(source_rir, noise_rirs, audio, noise, noise_length, noise_start_idx, snr)
+    clean = audio.unsqueeze(1)
+    rs = lambda x: torchaudio.functional.resample(x, 32000, sr, lowpass_filter_width=64, rolloff=0.9475937167399596,
+                                                  resampling_method="sinc_interp_kaiser", beta=14.769656459379492)
+    if sr != 32000:
+        scene, clean = rs(scene), rs(clean)
+    gen = crop_normalise(scene, starts, target_length)[perm]
+    cln = crop_normalise(clean, starts, target_length)[perm]
+    return gen, cln

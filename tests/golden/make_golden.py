@@ -218,8 +218,71 @@ def golden_interop():
     np.savez_compressed(os.path.join(HERE, "interop.npz"), **out)
 
 
+def golden_denoiser():
+    """SURVEY.md 8(f)-4, executed on the unmodified reference: Denoiser.on_after_batch_transfer (scene generation,
+    resampling, crops) with the random draws pinned, then Denoiser.forward + backward with a frozen WavJEPA-base
+    teacher loaded through the reference's own `_set_teacher` (a temporary Lightning-style checkpoint file)."""
+    import tempfile
+    from wavjepa.denoiser import Denoiser
+    out = {}
+    cfg = jo.Cfg()
+    sd_s = jo.make_state_dict(cfg, seed=11)
+    sd_t = jo.make_state_dict(cfg, seed=12)
+    ext = ref.ConvFeatureExtractor(conv_layers_spec=cfg.spec, in_channels=1)
+    alpha = 0.25
+    m = Denoiser(feature_extractor=ext, transformer_encoder_layers_cfg=ref.TransformerLayerCFG.create(),
+                 transformer_encoder_cfg=ref.TransformerEncoderCFG.create(), resample_sr=16000,
+                 process_audio_seconds=2.01, nr_samples_per_audio=2, size="base", alpha=alpha)
+    own = {k: v for k, v in sd_s.items() if k in m.state_dict()}
+    print("denoiser student load:", m.load_state_dict(own, strict=True))
+    with tempfile.TemporaryDirectory() as td:
+        path = os.path.join(td, "teacher.ckpt")
+        torch.save({"state_dict": sd_t}, path)
+        m._set_teacher(path)
+    json.dump(list(m.state_dict().keys()), open(os.path.join(HERE, "ref_denoiser_state_dict_keys.json"), "w"))
+    # ---- batch preparation with the two random draws pinned
+    batch = oi.denoiser_batch()
+    B, nr, tl = batch[0].shape[0], 2, m.target_length
+    L16 = batch[0].shape[1] // 2
+    g = torch.Generator().manual_seed(3)
+    starts = torch.randint(0, L16 - tl + 1, (B, nr), generator=g)
+    perm = torch.randperm(B * nr, generator=g)
+    # reference defect: on_after_batch_transfer reads `self.ORIGINAL_SR` (wavjepa/denoiser.py:262) but only the module
+    # constant ORIGINAL_SR = 32000 (:23) exists -> AttributeError as shipped.  The intended value is supplied here.
+    m.ORIGINAL_SR = 32000
+    real_randint, real_randperm = torch.randint, torch.randperm
+    torch.randint = lambda *a, **k: starts.clone()
+    torch.randperm = lambda *a, **k: perm.clone()
+    try:
+        gen16, clean16 = m.on_after_batch_transfer(batch, 0)
+    finally:
+        torch.randint, torch.randperm = real_randint, real_randperm
+    out["starts"], out["perm"] = starts.numpy(), perm.numpy()
+    out["gen"] = oi.subsample(gen16.float())
+    out["clean"] = oi.subsample(clean16.float())
+    out["gen_l2"], out["clean_l2"] = np.float64(gen16.float().norm()), np.float64(clean16.float().norm())
+    print("denoiser batch", tuple(gen16.shape), gen16.dtype)
+    # ---- forward + backward (fp32 CPU, like the other training goldens)
+    o = m(gen16.float(), clean16.float())
+    o["loss"].backward()
+    out["loss"] = np.float64(o["loss"].item())
+    out["loss_clean"] = np.float64(o["loss_clean"].item())
+    out["loss_dd"] = np.float64(o["loss_denoise_dereverb"].item())
+    gn = {}
+    for n, p in m.named_parameters():
+        if p.grad is not None:
+            gn[n] = float(p.grad.norm())
+            if n in ("encoder.layers.11.linear2.weight", "encoder.layers.0.self_attn.in_proj_weight",
+                     "post_extraction_mapper.weight", "extract_audio.cnn.0.0.weight", "extract_audio.cnn.3.0.weight",
+                     "encoder.norm.weight", "feature_norms.bias"):
+                out["grad:" + n] = oi.subsample(p.grad)
+    json.dump(dict(alpha=alpha, grad_norms=gn), open(os.path.join(HERE, "denoiser.json"), "w"), indent=0)
+    np.savez_compressed(os.path.join(HERE, "denoiser.npz"), **out)
+    print("denoiser losses", out["loss"], out["loss_clean"], out["loss_dd"], "grads", len(gn))
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["masks", "keys", "train", "nat", "hear", "interop"]
+    which = sys.argv[1:] or ["masks", "keys", "train", "nat", "hear", "interop", "denoiser"]
     if "masks" in which:
         golden_masks()
     if "keys" in which:
@@ -233,3 +296,5 @@ if __name__ == "__main__":
         golden_hear()
     if "interop" in which:
         golden_interop()
+    if "denoiser" in which:
+        golden_denoiser()

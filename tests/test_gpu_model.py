@@ -363,3 +363,63 @@ def test_gpu_input_pipeline_matches_reference_preprocessing():
     c_m, t_m, v_m = mk(batch_size=n * 8, n_times=200, in_channels=1)
     x16, *_ = model.on_after_batch_transfer((clips, c_m.view(n, 8, -1), t_m.view(n, 8, 4, -1), v_m.view(n, 8, 4, -1)), 0)
     assert x16.shape == (n * 8, 1, 32159) and torch.isfinite(x16.float()).all()
+
+
+# ------------------------------------------------------------------------------------------------- denoiser stage
+def _denoiser(alpha, nr=2):
+    from wavjepa_b200.denoiser import Denoiser
+    cfg = jo.Cfg()
+    ext = w.ConvFeatureExtractor(conv_layers_spec=cfg.spec, in_channels=1)
+    m = Denoiser(feature_extractor=ext, transformer_encoder_layers_cfg=w.TransformerLayerCFG.create(),
+                 transformer_encoder_cfg=w.TransformerEncoderCFG.create(), resample_sr=16000,
+                 process_audio_seconds=2.01, nr_samples_per_audio=nr, size="base", alpha=alpha)
+    sd_s = jo.make_state_dict(cfg, seed=11)
+    own = {k: v for k, v in sd_s.items() if k in m.state_dict()}
+    m.load_state_dict(own, strict=True)
+    m._set_teacher({"state_dict": jo.make_state_dict(cfg, seed=12)})
+    return m.to(DEV)
+
+
+def test_denoiser_stage_matches_reference_goldens():
+    """scene generation + resampling + crops, Denoiser.forward losses and every parameter gradient
+    against the fixtures of the executed reference (fp32 CPU); bf16 kernels -> the tolerances of the JEPA step."""
+    g = np.load(os.path.join(GOLD, "denoiser.npz"))
+    meta = json.load(open(os.path.join(GOLD, "denoiser.json")))
+    m = _denoiser(meta["alpha"])
+    batch = oi.denoiser_batch()
+    starts, perm = torch.from_numpy(g["starts"]), torch.from_numpy(g["perm"])
+    gen16, clean16 = m.on_after_batch_transfer(tuple(t.to(DEV) for t in batch), 0, starts=starts, perm=perm)
+    assert gen16.dtype == torch.bfloat16 and tuple(gen16.shape) == (4, 1, 32159)
+    assert rel(oi.subsample(gen16.float().cpu()), g["gen"]) < 3e-3
+    assert rel(oi.subsample(clean16.float().cpu()), g["clean"]) < 3e-3
+    assert abs(float(gen16.float().norm()) - float(g["gen_l2"])) / float(g["gen_l2"]) < 1e-3
+    # the reference's own inputs (restated on the host, pinned in tests/test_oracle_cpu.py) for the model comparison
+    gen_o, clean_o = jo.denoiser_batch(batch, starts, perm)
+    out, grads = m.forward_backward(gen_o.bfloat16().to(DEV), clean_o.bfloat16().to(DEV))
+    for k, gk in (("loss", "loss"), ("loss_clean", "loss_clean"), ("loss_denoise_dereverb", "loss_dd")):
+        assert abs(out[k].item() - float(g[gk])) / float(g[gk]) < 2e-3, (k, out[k].item(), float(g[gk]))
+    out_f = m(gen_o.bfloat16().to(DEV), clean_o.bfloat16().to(DEV))
+    assert abs(out_f["loss"].item() - out["loss"].item()) < 1e-5
+    for n_, ref_norm in meta["grad_norms"].items():
+        e = abs(float(grads[n_].norm()) - ref_norm) / (ref_norm + 1e-12)
+        assert e < GRAD_TOL, (n_, e)
+    for k in g.files:
+        if k.startswith("grad:"):
+            e = rel(oi.subsample(grads[k[5:]].cpu()), g[k])
+            assert e < GRAD_TOL, (k, e)
+
+
+def test_denoiser_train_step_learns():
+    m = _denoiser(0.25, nr=4)
+    m.global_step = 5000                      # past the warm-up: lr = 1e-4
+    g = torch.Generator().manual_seed(0)
+    clean = torch.randn(8, 1, 32159, generator=g).bfloat16().to(DEV)
+    gen = (clean.float() + 0.3 * torch.randn(8, 1, 32159, generator=g).to(DEV)).bfloat16()
+    before = {n: p.detach().clone() for n, p in m.named_parameters() if p.requires_grad}
+    teacher_before = m.teacher.encoder.layers[0].linear1.weight.detach().clone()
+    losses = [m.train_step(gen, clean)["loss"].item() for _ in range(6)]
+    assert losses[-1] < losses[0], losses
+    assert m.global_step == 5006
+    moved = [n for n, p in m.named_parameters() if p.requires_grad and not torch.equal(p.detach(), before[n])]
+    assert "encoder.layers.0.linear1.weight" in moved and "extract_audio.cnn.0.0.weight" in moved
+    assert torch.equal(m.teacher.encoder.layers[0].linear1.weight, teacher_before)      # frozen

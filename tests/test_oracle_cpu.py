@@ -232,3 +232,48 @@ def test_sinc_table_is_torchaudios():
         k, w, o, n = sinc_resample_table(asr, 16000)
         assert w == w_ref and (o, n) == (asr // g, 16000 // g)
         assert torch.equal(k, k_ref[:, 0, :])
+
+
+# ------------------------------------------------------------------------------------------------- denoiser stage
+def test_oracle_denoiser_matches_reference():
+    """the restated scene generation / batch preparation / Denoiser.forward + backward against the
+    fixtures produced by the executed reference (tests/golden/make_golden.py::golden_denoiser)."""
+    torch.set_num_threads(os.cpu_count())
+    g = np.load(os.path.join(GOLD, "denoiser.npz"))
+    meta = json.load(open(os.path.join(GOLD, "denoiser.json")))
+    batch = oi.denoiser_batch()
+    starts, perm = torch.from_numpy(g["starts"]), torch.from_numpy(g["perm"])
+    gen, clean = jo.denoiser_batch(batch, starts, perm)
+    gen16, clean16 = gen.bfloat16().float(), clean.bfloat16().float()
+    assert rel(oi.subsample(gen16), g["gen"]) < 2e-3 and rel(oi.subsample(clean16), g["clean"]) < 2e-3
+    assert abs(float(gen16.norm()) - float(g["gen_l2"])) / float(g["gen_l2"]) < 1e-4
+    cfg = jo.Cfg()
+    sd_s = {k: v.clone().requires_grad_(v.is_floating_point() and not k.startswith(("pos_", "teacher")))
+            for k, v in jo.make_state_dict(cfg, seed=11).items()}
+    sd_t = jo.make_state_dict(cfg, seed=12)
+    out = jo.denoiser_forward(gen16, clean16, sd_s, sd_t, cfg, meta["alpha"])
+    for k, gk in (("loss", "loss"), ("loss_clean", "loss_clean"), ("loss_denoise_dereverb", "loss_dd")):
+        assert abs(out[k].item() - float(g[gk])) / float(g[gk]) < 2e-4, (k, out[k].item(), float(g[gk]))
+    out["loss"].backward()
+    for n, ref_norm in meta["grad_norms"].items():
+        gr = sd_s[n].grad
+        assert gr is not None, n
+        assert abs(float(gr.norm()) - ref_norm) / (ref_norm + 1e-12) < 5e-3, n
+    for k in g.files:
+        if k.startswith("grad:"):
+            assert rel(oi.subsample(sd_s[k[5:]].grad), g[k]) < 5e-3, k
+
+
+def test_denoiser_state_dict_is_the_references():
+    import wavjepa_b200 as w
+    from wavjepa_b200.denoiser import Denoiser
+    keys = json.load(open(os.path.join(GOLD, "ref_denoiser_state_dict_keys.json")))
+    ext = w.ConvFeatureExtractor(conv_layers_spec=[(512, 10, 5)] + [(512, 3, 2)] * 4 + [(512, 2, 2)], in_channels=1)
+    m = Denoiser(feature_extractor=ext, transformer_encoder_layers_cfg=w.TransformerLayerCFG.create(),
+                 transformer_encoder_cfg=w.TransformerEncoderCFG.create(), nr_samples_per_audio=2, alpha=0.25)
+    own = [k for k in keys if not k.startswith("teacher.")]
+    assert list(m.state_dict().keys()) == own
+    m._set_teacher({"state_dict": jo.make_state_dict(jo.Cfg(), seed=12)})
+    assert list(m.state_dict().keys()) == keys
+    assert all(not p.requires_grad for p in m.teacher.parameters())
+    assert abs(m.lr_at(2500) - 0.5e-4) < 1e-12 and m.lr_at(0) == 0.0      # 5000 warm-up steps (denoiser.py:208-209)

@@ -2,12 +2,13 @@
 
 Same module API as the reference (labhamlet/wavjepa): `JEPA`, `ConvFeatureExtractor`, `ConvChannelFeatureExtractor`,
 `TimeInverseBlockMasker`, `SpeechMasker`, `TransformerLayerCFG`, `TransformerEncoderCFG`; HEAR entry points live in
-`wavjepa_b200.hear`.  All compute goes through libwavjepa_b200.so (include/wavjepa_b200.h); there is no fallback.
+`wavjepa_b200.hear`, the denoiser stage (`Denoiser`, scene generation) in `wavjepa_b200.denoiser`.  All compute goes through libwavjepa_b200.so (include/wavjepa_b200.h); there is no fallback.
 """
 from .types import ForwardReturn, TransformerEncoderCFG, TransformerLayerCFG  # noqa: F401
 from .extractors import ConvChannelFeatureExtractor, ConvFeatureExtractor, Extractor  # noqa: F401
 from .masking import SpeechMasker, TimeInverseBlockMasker  # noqa: F401
 from .jepa import JEPA  # noqa: F401
+from .denoiser import Denoiser  # noqa: F401
 
-__all__ = ["JEPA", "ConvFeatureExtractor", "ConvChannelFeatureExtractor", "Extractor", "TimeInverseBlockMasker",
+__all__ = ["JEPA", "Denoiser", "ConvFeatureExtractor", "ConvChannelFeatureExtractor", "Extractor", "TimeInverseBlockMasker",
            "SpeechMasker", "TransformerLayerCFG", "TransformerEncoderCFG", "ForwardReturn"]

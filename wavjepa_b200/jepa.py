@@ -563,10 +563,21 @@ class JEPA(nn.Module):
         dxc = self._enc_stack.backward(self._W_enc, G_enc, c.enc_saved, dxs, mi.cu_c, B, mi.max_nc,
                                        lambda i: ready(f"encoder.layers.{i}.self_attn.in_proj_weight"))
         # ---- scatter to the dense token grid: the mapper output is bf16 (autocast), so is its gradient
-        conv_saved, f2, ln16, st = c.local_saved
-        C = f2.shape[1]
         dlocal16 = torch.zeros(B * T, D, device=dev, dtype=bf)
         ops.scatter_dgelu(dxc, mi.ctx_rows, None, Nc, dlocal16)
+        self._local_backward(c.local_saved, dlocal16, B, g, ready)
+        if on_ready is not None:
+            on_ready(0)
+
+    def _local_backward(self, local_saved, dlocal16: torch.Tensor, B: int, g, ready) -> None:
+        """Backward of `_local_features` from the (bf16) gradient of the mapper output on the dense token grid:
+        post_extraction_mapper -> feature_norms -> conv stack(s)."""
+        T, D = self.total_patches, self.encoder_embedding_dim
+        dev = dlocal16.device
+        p32 = lambda n: self._view(self._flat_p, n)
+        p16 = lambda n: self._view(self._flat_w16, n)
+        conv_saved, f2, ln16, st = local_saved
+        C = f2.shape[1]
         ops.colsum(dlocal16, g("post_extraction_mapper.bias"))
         ops.gemm_wgrad(ops.plain_operand(dlocal16), ops.plain_operand(ln16), B * T, 1,
                        g("post_extraction_mapper.weight"), accumulate=True)
@@ -590,8 +601,6 @@ class JEPA(nn.Module):
                 self._conv_backward(prefix, ex.conv_layers_spec, sv, dfc, B, Tc, C, g, ready)
         else:
             self._conv_backward(exs[0][0], ex.conv_layers_spec, conv_saved[0], dfeat, B, T, C, g, ready)
-        if on_ready is not None:
-            on_ready(0)
 
     def _conv_backward(self, prefix, spec, sv, dfeat, B, T, C, g, ready):
         n = len(spec)
@@ -721,19 +730,23 @@ class JEPA(nn.Module):
         e0, e1 = self._enc_range
         ops.ema_update(self._flat_t, self._flat_p[e0:e1], r)
         ops.cast_bf16(self._flat_t, self._flat_t16)
-        # clip + AdamW (LambdaLR: the lr of optimizer step k is lr_at(k), k = global_step)
+        self._optimizer_tail(gflat, world, self.lr_at(self.global_step))
+        return c.loss
+
+    def _optimizer_tail(self, gflat: torch.Tensor, world: int, lr: float) -> None:
+        """Global-norm clip + AdamW over the flat buffers (+ bf16 working-weight refresh); the lr of optimizer step
+        k is the scheduler's value at k = global_step (LambdaLR)."""
         if self._adam_m is None:
             self._adam_m = torch.zeros_like(self._flat_p)
             self._adam_v = torch.zeros_like(self._flat_p)
         ss = torch.zeros(1, device=gflat.device, dtype=torch.float64)
         ops.sumsq(gflat, 1.0 / world, ss)
         b1, b2 = self.hparams.adam_betas
-        ops.adamw_step(self._flat_p, gflat, self._adam_m, self._adam_v, self.lr_at(self.global_step), b1, b2,
+        ops.adamw_step(self._flat_p, gflat, self._adam_m, self._adam_v, lr, b1, b2,
                        self.hparams.adam_eps, self.hparams.adam_weight_decay, self.global_step + 1, 1.0 / world,
                        self.grad_clip, ss, self._flat_w16)
         self._refresh_conv_weights()
         self.global_step += 1
-        return c.loss
 
     # ------------------------------------------------------------------------------------------- inference
     @torch.no_grad()

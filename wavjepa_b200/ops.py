@@ -457,3 +457,27 @@ def rms_gain_rows(clips: torch.Tensor, sumsq: torch.Tensor, counts: torch.Tensor
     p = lambda t: C.c_void_p(_ptr(t))
     check(lib.wj_rms_gain_rows(p(clips), p(sumsq), p(counts), clips.shape[0], C.c_int64(clips.shape[1]),
                                C.c_float(target_dbfs), _stream()))
+
+
+# ----------------------------------------------------------------------------------------------------- denoiser stage
+def mse_pair(pred: torch.Tensor, target: torch.Tensor, alpha: float, sums_f64: torch.Tensor, dpred=None):
+    """pred fp32 [2, M] (clean half, generated half), target fp32 [M]; sums_f64 [2] += squared-error sums."""
+    assert pred.dtype == torch.float32 and target.dtype == torch.float32 and sums_f64.dtype == torch.float64
+    M = target.numel()
+    assert pred.numel() == 2 * M and pred.is_contiguous() and target.is_contiguous()
+    lib = _lib.load()
+    p = lambda t: C.c_void_p(_ptr(t))
+    check(lib.wj_mse_pair(p(pred), p(target), C.c_int64(M), C.c_float(alpha), p(sums_f64), p(dpred), _stream()))
+
+
+def snr_mix(source: torch.Tensor, noise: torch.Tensor, start: torch.Tensor, length: torch.Tensor, snr: torch.Tensor,
+            out: torch.Tensor):
+    """source, noise, out fp32 [B, T]; start, length int32 [B]; snr fp32 [B]."""
+    B, T = source.shape
+    assert source.dtype == torch.float32 and noise.shape == source.shape and source.is_contiguous() and noise.is_contiguous()
+    assert start.dtype == torch.int32 and length.dtype == torch.int32 and snr.dtype == torch.float32
+    energy = torch.empty(B, 2, device=source.device, dtype=torch.float64)
+    lib = _lib.load()
+    p = lambda t: C.c_void_p(_ptr(t))
+    check(lib.wj_snr_mix(p(source), p(noise), p(start), p(length), p(snr), B, C.c_int64(T), p(energy), p(out), _stream()))
+    return energy
