@@ -111,13 +111,18 @@ def test_conv_implicit_gemm(Bn, L_in, k):
     assert rel(out, ref) < BF16_TOL
 
 
-@pytest.mark.parametrize("M,Nw,Kw,splits", [(1000, 256, 384, 0), (64, 128, 128, 1), (50000, 768, 3072, 0), (333, 1152, 384, 0)])
+@pytest.mark.parametrize("M,Nw,Kw,splits", [(1000, 256, 384, 0), (64, 128, 128, 1), (50000, 768, 3072, 0), (333, 1152, 384, 0),
+                                              (20000, 1536, 384, 0), (700, 512, 128, 3)])
 def test_wgrad(M, Nw, Kw, splits):
     dy = torch.randn(M, Nw, device=DEV).bfloat16()
     x = torch.randn(M, Kw, device=DEV).bfloat16()
     out = torch.full((Nw, Kw), float("nan"), device=DEV)
     ops.gemm_wgrad(ops.plain_operand(dy), ops.plain_operand(x), M, 1, out, splits=splits)
-    assert rel(out, dy.float().t() @ x.float()) < 5e-5
+    ref = dy.float().t() @ x.float()
+    assert rel(out, ref) < 5e-5
+    # accumulate semantics (out += ...), incl. the swapped-operand path taken when only the row count allows 256-wide tiles
+    ops.gemm_wgrad(ops.plain_operand(dy), ops.plain_operand(x), M, 1, out, splits=splits, accumulate=True)
+    assert rel(out, 2 * ref) < 5e-5
 
 
 @pytest.mark.parametrize("L_in,k", [(402, 3), (400, 2)])

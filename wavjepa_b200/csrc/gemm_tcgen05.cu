@@ -65,6 +65,7 @@ struct GemmParams {
   const int* out_rows;  // optional row indirection for the output / residual / aux rows (scatter), -1 = skip
   float* colsum;        // optional: colsum[n] += sum over rows of the stored output (bias gradients)
   int tma_store;        // bf16 outputs without residual / aux / scatter: staged in smem and written by TMA stores
+  int transpose_out;    // wgrad: the tile holds out^T (operands swapped so that the wide dimension is BN = 256)
 };
 
 struct OutMaps {
@@ -252,7 +253,12 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t t_ba
           }
         }
       }
-      if (p.out_f32) {
+      if (WGRAD && p.transpose_out) {
+        // element (orow, n0 + c) of the computed tile is out[n0 + c][orow]: 8 lanes (g) cover 8 consecutive floats
+        float* op = reinterpret_cast<float*>(p.out) + static_cast<long long>(n0) * p.ld_out + orow;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) atomicAdd(op + c * p.ld_out, x[c]);
+      } else if (p.out_f32) {
         float* op = reinterpret_cast<float*>(p.out) + orow * p.ld_out + n0;
         if (p.accumulate) {
           red_add_v4(op, x[0], x[1], x[2], x[3]);
@@ -1071,7 +1077,17 @@ extern "C" int wj_gemm_wgrad_bf16(const wj_operand_t* dY, const wj_operand_t* X,
                                   float* out, int64_t ld_out, int accumulate, int splits, void* stream) {
   if (L <= 0 || batch <= 0) return WJ_OK;
   if (M % BM != 0 || N % 64 != 0) { set_error("wj_gemm_wgrad_bf16: M must be a multiple of 128 and N of 64 (M=%d N=%d)", M, N); return WJ_ERR_ARG; }
-  const int block_n = (N % 256 == 0) ? 256 : ((N % 128 == 0) ? 128 : 0);
+  bool transposed = false;
+  // A 128-column B tile makes the main loop shared-memory-bandwidth bound (two 16 KB operand tiles per 128x128x64
+  // block of MMAs); when the OTHER dimension allows 256-wide tiles, compute out^T = X^T dY instead and let the
+  // (once-per-CTA) epilogue scatter the transposed tile.
+  // (A partial last 256-column tile is fine: TMA zero-fills the missing column atoms, the epilogue masks them.)
+  if (N % 256 != 0 && N % 128 == 0 && M > N && dY->seg_width == 0 && X->seg_width == 0) {
+    const wj_operand_t* t = dY; dY = X; X = t;
+    const int tm = M; M = N; N = tm;
+    transposed = true;
+  }
+  const int block_n = (N % 256 == 0 || (transposed && N > 512)) ? 256 : ((N % 128 == 0) ? 128 : 0);
   if (block_n == 0) { set_error("wj_gemm_wgrad_bf16: N must be a multiple of 128"); return WJ_ERR_ARG; }
   if (X->seg_width > 0 && X->seg_width % 64 != 0) { set_error("wj_gemm_wgrad_bf16: bad segment width"); return WJ_ERR_ARG; }
   CUtensorMap tmA, tmB, tmB1;
@@ -1085,7 +1101,7 @@ extern "C" int wj_gemm_wgrad_bf16(const wj_operand_t* dY, const wj_operand_t* X,
   memset(&p, 0, sizeof(p));
   p.L = L; p.batch = batch; p.N = N; p.M = M;
   p.m_blocks = M / BM;
-  p.n_blocks = N / block_n;
+  p.n_blocks = (N + block_n - 1) / block_n;
   p.kb_per_batch = (L + BK - 1) / BK;
   const int kb_total = batch * p.kb_per_batch;
   if (splits <= 0) {
@@ -1112,11 +1128,13 @@ extern "C" int wj_gemm_wgrad_bf16(const wj_operand_t* dY, const wj_operand_t* X,
   fill_seg(p.seg, X);
   p.b_single = (X->seg_width == 0 || X->seg_width % block_n == 0) ? 1 : 0;
   p.out = out; p.ld_out = ld_out; p.out_f32 = 1;
-  p.accumulate = (accumulate || splits > 1) ? 1 : 0;
-  if (splits > 1 && !accumulate) {
+  p.accumulate = (accumulate || splits > 1 || transposed) ? 1 : 0;
+  p.transpose_out = transposed ? 1 : 0;
+  if ((splits > 1 || transposed) && !accumulate) {
     // caller asked for overwrite semantics but we reduce with atomics: clear the destination first
-    cudaError_t e = cudaMemset2DAsync(out, ld_out * sizeof(float), 0, (size_t)N * sizeof(float), (size_t)M,
-                                      reinterpret_cast<cudaStream_t>(stream));
+    // (rows x columns of the caller's matrix: M x N, or N x M when the operands were swapped)
+    cudaError_t e = cudaMemset2DAsync(out, ld_out * sizeof(float), 0, (size_t)(transposed ? M : N) * sizeof(float),
+                                      (size_t)(transposed ? N : M), reinterpret_cast<cudaStream_t>(stream));
     if (e != cudaSuccess) { set_error("memset2d: %s", cudaGetErrorString(e)); return WJ_ERR_RUNTIME; }
   }
   const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
