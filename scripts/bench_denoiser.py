@@ -13,16 +13,19 @@ import torch  # noqa: E402
 import wavjepa_b200 as w  # noqa: E402
 from wavjepa_b200 import _lib  # noqa: E402
 from wavjepa_b200.denoiser import Denoiser  # noqa: E402
-from oracle import jepa_oracle as jo  # noqa: E402  (deterministic random-init weights only)
 
 dev = "cuda"
-cfg = jo.Cfg()
-ext = w.ConvFeatureExtractor(conv_layers_spec=cfg.spec, in_channels=1)
+SPEC = [(512, 10, 5)] + [(512, 3, 2)] * 4 + [(512, 2, 2)]
+torch.manual_seed(0)
+ext = w.ConvFeatureExtractor(conv_layers_spec=SPEC, in_channels=1)
 m = Denoiser(feature_extractor=ext, transformer_encoder_layers_cfg=w.TransformerLayerCFG.create(),
              transformer_encoder_cfg=w.TransformerEncoderCFG.create(), nr_samples_per_audio=16, alpha=0.25)
-sd = jo.make_state_dict(cfg, seed=11)
-m.load_state_dict({k: v for k, v in sd.items() if k in m.state_dict()}, strict=True)
-m._set_teacher({"state_dict": jo.make_state_dict(cfg, seed=12)})
+teacher = w.JEPA(feature_extractor=w.ConvFeatureExtractor(conv_layers_spec=SPEC, in_channels=1),
+                 transformer_encoder_cfg=w.TransformerEncoderCFG.create(),
+                 transformer_encoder_layers_cfg=w.TransformerLayerCFG.create(),
+                 transformer_decoder_cfg=w.TransformerEncoderCFG.create(),
+                 transformer_decoder_layers_cfg=w.TransformerLayerCFG.create(d_model=384))
+m._set_teacher({"state_dict": teacher.state_dict()})     # random-init weights (there is no network for checkpoints)
 m.to(dev)
 m.global_step = 5000
 

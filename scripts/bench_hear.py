@@ -65,8 +65,13 @@ if "--nat" in sys.argv:
                       "reserved_GiB": round(torch.cuda.memory_reserved() / 2**30, 1), "loss": step().item()}))
 else:
     torch.manual_seed(0)
-    from oracle import jepa_oracle as jo   # only for a deterministic random state_dict (test infrastructure)
-    model = hear.load_model({"state_dict": jo.make_state_dict(jo.Cfg(), seed=3)})
+    import wavjepa_b200 as w
+    init = w.JEPA(feature_extractor=w.ConvFeatureExtractor(conv_layers_spec=hear.BASE_SPEC, in_channels=1),
+                  transformer_encoder_cfg=w.TransformerEncoderCFG.create(),
+                  transformer_encoder_layers_cfg=w.TransformerLayerCFG.create(),
+                  transformer_decoder_cfg=w.TransformerEncoderCFG.create(),
+                  transformer_decoder_layers_cfg=w.TransformerLayerCFG.create(d_model=384))
+    model = hear.load_model({"state_dict": init.state_dict()})     # random-init weights (no network for checkpoints)
     n, L = 256, 160000
     audio = (torch.rand(n, L, device=dev) * 2 - 1)
     k0 = _lib.kernel_launches()
