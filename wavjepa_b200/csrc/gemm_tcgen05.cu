@@ -398,6 +398,88 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const Out
   }
 }
 
+// Backward of GELU on the TMA-store path (dgrad only): out (bf16) = acc * saved GELU'(h), optional fused column sums
+// (the bias gradient of the Linear whose output was h).  Row per lane: the lane reads its own 64 bytes of the saved
+// factor per 32-column chunk (issued before the TMEM wait), multiplies, packs, stages and TMA-stores like the plain
+// path; the column sums of the stored bf16 values are a 5-step reduce-scatter across the warp (lane l ends with column
+// l) and one atomic per lane.  ~5x fewer issued instructions per element than the generic epilogue.
+template <int BN, typename Arrive>
+__device__ __forceinline__ void epilogue_tile_tma_aux(const GemmParams& p, const OutMaps& om, uint32_t t_base, uint8_t* stg,
+                                                      int lane, int lane_grp, int col_q, int n_blk, int b,
+                                                      int row_in_batch0, Arrive arrive) {
+  constexpr int CHUNKS = BN / 32 / 4;
+  const int row0 = row_in_batch0 + lane_grp * 32;
+  const bool row_ok = row0 + lane < p.L;
+  const bf16* arow = p.aux + (static_cast<long long>(b) * p.L + row0 + lane) * p.ld_aux;
+  uint8_t* srow = stg + lane * 64;
+  const int sw = (lane >> 1) & 3;
+  uint32_t v[32];
+  tmem_ld_32x32(t_base, v);
+#pragma unroll 1
+  for (int ch = 0; ch < CHUNKS; ++ch) {
+    const int n0 = n_blk * BN + (col_q * CHUNKS + ch) * 32;
+    const bool live = n0 < p.N && row0 < p.L;   // warp-uniform
+    uint4 a[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      a[c] = make_uint4(0u, 0u, 0u, 0u);        // rows >= L / columns >= N contribute zeros (N is a multiple of 8)
+      if (live && row_ok && n0 + 8 * c < p.N) a[c] = *reinterpret_cast<const uint4*>(arow + n0 + 8 * c);
+    }
+    tmem_ld_wait();
+    float f[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+    if (ch + 1 < CHUNKS) {
+      tmem_ld_32x32(t_base + (ch + 1) * 32, v);
+    } else {
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) arrive();
+    }
+    if (!live) continue;
+    uint32_t w[16];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const uint32_t aw[4] = {a[c].x, a[c].y, a[c].z, a[c].w};
+#pragma unroll
+      for (int t = 0; t < 4; ++t)
+        w[4 * c + t] = pack_bf16x2(f[8 * c + 2 * t] * __uint_as_float(aw[t] << 16),
+                                   f[8 * c + 2 * t + 1] * __uint_as_float(aw[t] & 0xffff0000u));
+    }
+    if (lane == 0) bulk_wait_read0();   // the previous TMA store of this warp has finished reading the staging tile
+    __syncwarp();
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+      *reinterpret_cast<uint4*>(srow + ((c ^ sw) << 4)) = make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      tma_store_3d(&om.o, stg, n0, row0, b);
+      bulk_commit();
+    }
+    if (p.colsum != nullptr) {
+      // sums of the values as stored (bf16), like autograd's bias gradient: reduce-scatter over the 32 rows of the warp
+      float c32[32];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        c32[2 * j] = __uint_as_float(w[j] << 16);
+        c32[2 * j + 1] = __uint_as_float(w[j] & 0xffff0000u);
+      }
+#pragma unroll
+      for (int s = 16; s >= 1; s >>= 1) {
+        const bool up = (lane & s) != 0;
+#pragma unroll
+        for (int i = 0; i < s; ++i) {
+          const float mine = up ? c32[s + i] : c32[i];
+          const float other = up ? c32[i] : c32[s + i];
+          c32[i] = mine + __shfl_xor_sync(0xffffffffu, other, s);
+        }
+      }
+      if (n0 + lane < p.N) atomicAdd(p.colsum + n0 + lane, c32[0]);
+    }
+  }
+}
+
 // MODE 0: A K-major, B K-major (fwd)   MODE 1: A, B MN-major (wgrad)   MODE 2: A K-major, B MN-major (dgrad)
 template <int BN, int MODE, bool HEAVY>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -601,8 +683,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const uint32_t t_base = tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16) + acc * BN + col_q * (CHUNKS * 32);
       if constexpr (!WGRAD) {
         if (p.tma_store) {
-          epilogue_tile_tma<BN, HEAVY>(p, om, t_base, smem + C::STAGING_OFF + ew * 2048, lane, lane_grp, col_q, n_blk, b,
-                                row_in_batch0, [&]() { mbar_arrive(&tempty_bar[acc]); });
+          if constexpr (MODE == 2 && HEAVY) {   // (for dgrad the second instantiation is the GELU-backward path)
+            epilogue_tile_tma_aux<BN>(p, om, t_base, smem + C::STAGING_OFF + ew * 2048, lane, lane_grp, col_q, n_blk, b,
+                                      row_in_batch0, [&]() { mbar_arrive(&tempty_bar[acc]); });
+          } else {
+            epilogue_tile_tma<BN, HEAVY>(p, om, t_base, smem + C::STAGING_OFF + ew * 2048, lane, lane_grp, col_q, n_blk, b,
+                                         row_in_batch0, [&]() { mbar_arrive(&tempty_bar[acc]); });
+          }
           continue;
         }
       }
@@ -952,11 +1039,15 @@ static int encode_out_map(CUtensorMap* tm, const void* ptr, int N, int L, int ba
 }
 
 // Decides whether the epilogue can take the TMA-store path and builds its maps.
-static int setup_out_maps(GemmParams& p, OutMaps& om, int N, int L, int batch) {
+static int setup_out_maps(GemmParams& p, OutMaps& om, int N, int L, int batch, bool dgrad = false) {
   memset(&om, 0, sizeof(om));
   p.tma_store = 0;
-  const bool ok = !p.out_f32 && !p.accumulate && p.resid == nullptr && p.out_rows == nullptr && p.colsum == nullptr &&
-                  (p.act == 0 || p.act == 1) && (p.ld_out % 8 == 0) && (reinterpret_cast<uintptr_t>(p.out) % 16 == 0) &&
+  // dgrad also takes the GELU-backward form: out = acc * aux (+ fused column sums), no bias
+  const bool gelu_bwd = dgrad && p.act == 2 && p.aux != nullptr && p.bias == nullptr && p.out2 == nullptr &&
+                        p.ld_aux % 8 == 0 && reinterpret_cast<uintptr_t>(p.aux) % 16 == 0 && N % 8 == 0;
+  const bool ok = !p.out_f32 && !p.accumulate && p.resid == nullptr && p.out_rows == nullptr &&
+                  (gelu_bwd || (p.colsum == nullptr && (p.act == 0 || p.act == 1))) && (p.ld_out % 8 == 0) &&
+                  (reinterpret_cast<uintptr_t>(p.out) % 16 == 0) &&
                   (p.out2 == nullptr || (p.ld_out2 % 8 == 0 && reinterpret_cast<uintptr_t>(p.out2) % 16 == 0));
   if (!ok) return WJ_OK;
   int rc = encode_out_map(&om.o, p.out, N, L, batch, p.ld_out);
@@ -1006,6 +1097,9 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensor
   if constexpr (MODE != 1) {
     // the two-output epilogue (GELU + saved GELU') has its own instantiation of the TMA-store path (register budget)
     if (p.tma_store && p.out2 != nullptr) return launch_variant<BN, MODE, true>(tmA, tmB, tmB1, om, p, grid, st);
+  }
+  if constexpr (MODE == 2) {
+    if (p.tma_store && p.act == 2) return launch_variant<BN, MODE, true>(tmA, tmB, tmB1, om, p, grid, st);
   }
   return launch_variant<BN, MODE, false>(tmA, tmB, tmB1, om, p, grid, st);
 }
@@ -1174,7 +1268,7 @@ extern "C" int wj_gemm_dgrad_bf16(const wj_operand_t* A, const void* W, int64_t 
   const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   OutMaps om;
-  rc = setup_out_maps(p, om, N, L, batch);
+  rc = setup_out_maps(p, om, N, L, batch, /*dgrad=*/true);
   if (rc) return rc;
   if (block_n == 256) return launch<256, 2>(tmA, tmB, tmB, om, p, grid, st);
   return launch<128, 2>(tmA, tmB, tmB, om, p, grid, st);
