@@ -10,6 +10,7 @@ import torch.nn.functional as F
 pytestmark = pytest.mark.gpu
 
 from wavjepa_b200 import _lib, ops  # noqa: E402
+from oracle import jepa_oracle as jo  # noqa: E402  (the checker)
 
 DEV = "cuda"
 BF16_TOL = 4e-3   # rel-L2 of a bf16-rounded result against fp32 (bf16 eps = 3.9e-3, rel-L2 of rounding ~1.7e-3)
@@ -511,3 +512,36 @@ def test_gemm_pair_epilogues_and_conv():
     ops.gemm(ops.conv_operand(x, 3), wk, L_out, B, y.view(-1, C), block_n=-256)
     ref = F.conv1d(x.float().transpose(1, 2), wk.float().view(C, 3, C).permute(0, 2, 1), stride=2).transpose(1, 2)
     assert rel(y, ref) < BF16_TOL
+
+
+# ------------------------------------------------------------------------------------------------------- denoiser stage
+@pytest.mark.parametrize("M,alpha", [(4 * 200 * 768, 0.25), (1000, 0.0), (4096 * 33, 1.0)])
+def test_mse_pair(M, alpha):
+    pred = torch.randn(2, M, device=DEV)
+    tgt = torch.randn(M, device=DEV)
+    sums = torch.zeros(2, device=DEV, dtype=torch.float64)
+    dp = torch.full((2, M), float("nan"), device=DEV)
+    ops.mse_pair(pred, tgt, alpha, sums, dp)
+    ref = ((pred.double() - tgt.double()) ** 2).sum(dim=1)
+    assert torch.allclose(sums, ref, rtol=1e-6)
+    p2 = pred.clone().requires_grad_(True)
+    loss = alpha * F.mse_loss(p2[0], tgt) + (1 - alpha) * F.mse_loss(p2[1], tgt)
+    loss.backward()
+    assert rel(dp, p2.grad) < 1e-6
+    ops.mse_pair(pred, tgt, alpha, sums, None)          # forward only: accumulates, no gradient buffer
+    assert torch.allclose(sums, 2 * ref, rtol=1e-6)
+
+
+def test_snr_mix_matches_reference_formula():
+    B, T = 5, 70001
+    g = torch.Generator().manual_seed(4)
+    src = torch.randn(B, T, generator=g)
+    noise = torch.randn(B, T, generator=g) * 0.2
+    start = torch.tensor([0, 1000, 69000, 35000, 123])       # a window that runs past the end, an empty window
+    length = torch.tensor([T, 20000, 5000, 0, 1])
+    snr = torch.tensor([0.0, 10.0, -5.0, 20.0, 3.0])
+    ref = jo.scene_add_noise(src[:, None], noise[:, None], snr, start, length)[:, 0]
+    out = torch.full((B, T), float("nan"), device=DEV)
+    ops.snr_mix(src.to(DEV), noise.to(DEV), start.int().to(DEV), length.int().to(DEV), snr.to(DEV), out)
+    assert rel(out.cpu(), ref) < 1e-6
+    assert torch.equal(out[3].cpu(), src[3])                 # empty window: a = 0, the source passes through
