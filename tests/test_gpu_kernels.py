@@ -39,13 +39,19 @@ def test_gemm_plain(M, N, K, bn):
     assert rel(out, a.float() @ w.float().t()) < BF16_TOL
 
 
-def test_gemm_f32_out():
-    M, N, K = 5000, 768, 3072
+@pytest.mark.parametrize("M,N,K", [(5000, 768, 3072), (5000, 384, 1536), (777, 384, 384), (300, 576, 128)])
+def test_gemm_f32_out(M, N, K):
+    """fp32 outputs; N = 384 / 576 take the 192-column tiles."""
     a = torch.randn(M, K, device=DEV).bfloat16()
     w = (torch.randn(N, K, device=DEV) * 0.05).bfloat16()
     out = torch.empty(M, N, device=DEV)
     ops.gemm(ops.plain_operand(a), w, M, 1, out)
-    assert rel(out, a.float() @ w.float().t()) < 2e-5
+    base = a.float() @ w.float().t()
+    assert rel(out, base) < 2e-5
+    bias, res = torch.randn(N, device=DEV), torch.randn(M, N, device=DEV)
+    ops.gemm(ops.plain_operand(a), w, M, 1, out, bias=bias, resid=res, act=ops.ACT_BF16)
+    # (a few accumulators sit on a bf16 rounding boundary and land one ulp away from torch's: 1e-4 .. 2e-4 at K = 3072)
+    assert rel(out, (base + bias).bfloat16().float() + res) < 3e-4
 
 
 def test_gemm_epilogues():

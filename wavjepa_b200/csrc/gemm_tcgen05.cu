@@ -86,7 +86,7 @@ struct Cfg {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN == 256) ? 4 : ((BN == 128) ? 6 : 8);
+  static constexpr int STAGES = (BN == 256) ? 4 : ((BN == 192) ? 4 : ((BN == 128) ? 6 : 8));
   static constexpr int STAGING_OFF = STAGES * STAGE_BYTES + 1024;   // barriers live in the 1 KB before it
   static constexpr int SMEM_BYTES = STAGING_OFF + 1024 /*align slack*/ + kEpiWarps * 2048 /*TMA-store staging*/;
 };
@@ -116,15 +116,17 @@ template <int BN, bool WGRAD, typename Arrive>
 __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t t_base, int lane, int lane_grp, int col_q,
                                               int n_blk, int b, int row_in_batch0, long long wgrad_row0, bool have_k,
                                               Arrive arrive) {
-  constexpr int CHUNKS = BN / 32 / 4;       // 32-column chunks per warp
-  constexpr int UNITS = CHUNKS * 2;
+  // work units of 16 TMEM lanes x 32 columns: 2 * BN / 32 per lane group, BN / 64 consecutive ones per warp (the four
+  // warps of a lane group split them by col_q); t_base addresses column 0 of the accumulator for this lane group
+  constexpr int UNITS = BN / 64;
   const int g = lane >> 2, tg = lane & 3;
   uint32_t v[16];
-  tmem_ld_16x256b_x4(t_base, v);
+  tmem_ld_16x256b_x4(t_base + (static_cast<uint32_t>(((col_q * UNITS) & 1) * 16) << 16) + ((col_q * UNITS) >> 1) * 32, v);
 #pragma unroll 1
   for (int u = 0; u < UNITS; ++u) {
-    const int ch = u >> 1, half = u & 1;
-    const int n0 = n_blk * BN + (col_q * CHUNKS + ch) * 32 + tg * 8;
+    const int ug = col_q * UNITS + u;
+    const int ch = ug >> 1, half = ug & 1;
+    const int n0 = n_blk * BN + ch * 32 + tg * 8;
     const bool col_ok = n0 < p.N;   // N is a multiple of 8: groups of 8 columns are all-or-nothing
     // physical output rows of tile rows (lane_grp*32 + 16*half + 8*hr + g); -1 = nothing to write
     long long orow2[2];
@@ -180,7 +182,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t t_ba
       for (int c = 0; c < 8; ++c) f[hr][c] = __uint_as_float(a[c]);
     }
     if (u + 1 < UNITS) {
-      const int nu = u + 1;
+      const int nu = ug + 1;
       tmem_ld_16x256b_x4(t_base + (static_cast<uint32_t>((nu & 1) * 16) << 16) + (nu >> 1) * 32, v);
     } else {
       // every lane has executed tcgen05.wait::ld for its last unit -> hand the accumulator back to the MMA warp
@@ -680,7 +682,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      const uint32_t t_base = tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16) + acc * BN + col_q * (CHUNKS * 32);
+      const uint32_t t_acc = tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16) + acc * BN;
+      const uint32_t t_base = t_acc + col_q * (CHUNKS * 32);   // (TMA-store paths: CHUNKS consecutive chunks per warp)
       if constexpr (!WGRAD) {
         if (p.tma_store) {
           if constexpr (MODE == 2 && HEAVY) {   // (for dgrad the second instantiation is the GELU-backward path)
@@ -693,7 +696,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           continue;
         }
       }
-      epilogue_tile<BN, WGRAD>(p, t_base, lane, lane_grp, col_q, n_blk, b, row_in_batch0,
+      epilogue_tile<BN, WGRAD>(p, t_acc, lane, lane_grp, col_q, n_blk, b, row_in_batch0,
                                static_cast<long long>(m_blk) * BM, have_k, [&]() { mbar_arrive(&tempty_bar[acc]); });
     }
     if (p.tma_store && lane == 0) bulk_wait0();   // all TMA stores of this warp are complete before smem goes away
@@ -910,7 +913,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      const uint32_t t_base = tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16) + acc * BN + col_q * (CHUNKS * 32);
+      const uint32_t t_base = tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16) + acc * BN;
       const uint32_t te = mapa_shared(smem_u32(&tempty_bar[acc]), 0);
       epilogue_tile<BN, WGRAD>(p, t_base, lane, lane_grp, col_q, n_blk, b, row_in_batch0,
                                static_cast<long long>(m_blk) * BMP + static_cast<long long>(rank) * BM, have_k,
@@ -1094,12 +1097,19 @@ static int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
 template <int BN, int MODE>
 static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmB1, const OutMaps& om,
                   const GemmParams& p, int grid, cudaStream_t st) {
-  if constexpr (MODE != 1) {
-    // the two-output epilogue (GELU + saved GELU') has its own instantiation of the TMA-store path (register budget)
-    if (p.tma_store && p.out2 != nullptr) return launch_variant<BN, MODE, true>(tmA, tmB, tmB1, om, p, grid, st);
-  }
-  if constexpr (MODE == 2) {
-    if (p.tma_store && p.act == 2) return launch_variant<BN, MODE, true>(tmA, tmB, tmB1, om, p, grid, st);
+  if constexpr (BN == 192) {
+    // 192-column tiles serve fp32-output GEMMs with N = 384 only (generic epilogue; the TMA-store paths split the
+    // tile into 4 x 32k columns per lane group, which 192 is not)
+    if (p.tma_store) { set_error("gemm: BN = 192 has no TMA-store epilogue"); return WJ_ERR_ARG; }
+    return launch_variant<BN, MODE, false>(tmA, tmB, tmB1, om, p, grid, st);
+  } else {
+    if constexpr (MODE != 1) {
+      // the two-output epilogue (GELU + saved GELU') has its own instantiation of the TMA-store path (register budget)
+      if (p.tma_store && p.out2 != nullptr) return launch_variant<BN, MODE, true>(tmA, tmB, tmB1, om, p, grid, st);
+    }
+    if constexpr (MODE == 2) {
+      if (p.tma_store && p.act == 2) return launch_variant<BN, MODE, true>(tmA, tmB, tmB1, om, p, grid, st);
+    }
   }
   return launch_variant<BN, MODE, false>(tmA, tmB, tmB1, om, p, grid, st);
 }
@@ -1129,8 +1139,10 @@ extern "C" int wj_gemm_bf16(const wj_operand_t* A, const void* W, int64_t ldw, i
   if (A->seg_width > 0 && (A->seg_width % BK != 0 || K > 4 * A->seg_width)) { set_error("wj_gemm_bf16: bad segment width"); return WJ_ERR_ARG; }
   const bool pair = block_n < 0;   // -128 / -256: CTA-pair kernel (256-row tiles, tcgen05 cta_group::2)
   if (pair) block_n = -block_n;
-  if (block_n == 0) block_n = (N % 256 == 0 || N > 1024) ? 256 : 128;
-  if (block_n != 128 && block_n != 256) { set_error("wj_gemm_bf16: block_n must be 128 or 256"); return WJ_ERR_ARG; }
+  // N = 384-like fp32-output GEMMs: 192-column tiles (a 128-column B tile leaves the main loop smem-bandwidth bound)
+  const bool want192 = !pair && N % 192 == 0 && N % 256 != 0 && N <= 768 && epi != nullptr && epi->out_f32;
+  if (block_n == 0) block_n = want192 ? 192 : ((N % 256 == 0 || N > 1024) ? 256 : 128);
+  if (block_n != 128 && block_n != 256 && !(block_n == 192 && want192)) { set_error("wj_gemm_bf16: block_n must be 128 or 256 (192: fp32 outputs with N %% 192 == 0)"); return WJ_ERR_ARG; }
   CUtensorMap tmA, tmB;
   const uint32_t boxA[4] = {BK, 1, BM, 1};
   int rc = encode_map(&tmA, A, boxA);
@@ -1163,6 +1175,7 @@ extern "C" int wj_gemm_bf16(const wj_operand_t* A, const void* W, int64_t ldw, i
   rc = setup_out_maps(p, om, N, L, batch);
   if (rc) return rc;
   if (block_n == 256) return launch<256, 0>(tmA, tmB, tmB, om, p, grid, st);
+  if (block_n == 192) return launch<192, 0>(tmA, tmB, tmB, om, p, grid, st);
   return launch<128, 0>(tmA, tmB, tmB, om, p, grid, st);
 }
 
@@ -1247,8 +1260,9 @@ extern "C" int wj_gemm_dgrad_bf16(const wj_operand_t* A, const void* W, int64_t 
   if (L <= 0 || batch <= 0) return WJ_OK;
   if (K % BK != 0 || N % 64 != 0) { set_error("wj_gemm_dgrad_bf16: K must be a multiple of 64 and N of 64 (K=%d N=%d)", K, N); return WJ_ERR_ARG; }
   if (A->seg_width > 0 && (A->seg_width % BK != 0 || K > 4 * A->seg_width)) { set_error("wj_gemm_dgrad_bf16: bad segment width"); return WJ_ERR_ARG; }
-  if (block_n == 0) block_n = (N % 256 == 0 || N > 1024) ? 256 : 128;
-  if (block_n != 128 && block_n != 256) { set_error("wj_gemm_dgrad_bf16: block_n must be 128 or 256"); return WJ_ERR_ARG; }
+  const bool want192 = N % 192 == 0 && N % 256 != 0 && N <= 768 && epi != nullptr && epi->out_f32;
+  if (block_n == 0) block_n = want192 ? 192 : ((N % 256 == 0 || N > 1024) ? 256 : 128);
+  if (block_n != 128 && block_n != 256 && !(block_n == 192 && want192)) { set_error("wj_gemm_dgrad_bf16: block_n must be 128 or 256 (192: fp32 outputs with N %% 192 == 0)"); return WJ_ERR_ARG; }
   CUtensorMap tmA, tmB;
   const uint32_t boxA[4] = {BK, 1, BM, 1};
   int rc = encode_map(&tmA, A, boxA);
@@ -1270,6 +1284,7 @@ extern "C" int wj_gemm_dgrad_bf16(const wj_operand_t* A, const void* W, int64_t 
   OutMaps om;
   rc = setup_out_maps(p, om, N, L, batch, /*dgrad=*/true);
   if (rc) return rc;
+  if (block_n == 192) return launch<192, 2>(tmA, tmB, tmB, om, p, grid, st);
   if (block_n == 256) return launch<256, 2>(tmA, tmB, tmB, om, p, grid, st);
   return launch<128, 2>(tmA, tmB, tmB, om, p, grid, st);
 }
