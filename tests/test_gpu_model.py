@@ -423,3 +423,30 @@ def test_denoiser_train_step_learns():
     moved = [n for n, p in m.named_parameters() if p.requires_grad and not torch.equal(p.detach(), before[n])]
     assert "encoder.layers.0.linear1.weight" in moved and "extract_audio.cnn.0.0.weight" in moved
     assert torch.equal(m.teacher.encoder.layers[0].linear1.weight, teacher_before)      # frozen
+
+
+def test_generate_scene_cases():
+    """The four branches of generate_scene (generate_scenes_batch.py:148-188) and the 32 -> 16 kHz resampler."""
+    import torchaudio
+    from wavjepa_b200 import denoiser as dn
+    audio, source_rir, noise, noise_len, noise_start, noise_rirs, snr = oi.denoiser_batch(B=3, T32=40000, rir_len=1500, seed=9)
+    dev = lambda t: t.to(DEV)
+    # RIR and noise: pinned by the golden test above; here against the live oracle on a different batch
+    full = dn.generate_scene(dev(source_rir), dev(noise_rirs), dev(audio), dev(noise), dev(noise_len), dev(noise_start), dev(snr))
+    assert rel(full.cpu().numpy(), jo.generate_scene(source_rir, noise_rirs, audio, noise, noise_len, noise_start, snr).numpy()) < 1e-5
+    # RIR only
+    only_rir = dn.generate_scene(dev(source_rir), None, dev(audio), [None], None, None, None)
+    assert tuple(only_rir.shape) == (3, 1, 40000)
+    assert rel(only_rir.cpu().numpy(), jo.scene_convolve_with_rir(audio, source_rir[:, [0]]).numpy()) < 1e-5
+    # noise only (raw source + scaled noise)
+    only_noise = dn.generate_scene([None], None, dev(audio), dev(noise), dev(noise_len), dev(noise_start), dev(snr))
+    ref = jo.scene_add_noise(audio[:, None], noise[:, None], snr, noise_start, noise_len)
+    assert rel(only_noise.cpu().numpy(), ref.numpy()) < 1e-6
+    # neither: the source passes through
+    assert dn.generate_scene([None], None, dev(audio), [None], None, None, None) is not None
+    assert torch.equal(dn.generate_scene([None], None, dev(audio), [None], None, None, None).cpu(), audio)
+    # resample == torchaudio with the reference's arguments (wavjepa/denoiser.py:29-41)
+    r = dn.resample(dev(audio).unsqueeze(1), 16000, 32000)
+    t = torchaudio.functional.resample(audio.unsqueeze(1), 32000, 16000, lowpass_filter_width=64, rolloff=0.9475937167399596,
+                                       resampling_method="sinc_interp_kaiser", beta=14.769656459379492)
+    assert tuple(r.shape) == tuple(t.shape) and rel(r.cpu().numpy(), t.numpy()) < 1e-5
