@@ -156,6 +156,17 @@ int wj_layernorm_fwd(const void* x, int x_is_bf16, const float* gamma, const flo
 int wj_layernorm_bwd(const float* dy, const void* x, int x_is_bf16, const float* stats, const float* gamma, int M,
                      int D, float* dx_f32, void* dx_bf16, float* dgamma, float* dbeta, float* colsum, void* stream);
 
+/* Residual add + LayerNorm in one pass (post-norm layer, wavjepa/types/wavjepa_configs.py:29-47: x = LN(x + Linear(..))):
+ * the row normalised is y = x (fp32 residual stream) + add (bf16 = the Linear output as autocast rounds it; NULL = 0).
+ * The GEMM before it therefore writes 2 bytes per element and y never exists in HBM; outputs as wj_layernorm_fwd. */
+int wj_add_layernorm_fwd(const float* x, const void* add_bf16, const float* gamma, const float* beta, float eps, int M,
+                         int D, float* out_f32, void* out_bf16, float* stats, float* rowsum, void* stream);
+/* Backward of the above.  Gradient w.r.t. the LayerNorm output = dy_f32 (fp32 residual branch, may be NULL) + dy_bf16
+ * (bf16 data gradient of the Linear that consumed the output, may be NULL); y is re-formed as x + add_bf16. */
+int wj_add_layernorm_bwd(const float* dy_f32, const void* dy_bf16, const float* x, const void* add_bf16,
+                         const float* stats, const float* gamma, int M, int D, float* dx_f32, void* dx_bf16,
+                         float* dgamma, float* dbeta, float* colsum, void* stream);
+
 /* out[i] = (g*audio[clip, :, start_i : start_i+crop_len] - mean) / (std_unbiased + 1e-5), statistics over
  * (C, crop_len) jointly; i = clip*crops_per_clip + j; samples past clip_len read as zero; g = gain[clip] (NULL = 1).
  * JEPA.on_after_batch_transfer (wavjepa/jepa.py:291-311) and hear_api/runtime.py:12-16 (normalize). */
@@ -244,7 +255,16 @@ int wj_sumsq(const float* x, int64_t n, float scale, double* out, void* stream);
 int wj_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
                   float eps, float weight_decay, int step, float grad_scale, float max_norm, const double* grad_sumsq,
                   void* p_bf16, void* stream);
+/* The same step with the EMA teacher update folded into the pass over the parameters: for
+ * i in [ema_lo, ema_hi): teacher[i - ema_lo] = teacher * ema_decay + (1 - ema_decay) * p_old[i] (the student value BEFORE
+ * this optimizer step, as JEPA.training_step orders it, wavjepa/jepa.py:330-331) + its bf16 working copy. */
+int wj_adamw_ema_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+                      float eps, float weight_decay, int step, float grad_scale, float max_norm,
+                      const double* grad_sumsq, void* p_bf16, float* teacher, void* teacher_bf16, int64_t ema_lo,
+                      int64_t ema_hi, double ema_decay, void* stream);
 int wj_cast_bf16(const float* x, void* y_bf16, int64_t n, void* stream);
+/* a[i] += float(b[i]) (b bf16): joins an fp32 residual-branch gradient with a bf16 Linear data gradient. */
+int wj_add_bf16(float* a, const void* b_bf16, int64_t n, void* stream);
 /* out[n] += sum_m x[m, n] (bias gradients). */
 int wj_colsum(const void* x, int x_is_bf16, int64_t M, int N, int64_t ld, float* out, void* stream);
 int wj_scale_bf16(void* x_bf16, const float* scale_dev, int64_t n, void* stream);

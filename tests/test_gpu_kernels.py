@@ -30,7 +30,10 @@ def _device():
 
 # ------------------------------------------------------------------------------------------------------- GEMM
 @pytest.mark.parametrize("M,N,K,bn", [(128, 256, 64, 256), (128, 128, 64, 128), (300, 768, 512, 0), (300, 384, 768, 256),
-                                      (20000, 2304, 768, 256), (20000, 1152, 384, 128), (77, 3072, 768, 0)])
+                                      (20000, 2304, 768, 256), (20000, 1152, 384, 128), (77, 3072, 768, 0),
+                                      # 192-column tiles on the bf16 TMA-store epilogue (auto for N = 384 / 576)
+                                      (777, 384, 384, 0), (5000, 384, 1536, 0), (20000, 1152, 384, 192),
+                                      (300, 576, 128, 0), (1000, 768, 256, 192)])
 def test_gemm_plain(M, N, K, bn):
     a = torch.randn(M, K, device=DEV).bfloat16()
     w = (torch.randn(N, K, device=DEV) * 0.05).bfloat16()
@@ -169,6 +172,16 @@ def test_dgrad(M, N, K):
     assert rel(cs, o2.float().sum(0)) < 1e-5
 
 
+@pytest.mark.parametrize("M,N,K", [(1000, 768, 2304), (515, 384, 1536), (4000, 384, 1152), (777, 384, 384)])
+def test_dgrad_bf16_out(M, N, K):
+    """bf16 data gradients (what autocast's Linear backward returns): TMA-store epilogue, 192-column tiles for N = 384."""
+    dy = torch.randn(M, K, device=DEV).bfloat16()
+    w = (torch.randn(K, N, device=DEV) * 0.05).bfloat16()
+    out = torch.full((M, N), float("nan"), device=DEV, dtype=torch.bfloat16)
+    ops.gemm_dgrad(ops.plain_operand(dy), w, M, 1, out, K=K, N=N)
+    assert rel(out, dy.float() @ w.float()) < BF16_TOL
+
+
 # ------------------------------------------------------------------------------------------------------- masks
 def test_masks_time_inverse_bit_exact():
     from oracle import masks_oracle as mo
@@ -301,6 +314,56 @@ def test_layernorm_fwd_bwd(D, dtype):
     assert rel(dxf, xr.grad) < 1e-4 and rel(dxb, xr.grad) < BF16_TOL
     assert rel(dg, gr.grad) < 1e-4 and rel(db, br.grad) < 1e-4
     assert (cs - xr.grad.sum(0)).abs().max().item() < 1e-2
+
+
+@pytest.mark.parametrize("D", [384, 768])
+def test_add_layernorm_fwd_bwd(D):
+    """LayerNorm(x + bf16 addend) with the sum formed in registers, and its backward with a two-part output gradient
+    (fp32 residual branch + bf16 Linear data gradient) -- the post-norm layer of wavjepa/types/wavjepa_configs.py:29-47."""
+    M = 1237
+    x = torch.randn(M, D, device=DEV) * 2 + 0.5
+    a = torch.randn(M, D, device=DEV).bfloat16()
+    g = 1 + 0.1 * torch.randn(D, device=DEV)
+    b = 0.1 * torch.randn(D, device=DEV)
+    of = torch.empty(M, D, device=DEV)
+    ob = torch.empty(M, D, device=DEV, dtype=torch.bfloat16)
+    st = torch.empty(M, 2, device=DEV)
+    rs = torch.empty(M, 2, device=DEV)
+    ops.add_layernorm_fwd(x, a, g, b, 1e-6, of, ob, st, rs)
+    xr = x.clone().requires_grad_(True)
+    ar = a.float().requires_grad_(True)
+    gr = g.clone().requires_grad_(True)
+    br = b.clone().requires_grad_(True)
+    y = F.layer_norm(xr + ar, (D,), gr, br, 1e-6)
+    assert rel(of, y) < 1e-5 and rel(ob, y) < BF16_TOL
+    assert rel(rs[:, 1], (y * y).sum(1)) < 1e-5
+    d32 = torch.randn(M, D, device=DEV)
+    d16 = torch.randn(M, D, device=DEV).bfloat16()
+    y.backward(d32 + d16.float())
+    for (da, db_) in ((d32, d16), (d32 + d16.float(), None), (None, None)):
+        dxf = torch.empty(M, D, device=DEV)
+        dxb = torch.empty(M, D, device=DEV, dtype=torch.bfloat16)
+        dg = torch.zeros(D, device=DEV)
+        db = torch.zeros(D, device=DEV)
+        cs = torch.zeros(D, device=DEV)
+        if da is None:
+            with pytest.raises(_lib.WavJepaLibError):
+                ops.add_layernorm_bwd(None, None, x, a, st, g, dxf, dxb, dg, db, cs)
+            continue
+        ops.add_layernorm_bwd(da, db_, x, a, st, g, dxf, dxb, dg, db, cs)
+        assert rel(dxf, xr.grad) < 1e-4 and rel(dxb, xr.grad) < BF16_TOL
+        assert rel(dg, gr.grad) < 1e-4 and rel(db, br.grad) < 1e-4
+        assert (cs - xr.grad.sum(0)).abs().max().item() < 1e-2
+    # bf16-only output gradient, no addend (degenerates to the plain LayerNorm backward)
+    ops.add_layernorm_fwd(x, None, g, b, 1e-6, of, None, st, None)
+    xr2 = x.clone().requires_grad_(True)
+    F.layer_norm(xr2, (D,), g, b, 1e-6).backward(d16.float())
+    dxf = torch.empty(M, D, device=DEV)
+    ops.add_layernorm_bwd(None, d16, x, None, st, g, dxf, None, None, None, None)
+    assert rel(dxf, xr2.grad) < 1e-4
+    acc = d32.clone()
+    ops.add_bf16(acc, d16)
+    assert torch.equal(acc, d32 + d16.float())
 
 
 def test_crop_norm():
@@ -464,6 +527,21 @@ def test_ema_bitwise_and_optimizer_tail():
         ops.adamw_step(p, g * step, m, v, 4e-4, 0.9, 0.98, 1e-6, 0.04, step, 1.0, 5.0, ss, pb)
         assert rel(p, pr.data) < 1e-6
     assert torch.equal(pb, p.bfloat16())
+    # the same step with the EMA teacher update folded in (pre-step student values of p[lo:hi]): bitwise equal to the
+    # two separate kernels
+    lo, hi = 4096, 4096 + 500_000
+    p2, m2, v2 = p.clone(), m.clone(), v.clone()
+    tea = torch.randn(hi - lo, device=DEV)
+    tea_ref = tea.clone()
+    ops.ema_update(tea_ref, p[lo:hi], 0.9995)
+    ss = torch.zeros(1, device=DEV, dtype=torch.float64)
+    ops.sumsq(g, 1.0, ss)
+    ops.adamw_step(p, g, m, v, 4e-4, 0.9, 0.98, 1e-6, 0.04, 4, 1.0, 5.0, ss, pb)
+    pb2 = torch.empty_like(pb)
+    tb = torch.empty(hi - lo, device=DEV, dtype=torch.bfloat16)
+    ops.adamw_ema_step(p2, g, m2, v2, 4e-4, 0.9, 0.98, 1e-6, 0.04, 4, 1.0, 5.0, ss, pb2, tea, tb, lo, hi, 0.9995)
+    assert torch.equal(p2, p) and torch.equal(m2, m) and torch.equal(v2, v) and torch.equal(pb2, pb)
+    assert torch.equal(tea, tea_ref) and torch.equal(tb, tea_ref.bfloat16())
     y = torch.empty(n, device=DEV, dtype=torch.bfloat16)
     ops.cast_bf16(s, y)
     assert torch.equal(y, s.bfloat16())

@@ -213,11 +213,18 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ x,
 
 // torch.optim.AdamW (non-amsgrad, decoupled decay) with the clip_grad_norm_ coefficient folded in:
 //   g *= grad_scale * min(1, max_norm / (sqrt(sumsq) + 1e-6));  p *= 1 - lr*wd;  m,v updates;  p -= lr/bc1 * m / (sqrt(v)/sqrt(bc2) + eps)
+// and, folded into the same pass over the parameters: the EMA teacher update with the PRE-step
+// student value, teacher[i - ema_lo] = fl(fl(teacher * r) + fl(p_old * q)) for i in [ema_lo, ema_hi)
+// (JEPA._step_teacher, wavjepa/jepa.py:193-198, runs before the optimizer step in training_step :330-331), plus the bf16
+// working copies of both.  One float4 per thread per array (n, ema_lo, ema_hi are multiples of 4).
 __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
-                                                    float* __restrict__ m, float* __restrict__ v, long long n, float lr,
+                                                    float* __restrict__ m, float* __restrict__ v, long long n4, float lr,
                                                     float beta1, float beta2, float eps, float wd, float bc1,
                                                     float bc2_sqrt, float grad_scale, float max_norm,
-                                                    const double* __restrict__ sumsq, bf16* __restrict__ p_bf16) {
+                                                    const double* __restrict__ sumsq, bf16* __restrict__ p_bf16,
+                                                    float* __restrict__ teacher, bf16* __restrict__ teacher_bf16,
+                                                    long long ema_lo4, long long ema_hi4, float ema_r, float ema_q,
+                                                    long long n) {
   float coef = grad_scale;
   if (sumsq != nullptr && max_norm > 0.f) {
     const float total = static_cast<float>(sqrt(*sumsq));
@@ -225,18 +232,67 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const
     coef *= fminf(c, 1.0f);
   }
   const float step = lr / bc1;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+  const float decay = 1.0f - lr * wd;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const float gr = g[i] * coef;
-    float pv = p[i] * (1.0f - lr * wd);
-    const float mv = beta1 * m[i] + (1.0f - beta1) * gr;
-    const float vv = beta2 * v[i] + (1.0f - beta2) * gr * gr;
-    m[i] = mv;
-    v[i] = vv;
-    const float denom = sqrtf(vv) / bc2_sqrt + eps;
-    pv -= step * (mv / denom);
-    p[i] = pv;
-    if (p_bf16 != nullptr) p_bf16[i] = __float2bfloat16_rn(pv);
+    const float4 g4 = reinterpret_cast<const float4*>(g)[i];
+    float4 p4 = reinterpret_cast<float4*>(p)[i];
+    float4 m4 = reinterpret_cast<float4*>(m)[i];
+    float4 v4 = reinterpret_cast<float4*>(v)[i];
+    if (teacher != nullptr && i >= ema_lo4 && i < ema_hi4) {
+      float4 t = reinterpret_cast<float4*>(teacher)[i - ema_lo4];
+      t.x = __fadd_rn(__fmul_rn(t.x, ema_r), __fmul_rn(p4.x, ema_q));
+      t.y = __fadd_rn(__fmul_rn(t.y, ema_r), __fmul_rn(p4.y, ema_q));
+      t.z = __fadd_rn(__fmul_rn(t.z, ema_r), __fmul_rn(p4.z, ema_q));
+      t.w = __fadd_rn(__fmul_rn(t.w, ema_r), __fmul_rn(p4.w, ema_q));
+      reinterpret_cast<float4*>(teacher)[i - ema_lo4] = t;
+      if (teacher_bf16 != nullptr) store4(nullptr, teacher_bf16, static_cast<size_t>(i - ema_lo4) * 4, t);
+    }
+    float* pp = reinterpret_cast<float*>(&p4);
+    float* mm = reinterpret_cast<float*>(&m4);
+    float* vv = reinterpret_cast<float*>(&v4);
+    const float* gg = reinterpret_cast<const float*>(&g4);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float gr = gg[k] * coef;
+      float pv = pp[k] * decay;
+      const float mv = beta1 * mm[k] + (1.0f - beta1) * gr;
+      const float v2 = beta2 * vv[k] + (1.0f - beta2) * gr * gr;
+      mm[k] = mv;
+      vv[k] = v2;
+      const float denom = sqrtf(v2) / bc2_sqrt + eps;
+      pv -= step * (mv / denom);
+      pp[k] = pv;
+    }
+    reinterpret_cast<float4*>(m)[i] = m4;
+    reinterpret_cast<float4*>(v)[i] = v4;
+    reinterpret_cast<float4*>(p)[i] = p4;
+    if (p_bf16 != nullptr) store4(nullptr, p_bf16, static_cast<size_t>(i) * 4, p4);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {   // scalar tail (n not a multiple of 4; never inside the EMA range)
+    for (long long i = n4 * 4; i < n; ++i) {
+      const float gr = g[i] * coef;
+      float pv = p[i] * decay;
+      const float mv = beta1 * m[i] + (1.0f - beta1) * gr;
+      const float v2 = beta2 * v[i] + (1.0f - beta2) * gr * gr;
+      m[i] = mv;
+      v[i] = v2;
+      pv -= step * (mv / (sqrtf(v2) / bc2_sqrt + eps));
+      p[i] = pv;
+      if (p_bf16 != nullptr) p_bf16[i] = __float2bfloat16_rn(pv);
+    }
+  }
+}
+
+// a (fp32) += b (bf16): joins the two halves of a gradient (fp32 residual branch + bf16 Linear data gradient) where a
+// consumer wants one fp32 tensor (the bottom of a transformer stack)
+__global__ void __launch_bounds__(256) add_bf16_kernel(float* __restrict__ a, const bf16* __restrict__ b, long long n4) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float4 x = reinterpret_cast<float4*>(a)[i];
+    const float4 y = load4(b, true, static_cast<size_t>(i) * 4);
+    x.x += y.x; x.y += y.y; x.z += y.z; x.w += y.w;
+    reinterpret_cast<float4*>(a)[i] = x;
   }
 }
 
@@ -441,17 +497,37 @@ extern "C" int wj_sumsq(const float* x, int64_t n, float scale, double* out, voi
   return check_launch("sumsq");
 }
 
+extern "C" int wj_adamw_ema_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
+                                 float beta2, float eps, float weight_decay, int step, float grad_scale, float max_norm,
+                                 const double* grad_sumsq, void* p_bf16, float* teacher, void* teacher_bf16,
+                                 int64_t ema_lo, int64_t ema_hi, double ema_decay, void* stream) {
+  if (n <= 0) return WJ_OK;
+  if (teacher != nullptr && (ema_lo % 4 != 0 || ema_hi % 4 != 0 || ema_lo < 0 || ema_hi > n || ema_hi < ema_lo)) {
+    set_error("wj_adamw_ema_step: the EMA range must be 4-aligned and inside [0, n) (n=%lld, [%lld, %lld))", (long long)n,
+              (long long)ema_lo, (long long)ema_hi);
+    return WJ_ERR_ARG;
+  }
+  const double bc1 = 1.0 - pow(static_cast<double>(beta1), step);
+  const double bc2 = 1.0 - pow(static_cast<double>(beta2), step);
+  adamw_kernel<<<grid_for(n / 4 + 1), 256, 0, WJ_STREAM(stream)>>>(
+      p, g, m, v, n / 4, lr, beta1, beta2, eps, weight_decay, static_cast<float>(bc1), static_cast<float>(sqrt(bc2)),
+      grad_scale, max_norm, grad_sumsq, reinterpret_cast<bf16*>(p_bf16), teacher, reinterpret_cast<bf16*>(teacher_bf16),
+      ema_lo / 4, ema_hi / 4, static_cast<float>(ema_decay), static_cast<float>(1.0 - ema_decay), n);
+  return check_launch("adamw_step");
+}
+
 extern "C" int wj_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
                              float beta2, float eps, float weight_decay, int step, float grad_scale, float max_norm,
                              const double* grad_sumsq, void* p_bf16, void* stream) {
+  return wj_adamw_ema_step(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, step, grad_scale, max_norm, grad_sumsq,
+                           p_bf16, nullptr, nullptr, 0, 0, 0.0, stream);
+}
+
+extern "C" int wj_add_bf16(float* a, const void* b_bf16, int64_t n, void* stream) {
   if (n <= 0) return WJ_OK;
-  const double bc1 = 1.0 - pow(static_cast<double>(beta1), step);
-  const double bc2 = 1.0 - pow(static_cast<double>(beta2), step);
-  adamw_kernel<<<grid_for(n), 256, 0, WJ_STREAM(stream)>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay,
-                                                          static_cast<float>(bc1), static_cast<float>(sqrt(bc2)),
-                                                          grad_scale, max_norm, grad_sumsq,
-                                                          reinterpret_cast<bf16*>(p_bf16));
-  return check_launch("adamw_step");
+  if (n % 4 != 0) { set_error("wj_add_bf16: n must be a multiple of 4"); return WJ_ERR_ARG; }
+  add_bf16_kernel<<<grid_for(n / 4), 256, 0, WJ_STREAM(stream)>>>(a, reinterpret_cast<const bf16*>(b_bf16), n / 4);
+  return check_launch("add_bf16");
 }
 
 extern "C" int wj_cast_bf16(const float* x, void* y_bf16, int64_t n, void* stream) {

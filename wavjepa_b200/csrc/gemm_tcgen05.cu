@@ -308,21 +308,29 @@ template <int BN, bool HEAVY, typename Arrive>
 __device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const OutMaps& om, uint32_t t_base, uint8_t* stg,
                                                   int lane, int lane_grp, int col_q, int n_blk, int b, int row_in_batch0,
                                                   Arrive arrive) {
-  constexpr int CHUNKS = BN / 32 / 4;
+  // 32-column chunks per warp: BN/128, except BN = 192 (6 chunks per lane group): the warps of column quarters 0..2
+  // take two each and quarter 3 only hands the accumulator back
+  constexpr int CHUNKS = (BN / 32 + 3) / 4;
+  const int n_ch = (BN / 32 - col_q * CHUNKS) < CHUNKS ? (BN / 32 - col_q * CHUNKS) : CHUNKS;
+  if (n_ch <= 0) {
+    __syncwarp();
+    if (lane == 0) arrive();
+    return;
+  }
   const int row0 = row_in_batch0 + lane_grp * 32;
   uint8_t* srow = stg + lane * 64;          // staging row = lane (64 B); 16-byte chunk c lives at c ^ ((row >> 1) & 3)
   const int sw = (lane >> 1) & 3;           // (CU_TENSOR_MAP_SWIZZLE_64B)
   uint32_t v[32];
   tmem_ld_32x32(t_base, v);
 #pragma unroll 1
-  for (int ch = 0; ch < CHUNKS; ++ch) {
+  for (int ch = 0; ch < n_ch; ++ch) {
     const int n0 = n_blk * BN + (col_q * CHUNKS + ch) * 32;
     const bool live = n0 < p.N && row0 < p.L;   // warp-uniform
     tmem_ld_wait();
     float f[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-    if (ch + 1 < CHUNKS) {
+    if (ch + 1 < n_ch) {
       tmem_ld_32x32(t_base + (ch + 1) * 32, v);   // in flight during the math of this chunk
     } else {
       tc_fence_before();
@@ -661,7 +669,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const int ew = warp - kEpiWarp0;
     const int lane_grp = warp & 3;            // TMEM lanes [32*lane_grp, +32) are accessible to this warp
     const int col_q = ew >> 2;                // which quarter of the BN columns this warp handles
-    constexpr int CHUNKS = BN / 32 / 4;       // 32-column chunks per warp
+    constexpr int CHUNKS = (BN / 32 + 3) / 4; // 32-column chunks per warp (TMA-store paths)
     int it = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
@@ -1065,6 +1073,14 @@ static int setup_out_maps(GemmParams& p, OutMaps& om, int N, int L, int batch, b
 
 static int num_sms() { return sm_count(); }
 
+// 192-column tiles exist for the generic (fp32-output) epilogue and for the plain bf16 TMA-store epilogue
+static bool tile192_ok(const wj_epilogue_t* e, int N) {
+  if (e == nullptr || N % 192 != 0) return false;
+  if (e->out_f32) return true;
+  return !e->accumulate && e->resid == nullptr && e->out_rows == nullptr && e->colsum == nullptr && e->out2 == nullptr &&
+         (e->act == 0 || e->act == 1) && e->ld_out % 8 == 0 && reinterpret_cast<uintptr_t>(e->out) % 16 == 0;
+}
+
 template <int BN, int MODE, bool HEAVY>
 static int launch_variant(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmB1, const OutMaps& om,
                           const GemmParams& p, int grid, cudaStream_t st) {
@@ -1098,9 +1114,8 @@ template <int BN, int MODE>
 static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmB1, const OutMaps& om,
                   const GemmParams& p, int grid, cudaStream_t st) {
   if constexpr (BN == 192) {
-    // 192-column tiles serve fp32-output GEMMs with N = 384 only (generic epilogue; the TMA-store paths split the
-    // tile into 4 x 32k columns per lane group, which 192 is not)
-    if (p.tma_store) { set_error("gemm: BN = 192 has no TMA-store epilogue"); return WJ_ERR_ARG; }
+    // 192-column tiles (N = 384-like shapes): generic epilogue, or the plain bf16 TMA-store epilogue (bias / GELU)
+    if (p.tma_store && (p.out2 != nullptr || p.act == 2)) { set_error("gemm: BN = 192 has only the plain TMA-store epilogue"); return WJ_ERR_ARG; }
     return launch_variant<BN, MODE, false>(tmA, tmB, tmB1, om, p, grid, st);
   } else {
     if constexpr (MODE != 1) {
@@ -1140,9 +1155,9 @@ extern "C" int wj_gemm_bf16(const wj_operand_t* A, const void* W, int64_t ldw, i
   const bool pair = block_n < 0;   // -128 / -256: CTA-pair kernel (256-row tiles, tcgen05 cta_group::2)
   if (pair) block_n = -block_n;
   // N = 384-like fp32-output GEMMs: 192-column tiles (a 128-column B tile leaves the main loop smem-bandwidth bound)
-  const bool want192 = !pair && N % 192 == 0 && N % 256 != 0 && N <= 768 && epi != nullptr && epi->out_f32;
-  if (block_n == 0) block_n = want192 ? 192 : ((N % 256 == 0 || N > 1024) ? 256 : 128);
-  if (block_n != 128 && block_n != 256 && !(block_n == 192 && want192)) { set_error("wj_gemm_bf16: block_n must be 128 or 256 (192: fp32 outputs with N %% 192 == 0)"); return WJ_ERR_ARG; }
+  const bool ok192 = !pair && tile192_ok(epi, N);
+  if (block_n == 0) block_n = (ok192 && N % 256 != 0 && N <= 768) ? 192 : ((N % 256 == 0 || N > 1024) ? 256 : 128);
+  if (block_n != 128 && block_n != 256 && !(block_n == 192 && ok192)) { set_error("wj_gemm_bf16: block_n must be 128 or 256 (192: N %% 192 == 0 with an fp32 or plain bf16 output)"); return WJ_ERR_ARG; }
   CUtensorMap tmA, tmB;
   const uint32_t boxA[4] = {BK, 1, BM, 1};
   int rc = encode_map(&tmA, A, boxA);
@@ -1260,9 +1275,9 @@ extern "C" int wj_gemm_dgrad_bf16(const wj_operand_t* A, const void* W, int64_t 
   if (L <= 0 || batch <= 0) return WJ_OK;
   if (K % BK != 0 || N % 64 != 0) { set_error("wj_gemm_dgrad_bf16: K must be a multiple of 64 and N of 64 (K=%d N=%d)", K, N); return WJ_ERR_ARG; }
   if (A->seg_width > 0 && (A->seg_width % BK != 0 || K > 4 * A->seg_width)) { set_error("wj_gemm_dgrad_bf16: bad segment width"); return WJ_ERR_ARG; }
-  const bool want192 = N % 192 == 0 && N % 256 != 0 && N <= 768 && epi != nullptr && epi->out_f32;
-  if (block_n == 0) block_n = want192 ? 192 : ((N % 256 == 0 || N > 1024) ? 256 : 128);
-  if (block_n != 128 && block_n != 256 && !(block_n == 192 && want192)) { set_error("wj_gemm_dgrad_bf16: block_n must be 128 or 256 (192: fp32 outputs with N %% 192 == 0)"); return WJ_ERR_ARG; }
+  const bool ok192 = tile192_ok(epi, N) && (epi->out_f32 || epi->act == 0);
+  if (block_n == 0) block_n = (ok192 && N % 256 != 0 && N <= 768) ? 192 : ((N % 256 == 0 || N > 1024) ? 256 : 128);
+  if (block_n != 128 && block_n != 256 && !(block_n == 192 && ok192)) { set_error("wj_gemm_dgrad_bf16: block_n must be 128 or 256 (192: N %% 192 == 0 with an fp32 or plain bf16 output)"); return WJ_ERR_ARG; }
   CUtensorMap tmA, tmB;
   const uint32_t boxA[4] = {BK, 1, BM, 1};
   int rc = encode_map(&tmA, A, boxA);

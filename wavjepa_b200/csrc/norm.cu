@@ -16,7 +16,10 @@ template <int D, typename TIn>
 __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const TIn* __restrict__ x, const float* __restrict__ gamma,
                                                             const float* __restrict__ beta, float eps, int M,
                                                             float* __restrict__ out_f32, bf16* __restrict__ out_bf16,
-                                                            float* __restrict__ stats, float* __restrict__ rowsum) {
+                                                            float* __restrict__ stats, float* __restrict__ rowsum,
+                                                            const bf16* __restrict__ add) {
+  // add (optional, bf16 [M, D]): the row normalised is x + add -- the residual sum y = x + bf16(Linear(...)) of the
+  // post-norm layer, formed here in registers so that the GEMM writes 2 bytes per element and y never exists in HBM
   constexpr int PER = D / 32;  // elements per lane, contiguous chunks of 4
   static_assert(PER % 4 == 0, "D must be a multiple of 128");
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -35,6 +38,12 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const TIn* __restric
       const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
       const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
       v[4 * i] = a.x; v[4 * i + 1] = a.y; v[4 * i + 2] = b.x; v[4 * i + 3] = b.y;
+    }
+    if (add != nullptr) {
+      const uint2 u = *reinterpret_cast<const uint2*>(add + base + col);
+      const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+      const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+      v[4 * i] += a.x; v[4 * i + 1] += a.y; v[4 * i + 2] += b.x; v[4 * i + 3] += b.y;
     }
   }
   float s = 0.f;
@@ -83,7 +92,10 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
                                                             const float* __restrict__ gamma, int M,
                                                             float* __restrict__ dx_f32, bf16* __restrict__ dx_bf16,
                                                             float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                                            float* __restrict__ colsum, int rows_per_warp) {
+                                                            float* __restrict__ colsum, int rows_per_warp,
+                                                            const bf16* __restrict__ dy_b, const bf16* __restrict__ x_add) {
+  // dy (fp32, may be NULL) + dy_b (bf16, may be NULL) = gradient w.r.t. the LayerNorm output: the fp32 residual branch
+  // plus the bf16 data gradient of the Linear that consumed the output.  x + x_add = the normalised row (see forward).
   constexpr int PER = D / 32;
   __shared__ float s_red[8][D];
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -116,7 +128,20 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
         const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
         xv = make_float4(a.x, a.y, b.x, b.y);
       }
-      const float4 dv = *reinterpret_cast<const float4*>(dy + base + col);
+      if (x_add != nullptr) {
+        const uint2 u = *reinterpret_cast<const uint2*>(x_add + base + col);
+        const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+        const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+        xv.x += a.x; xv.y += a.y; xv.z += b.x; xv.w += b.y;
+      }
+      float4 dv = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (dy != nullptr) dv = *reinterpret_cast<const float4*>(dy + base + col);
+      if (dy_b != nullptr) {
+        const uint2 u = *reinterpret_cast<const uint2*>(dy_b + base + col);
+        const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+        const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+        dv.x += a.x; dv.y += a.y; dv.z += b.x; dv.w += b.y;
+      }
       xh[4 * i] = (xv.x - mean) * rstd; xh[4 * i + 1] = (xv.y - mean) * rstd;
       xh[4 * i + 2] = (xv.z - mean) * rstd; xh[4 * i + 3] = (xv.w - mean) * rstd;
       d[4 * i] = dv.x; d[4 * i + 1] = dv.y; d[4 * i + 2] = dv.z; d[4 * i + 3] = dv.w;
@@ -261,16 +286,16 @@ __global__ void __launch_bounds__(256) target_accum_kernel(const float* __restri
 
 template <typename TIn>
 static int launch_ln_fwd(const void* x, const float* g, const float* b, float eps, int M, int D, float* of, bf16* ob,
-                         float* stats, float* rowsum, cudaStream_t st) {
+                         float* stats, float* rowsum, cudaStream_t st, const bf16* add = nullptr) {
   const int blocks = (M + 7) / 8;
   const TIn* xi = reinterpret_cast<const TIn*>(x);
   switch (D) {
-    case 128: layernorm_fwd_kernel<128, TIn><<<blocks, 256, 0, st>>>(xi, g, b, eps, M, of, ob, stats, rowsum); break;
-    case 256: layernorm_fwd_kernel<256, TIn><<<blocks, 256, 0, st>>>(xi, g, b, eps, M, of, ob, stats, rowsum); break;
-    case 384: layernorm_fwd_kernel<384, TIn><<<blocks, 256, 0, st>>>(xi, g, b, eps, M, of, ob, stats, rowsum); break;
-    case 512: layernorm_fwd_kernel<512, TIn><<<blocks, 256, 0, st>>>(xi, g, b, eps, M, of, ob, stats, rowsum); break;
-    case 768: layernorm_fwd_kernel<768, TIn><<<blocks, 256, 0, st>>>(xi, g, b, eps, M, of, ob, stats, rowsum); break;
-    case 1024: layernorm_fwd_kernel<1024, TIn><<<blocks, 256, 0, st>>>(xi, g, b, eps, M, of, ob, stats, rowsum); break;
+    case 128: layernorm_fwd_kernel<128, TIn><<<blocks, 256, 0, st>>>(xi, g, b, eps, M, of, ob, stats, rowsum, add); break;
+    case 256: layernorm_fwd_kernel<256, TIn><<<blocks, 256, 0, st>>>(xi, g, b, eps, M, of, ob, stats, rowsum, add); break;
+    case 384: layernorm_fwd_kernel<384, TIn><<<blocks, 256, 0, st>>>(xi, g, b, eps, M, of, ob, stats, rowsum, add); break;
+    case 512: layernorm_fwd_kernel<512, TIn><<<blocks, 256, 0, st>>>(xi, g, b, eps, M, of, ob, stats, rowsum, add); break;
+    case 768: layernorm_fwd_kernel<768, TIn><<<blocks, 256, 0, st>>>(xi, g, b, eps, M, of, ob, stats, rowsum, add); break;
+    case 1024: layernorm_fwd_kernel<1024, TIn><<<blocks, 256, 0, st>>>(xi, g, b, eps, M, of, ob, stats, rowsum, add); break;
     default: set_error("layernorm: unsupported D=%d (128,256,384,512,768,1024)", D); return WJ_ERR_ARG;
   }
   return check_launch("layernorm_fwd");
@@ -289,19 +314,20 @@ extern "C" int wj_layernorm_fwd(const void* x, int x_is_bf16, const float* gamma
 
 template <typename TIn>
 static int launch_ln_bwd(const float* dy, const void* xv, const float* stats, const float* gamma, int M, int D,
-                         float* dx_f32, bf16* db, float* dgamma, float* dbeta, float* colsum, cudaStream_t st) {
+                         float* dx_f32, bf16* db, float* dgamma, float* dbeta, float* colsum, cudaStream_t st,
+                         const bf16* dy_b = nullptr, const bf16* x_add = nullptr) {
   // aim for ~4 waves of 8-warp blocks; each warp walks a contiguous run of rows to amortise the column atomics
   int rows_per_warp = (M + sm_count() * 4 * 8 - 1) / (sm_count() * 4 * 8);
   if (rows_per_warp < 1) rows_per_warp = 1;
   const int blocks = (M + rows_per_warp * 8 - 1) / (rows_per_warp * 8);
   const TIn* x = reinterpret_cast<const TIn*>(xv);
   switch (D) {
-    case 128: layernorm_bwd_kernel<128, TIn><<<blocks, 256, 0, st>>>(dy, x, stats, gamma, M, dx_f32, db, dgamma, dbeta, colsum, rows_per_warp); break;
-    case 256: layernorm_bwd_kernel<256, TIn><<<blocks, 256, 0, st>>>(dy, x, stats, gamma, M, dx_f32, db, dgamma, dbeta, colsum, rows_per_warp); break;
-    case 384: layernorm_bwd_kernel<384, TIn><<<blocks, 256, 0, st>>>(dy, x, stats, gamma, M, dx_f32, db, dgamma, dbeta, colsum, rows_per_warp); break;
-    case 512: layernorm_bwd_kernel<512, TIn><<<blocks, 256, 0, st>>>(dy, x, stats, gamma, M, dx_f32, db, dgamma, dbeta, colsum, rows_per_warp); break;
-    case 768: layernorm_bwd_kernel<768, TIn><<<blocks, 256, 0, st>>>(dy, x, stats, gamma, M, dx_f32, db, dgamma, dbeta, colsum, rows_per_warp); break;
-    case 1024: layernorm_bwd_kernel<1024, TIn><<<blocks, 256, 0, st>>>(dy, x, stats, gamma, M, dx_f32, db, dgamma, dbeta, colsum, rows_per_warp); break;
+    case 128: layernorm_bwd_kernel<128, TIn><<<blocks, 256, 0, st>>>(dy, x, stats, gamma, M, dx_f32, db, dgamma, dbeta, colsum, rows_per_warp, dy_b, x_add); break;
+    case 256: layernorm_bwd_kernel<256, TIn><<<blocks, 256, 0, st>>>(dy, x, stats, gamma, M, dx_f32, db, dgamma, dbeta, colsum, rows_per_warp, dy_b, x_add); break;
+    case 384: layernorm_bwd_kernel<384, TIn><<<blocks, 256, 0, st>>>(dy, x, stats, gamma, M, dx_f32, db, dgamma, dbeta, colsum, rows_per_warp, dy_b, x_add); break;
+    case 512: layernorm_bwd_kernel<512, TIn><<<blocks, 256, 0, st>>>(dy, x, stats, gamma, M, dx_f32, db, dgamma, dbeta, colsum, rows_per_warp, dy_b, x_add); break;
+    case 768: layernorm_bwd_kernel<768, TIn><<<blocks, 256, 0, st>>>(dy, x, stats, gamma, M, dx_f32, db, dgamma, dbeta, colsum, rows_per_warp, dy_b, x_add); break;
+    case 1024: layernorm_bwd_kernel<1024, TIn><<<blocks, 256, 0, st>>>(dy, x, stats, gamma, M, dx_f32, db, dgamma, dbeta, colsum, rows_per_warp, dy_b, x_add); break;
     default: set_error("layernorm_bwd: unsupported D=%d", D); return WJ_ERR_ARG;
   }
   return check_launch("layernorm_bwd");
@@ -314,6 +340,24 @@ extern "C" int wj_layernorm_bwd(const float* dy, const void* x, int x_is_bf16, c
   bf16* db = reinterpret_cast<bf16*>(dx_bf16);
   if (x_is_bf16) return launch_ln_bwd<bf16>(dy, x, stats, gamma, M, D, dx_f32, db, dgamma, dbeta, colsum, WJ_STREAM(stream));
   return launch_ln_bwd<float>(dy, x, stats, gamma, M, D, dx_f32, db, dgamma, dbeta, colsum, WJ_STREAM(stream));
+}
+
+extern "C" int wj_add_layernorm_fwd(const float* x, const void* add_bf16, const float* gamma, const float* beta, float eps,
+                                    int M, int D, float* out_f32, void* out_bf16, float* stats, float* rowsum,
+                                    void* stream) {
+  if (M <= 0) return WJ_OK;
+  return launch_ln_fwd<float>(x, gamma, beta, eps, M, D, out_f32, reinterpret_cast<bf16*>(out_bf16), stats, rowsum,
+                              WJ_STREAM(stream), reinterpret_cast<const bf16*>(add_bf16));
+}
+
+extern "C" int wj_add_layernorm_bwd(const float* dy_f32, const void* dy_bf16, const float* x, const void* add_bf16,
+                                    const float* stats, const float* gamma, int M, int D, float* dx_f32, void* dx_bf16,
+                                    float* dgamma, float* dbeta, float* colsum, void* stream) {
+  if (M <= 0) return WJ_OK;
+  if (dy_f32 == nullptr && dy_bf16 == nullptr) { set_error("wj_add_layernorm_bwd: no output gradient given"); return WJ_ERR_ARG; }
+  return launch_ln_bwd<float>(dy_f32, x, stats, gamma, M, D, dx_f32, reinterpret_cast<bf16*>(dx_bf16), dgamma, dbeta, colsum,
+                              WJ_STREAM(stream), reinterpret_cast<const bf16*>(dy_bf16),
+                              reinterpret_cast<const bf16*>(add_bf16));
 }
 
 extern "C" int wj_crop_norm(const float* audio, const int* starts, const float* gain, int n_clips, int channels,

@@ -725,26 +725,31 @@ class JEPA(nn.Module):
         if ddp is not None:
             ddp.finish()
             world = ddp.world_size
-        # EMA uses the student weights BEFORE the optimizer step
-        r = self._get_ema_decay()
-        e0, e1 = self._enc_range
-        ops.ema_update(self._flat_t, self._flat_p[e0:e1], r)
-        ops.cast_bf16(self._flat_t, self._flat_t16)
-        self._optimizer_tail(gflat, world, self.lr_at(self.global_step))
+        # the EMA uses the student weights BEFORE the optimizer step (wavjepa/jepa.py:330-331): folded into the
+        # AdamW pass, which reads every parameter once anyway
+        self._optimizer_tail(gflat, world, self.lr_at(self.global_step), ema_decay=self._get_ema_decay())
         return c.loss
 
-    def _optimizer_tail(self, gflat: torch.Tensor, world: int, lr: float) -> None:
-        """Global-norm clip + AdamW over the flat buffers (+ bf16 working-weight refresh); the lr of optimizer step
-        k is the scheduler's value at k = global_step (LambdaLR)."""
+    def _optimizer_tail(self, gflat: torch.Tensor, world: int, lr: float, ema_decay: Optional[float] = None) -> None:
+        """Global-norm clip + AdamW over the flat buffers (+ bf16 working-weight refresh) and, when `ema_decay` is
+        given, the EMA teacher update with the pre-step student in the same pass; the lr of optimizer step k is the
+        scheduler's value at k = global_step (LambdaLR)."""
         if self._adam_m is None:
             self._adam_m = torch.zeros_like(self._flat_p)
             self._adam_v = torch.zeros_like(self._flat_p)
         ss = torch.zeros(1, device=gflat.device, dtype=torch.float64)
         ops.sumsq(gflat, 1.0 / world, ss)
         b1, b2 = self.hparams.adam_betas
-        ops.adamw_step(self._flat_p, gflat, self._adam_m, self._adam_v, lr, b1, b2,
-                       self.hparams.adam_eps, self.hparams.adam_weight_decay, self.global_step + 1, 1.0 / world,
-                       self.grad_clip, ss, self._flat_w16)
+        if ema_decay is None:
+            ops.adamw_step(self._flat_p, gflat, self._adam_m, self._adam_v, lr, b1, b2,
+                           self.hparams.adam_eps, self.hparams.adam_weight_decay, self.global_step + 1, 1.0 / world,
+                           self.grad_clip, ss, self._flat_w16)
+        else:
+            e0, e1 = self._enc_range
+            ops.adamw_ema_step(self._flat_p, gflat, self._adam_m, self._adam_v, lr, b1, b2,
+                               self.hparams.adam_eps, self.hparams.adam_weight_decay, self.global_step + 1,
+                               1.0 / world, self.grad_clip, ss, self._flat_w16, self._flat_t, self._flat_t16, e0, e1,
+                               ema_decay)
         self._refresh_conv_weights()
         self.global_step += 1
 

@@ -305,6 +305,45 @@ def layernorm_bwd(dy: torch.Tensor, x: torch.Tensor, stats, gamma, dx_f32=None, 
                                p(dx_bf16), p(dgamma), p(dbeta), p(colsum), _stream()))
 
 
+def add_layernorm_fwd(x: torch.Tensor, add: Optional[torch.Tensor], gamma, beta, eps: float, out_f32=None, out_bf16=None,
+                      stats=None, rowsum=None):
+    """LayerNorm(x + add): x fp32 residual stream, add bf16 (the Linear output as autocast rounds it) or None."""
+    M, D = x.shape
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    assert add is None or (add.dtype == torch.bfloat16 and add.is_contiguous() and add.shape == x.shape)
+    lib = _lib.load()
+    p = lambda t: C.c_void_p(_ptr(t))
+    if _lib._profile is not None:
+        _lib._profile.meta = (0.0, M, D, add is not None, out_f32 is not None, out_bf16 is not None)
+    check(lib.wj_add_layernorm_fwd(p(x), p(add), p(gamma), p(beta), C.c_float(eps), M, D, p(out_f32), p(out_bf16),
+                                   p(stats), p(rowsum), _stream()))
+
+
+def add_layernorm_bwd(dy_f32: Optional[torch.Tensor], dy_bf16: Optional[torch.Tensor], x: torch.Tensor,
+                      add: Optional[torch.Tensor], stats, gamma, dx_f32=None, dx_bf16=None, dgamma=None, dbeta=None,
+                      colsum=None):
+    """Backward of add_layernorm_fwd; the output gradient is dy_f32 + dy_bf16 (either may be None)."""
+    M, D = x.shape
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    assert dy_f32 is None or (dy_f32.dtype == torch.float32 and dy_f32.is_contiguous())
+    assert dy_bf16 is None or (dy_bf16.dtype == torch.bfloat16 and dy_bf16.is_contiguous())
+    assert add is None or (add.dtype == torch.bfloat16 and add.is_contiguous())
+    lib = _lib.load()
+    p = lambda t: C.c_void_p(_ptr(t))
+    if _lib._profile is not None:
+        _lib._profile.meta = (0.0, M, D, dy_f32 is not None, dy_bf16 is not None, colsum is not None)
+    check(lib.wj_add_layernorm_bwd(p(dy_f32), p(dy_bf16), p(x), p(add), p(stats), p(gamma), M, D, p(dx_f32), p(dx_bf16),
+                                   p(dgamma), p(dbeta), p(colsum), _stream()))
+
+
+def add_bf16(a: torch.Tensor, b: torch.Tensor):
+    """a (fp32) += b (bf16), in place."""
+    assert a.dtype == torch.float32 and b.dtype == torch.bfloat16 and a.numel() == b.numel()
+    assert a.is_contiguous() and b.is_contiguous()
+    lib = _lib.load()
+    check(lib.wj_add_bf16(C.c_void_p(_ptr(a)), C.c_void_p(_ptr(b)), C.c_int64(a.numel()), _stream()))
+
+
 def crop_norm(audio: torch.Tensor, starts: Optional[torch.Tensor], crops_per_clip: int, crop_len: int,
               out_bf16=None, out_f32=None, gain: Optional[torch.Tensor] = None):
     n_clips, ch, clip_len = audio.shape
@@ -413,6 +452,18 @@ def adamw_step(p_, g, m, v, lr, beta1, beta2, eps, wd, step, grad_scale=1.0, max
     check(lib.wj_adamw_step(p(p_), p(g), p(m), p(v), C.c_int64(p_.numel()), C.c_float(lr), C.c_float(beta1),
                             C.c_float(beta2), C.c_float(eps), C.c_float(wd), int(step), C.c_float(grad_scale),
                             C.c_float(max_norm), p(grad_sumsq), p(p_bf16), _stream()))
+
+
+def adamw_ema_step(p_, g, m, v, lr, beta1, beta2, eps, wd, step, grad_scale, max_norm, grad_sumsq, p_bf16, teacher,
+                   teacher_bf16, ema_lo: int, ema_hi: int, ema_decay: float):
+    """adamw_step with the EMA teacher update (pre-step student values of p_[ema_lo:ema_hi]) folded into the same pass."""
+    lib = _lib.load()
+    p = lambda t: C.c_void_p(_ptr(t))
+    assert teacher.numel() == ema_hi - ema_lo
+    check(lib.wj_adamw_ema_step(p(p_), p(g), p(m), p(v), C.c_int64(p_.numel()), C.c_float(lr), C.c_float(beta1),
+                                C.c_float(beta2), C.c_float(eps), C.c_float(wd), int(step), C.c_float(grad_scale),
+                                C.c_float(max_norm), p(grad_sumsq), p(p_bf16), p(teacher), p(teacher_bf16),
+                                C.c_int64(ema_lo), C.c_int64(ema_hi), C.c_double(ema_decay), _stream()))
 
 
 def cast_bf16(x: torch.Tensor, y: torch.Tensor):
