@@ -97,6 +97,12 @@ if "--conv-wgrad" in sys.argv:
     run_conv_wgrad()
     sys.exit(0)
 run("pred qkv plain", 172433, 1152, 384)
+run("pred qkv plain bn192", 172433, 1152, 384, bn=192)
+run("pred qkv plain bn128", 172433, 1152, 384, bn=128)
+run("pred fc2 plain bf16 (bn192)", 172433, 384, 1536)
+run("pred fc2 plain bf16 bn128", 172433, 384, 1536, bn=128)
+run("pred outproj plain bf16 (bn192)", 172433, 384, 384)
+run("pred outproj plain bf16 bn128", 172433, 384, 384, bn=128)
 run("pred fc1 gelu+save", 172433, 1536, 384, act=1, out2=True)
 run("pred fc1 gelu", 172433, 1536, 384, act=1)
 run("pred fc1 plain", 172433, 1536, 384)

@@ -74,13 +74,14 @@ with _lib.KernelProfile() as kp:
     step()
 torch.cuda.synchronize()
 groups = {}
-for name, a, b, meta in kp.records:
+for name, a, b, meta, nbytes in kp.records:
     key = (name, meta[1:] if meta else None)
-    c, t, f = groups.get(key, (0, 0.0, 0.0))
-    groups[key] = (c + 1, t + a.elapsed_time(b), f + (meta[0] if meta else 0.0))
-tot = sum(t for (_, t, _) in groups.values())
+    c, t, f, nb = groups.get(key, (0, 0.0, 0.0, 0))
+    groups[key] = (c + 1, t + a.elapsed_time(b), f + (meta[0] if meta else 0.0), nb + (nbytes or 0))
+tot = sum(t for (_, t, _, _) in groups.values())
 print(f"sum of bracketed launches: {tot:.2f} ms")
-print(f"{'entry':28s} {'(M, N, K, act, f32out)':34s} {'calls':>5s} {'ms':>9s} {'%':>6s} {'TFLOP/s':>8s}")
-for (name, shape), (c, t, f) in sorted(groups.items(), key=lambda kv: -kv[1][1]):
+print(f"{'entry':28s} {'(M, N, K, act, f32out)':34s} {'calls':>5s} {'ms':>9s} {'%':>6s} {'TFLOP/s':>8s} {'GB/s':>7s}")
+for (name, shape), (c, t, f, nb) in sorted(groups.items(), key=lambda kv: -kv[1][1]):
     tf = f / (t * 1e-3) / 1e12 if f else 0.0
-    print(f"{name[3:]:28s} {str(shape) if shape else '':34s} {c:5d} {t:9.3f} {100 * t / tot:6.2f} {tf:8.1f}")
+    gbs = nb / (t * 1e-3) / 1e9 if nb else 0.0
+    print(f"{name[3:]:28s} {str(shape) if shape else '':34s} {c:5d} {t:9.3f} {100 * t / tot:6.2f} {tf:8.1f} {gbs:7.0f}")

@@ -254,11 +254,7 @@ def test_conv0_gn_gelu_fwd_bwd(Cin, L):
     L_out = (L - 10) // 5 + 1
     out = torch.empty(B, L_out, C, device=DEV, dtype=torch.bfloat16)
     mom, stats, red = ops.conv0_workspaces(B, Cin, C, DEV, backward=True)
-    dgelu = torch.empty_like(out)
-    ops.conv0_fwd(x, w, gamma, beta, out, mom, stats, dgelu)
-    out_inf = torch.empty_like(out)            # inference: nothing saved, same values
-    ops.conv0_fwd(x, w, gamma, beta, out_inf, mom, stats, None)
-    assert torch.equal(out, out_inf)
+    ops.conv0_fwd(x, w, gamma, beta, out, mom, stats)
     wr = w.bfloat16().float().requires_grad_(True)
     gr = gamma.clone().requires_grad_(True)
     br = beta.clone().requires_grad_(True)
@@ -271,15 +267,12 @@ def test_conv0_gn_gelu_fwd_bwd(Cin, L):
     dw = torch.zeros_like(w)
     dg = torch.zeros(C, device=DEV)
     db = torch.zeros(C, device=DEV)
-    zq = F.group_norm(hq, C, gr, br, 1e-5).detach().requires_grad_(True)
-    F.gelu(zq).sum().backward()
-    assert rel(dgelu, zq.grad.transpose(1, 2)) < BF16_TOL
-    ops.conv0_bwd(x, w, gamma, beta, mom, stats, dy, dgelu, red, dw, dg, db)
+    ops.conv0_bwd(x, w, gamma, beta, mom, stats, dy, red, dw, dg, db)     # GELU' recomputed from x: nothing saved
     # closed-form GroupNorm statistics == statistics of the conv output (to fp32 accuracy)
     hm = h.detach().mean(dim=2)
     assert (stats[..., 0] - hm).abs().max() < 1e-4
     assert rel(stats[..., 1], 1.0 / torch.sqrt(h.detach().var(dim=2, unbiased=False) + 1e-5)) < 1e-4
-    # the saved GELU' and dz are bf16 (like autograd's bf16 conv weight gradient): ~2^-9 relative noise per term
+    # the recomputed GELU' (packed fp16) and dz (bf16, like autograd's bf16 conv weight gradient): ~2^-9 noise per term
     assert rel(dw, wr.grad) < 4e-3
     assert rel(dg, gr.grad) < 4e-3
     assert rel(db, br.grad) < 4e-3

@@ -60,8 +60,9 @@ class KernelProfile:
     kernel's average duration for the roofline.  Not active unless `with KernelProfile() as kp:` is entered."""
 
     def __init__(self):
-        self.records = []   # (entry point, start event, end event, meta)
+        self.records = []   # (entry point, start event, end event, meta, algorithmic bytes | None)
         self.meta = None
+        self.nbytes = None  # set by ops.* for the HBM-bound kernels: the bytes the op must move (reads + writes)
 
     def __enter__(self):
         global _profile
@@ -77,9 +78,21 @@ class KernelProfile:
         import torch
         torch.cuda.synchronize()
         out = {}
-        for name, e0, e1, _ in self.records:
+        for name, e0, e1, _, _ in self.records:
             c, t = out.get(name, (0, 0.0))
             out[name] = (c + 1, t + e0.elapsed_time(e1))
+        return out
+
+    def hbm_summary(self):
+        """-> {entry point: (calls, total ms, total algorithmic bytes)} over the calls that declared their bytes."""
+        import torch
+        torch.cuda.synchronize()
+        out = {}
+        for name, e0, e1, _, nb in self.records:
+            if nb is None:
+                continue
+            c, t, b = out.get(name, (0, 0.0, 0))
+            out[name] = (c + 1, t + e0.elapsed_time(e1), b + int(nb))
         return out
 
 
@@ -107,8 +120,9 @@ class _Proxy:
             e0.record()
             rc = fn(*args)
             e1.record()
-            _profile.records.append((name, e0, e1, _profile.meta))
+            _profile.records.append((name, e0, e1, _profile.meta, _profile.nbytes))
             _profile.meta = None
+            _profile.nbytes = None
             return rc
 
         setattr(self, name, call)

@@ -12,10 +12,13 @@
 //                     with variance 2^-18 h^2 / 3), far below the bf16 resolution of the result.
 //   forward   (one pass) conv (bf16-rounded, as autocast does) -> normalise -> affine -> GELU -> [B, L_out, C] bf16
 //   backward  (one pass over dY) per (instance, channel): S1 = sum dz, S2 = sum dz hhat, P[a] = sum dz x_a with
-//                     dz = dY gelu'(z); then (tiny) dW[c,a] += rstd gamma (P[a] - S1/L s[a] - S2/L Q[a]),
+//                     dz = dY gelu'(z), z RECOMPUTED from the input window (10 MAC on the tensor cores + the closed-form
+//                     statistics) instead of read from a saved copy: the forward writes its 3.37 GB (B = 512) once and
+//                     the backward reads dY once; then (tiny) dW[c,a] += rstd gamma (P[a] - S1/L s[a] - S2/L Q[a]),
 //                     Q[a] = sum_t hhat x_a = rstd ((R w)[a] - mean s[a]); dgamma += S2, dbeta += S1.
-// Thread <-> 2 adjacent channels, weights in registers, the input window of 4 consecutive outputs in registers
-// (5 x LDS.128 per 4 outputs), stores / dY loads are 128 contiguous bytes per warp.
+// MMA column <-> channel mapping: inside a group of 64 channels, column j of n-tile nt is channel
+// (j >> 1) * 16 + nt * 2 + (j & 1), so that the accumulator columns a lane owns over the 8 n-tiles (2 tg, 2 tg + 1) are 16
+// CONSECUTIVE channels: a lane stores / loads 32 contiguous bytes per row, a warp 8 rows x 128 contiguous bytes.
 #include "common.cuh"
 
 namespace wj {
@@ -159,29 +162,35 @@ __device__ __forceinline__ void conv_at_frag(const bf16* sx, int tl0, int g, int
   a[3] = g < 2 ? pack2(c1[8], c1[kC0S + 8]) : 0u;
 }
 
-// grid (ceil(chunks / chunks_per_block), B), block C/2 threads = C/64 warps... the forward gives every warp one block of
-// 16 outputs of the 128-output tile and ALL channels (8 warps x 16 = 128 outputs).
+// channel of column j (0..7) of n-tile nt (0..7) in the 64-channel group cg
+__device__ __forceinline__ int c0_chan(int cg, int nt, int j) { return cg * 64 + (j >> 1) * 16 + nt * 2 + (j & 1); }
+
+// grid (ceil(chunks / chunks_per_block), B), block 256 = 8 warps: every warp takes one block of 16 outputs of the
+// 128-output tile and ALL channels, 64 at a time.  Weights and the per-channel (scale, shift) sit in shared memory in
+// FRAGMENT order ([ci][cg][nt][column g][16 taps], [cg][nt][tg]) so that the mapping above costs nothing in the loop.
 template <int CIN>
 __global__ void __launch_bounds__(256) conv0_fwd_kernel(Conv0Args a, const float* __restrict__ stats,
                                                         const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, bf16* __restrict__ out,
-                                                        bf16* __restrict__ dgelu, int chunks_per_block) {
+                                                        int chunks_per_block) {
   extern __shared__ __align__(16) uint8_t smem_c0[];
-  bf16* s_w = reinterpret_cast<bf16*>(smem_c0);                       // [CIN][C][16] taps (10..15 zero)
-  float4* s_p = reinterpret_cast<float4*>(s_w + CIN * a.C * 16);      // [C/2] (scale0, shift0, scale1, shift1)
+  bf16* s_w = reinterpret_cast<bf16*>(smem_c0);                       // [CIN][C (fragment order)][16] taps (10..15 zero)
+  float4* s_p = reinterpret_cast<float4*>(s_w + CIN * a.C * 16);      // [C/2 (fragment order)] (scale0, shift0, scale1, shift1)
   bf16* s_x = reinterpret_cast<bf16*>(s_p + a.C / 2);                 // [CIN][kC0WinB]
   const int b = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tg = lane & 3;
   for (int i = threadIdx.x; i < CIN * a.C * 16; i += blockDim.x) {
-    const int k = i & 15, c = (i >> 4) % a.C, ci = (i >> 4) / a.C;
+    const int k = i & 15, pos = (i >> 4) % a.C, ci = (i >> 4) / a.C;
+    const int c = c0_chan(pos >> 6, (pos >> 3) & 7, pos & 7);
     s_w[i] = __float2bfloat16_rn(k < kC0K ? a.w[(static_cast<size_t>(c) * CIN + ci) * kC0K + k] : 0.f);
   }
   for (int i = threadIdx.x; i < a.C / 2; i += blockDim.x) {
-    const float4 st = *reinterpret_cast<const float4*>(stats + (static_cast<size_t>(b) * a.C + 2 * i) * 2);  // m0 r0 m1 r1
-    const float g0 = gamma[2 * i] * st.y, g1 = gamma[2 * i + 1] * st.w;
-    s_p[i] = make_float4(g0, beta[2 * i] - st.x * g0, g1, beta[2 * i + 1] - st.z * g1);
+    const int c = c0_chan(i >> 5, (i >> 2) & 7, 2 * (i & 3));     // pair (c, c + 1) of lane column pair tg = i & 3
+    const float4 st = *reinterpret_cast<const float4*>(stats + (static_cast<size_t>(b) * a.C + c) * 2);  // m0 r0 m1 r1
+    const float g0 = gamma[c] * st.y, g1 = gamma[c + 1] * st.w;
+    s_p[i] = make_float4(g0, beta[c] - st.x * g0, g1, beta[c + 1] - st.z * g1);
   }
-  const int n_tiles = a.C / 8;
+  const int n_groups = a.C / 64;
   for (int ch = 0; ch < chunks_per_block; ++ch) {
     const int t0 = (blockIdx.x * chunks_per_block + ch) * kC0TT;
     if (t0 >= a.L_out) break;
@@ -195,70 +204,63 @@ __global__ void __launch_bounds__(256) conv0_fwd_kernel(Conv0Args a, const float
     for (int ci = 0; ci < CIN; ++ci) conv_a_frag(s_x + ci * kC0WinB, tl0, g, tg, af[ci]);
     const int ta = t0 + tl0 + g, tb = ta + 8;
     const bool va = ta < a.L_out, vb = tb < a.L_out;
-    // lanes with even tg store tile nt, lanes with odd tg store tile nt+1 (4 consecutive channels = 8 bytes each)
-    const int ccol = ((tg & 1) ? 8 : 0) + (tg >> 1) * 4;
-    for (int nt = 0; nt < n_tiles; nt += 2) {
-      uint32_t y[2][2], d[2][2];   // [tile][row]
+    bf16* oa = out + (static_cast<size_t>(b) * a.L_out + ta) * a.C + tg * 16;
+    bf16* ob = oa + static_cast<size_t>(8) * a.C;
+    for (int cg = 0; cg < n_groups; ++cg) {
+      uint32_t ya[8], yb[8];   // 16 consecutive channels (cg*64 + tg*16 ..) of rows ta / tb, bf16x2 per n-tile
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
+      for (int nt = 0; nt < 8; ++nt) {
         float c[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int ci = 0; ci < CIN; ++ci) {
-          const uint32_t* wp = reinterpret_cast<const uint32_t*>(s_w + (static_cast<size_t>(ci) * a.C + (nt + u) * 8 + g) * 16) + tg;
+          const uint32_t* wp = reinterpret_cast<const uint32_t*>(s_w + (static_cast<size_t>(ci) * a.C + (cg * 8 + nt) * 8 + g) * 16) + tg;
           mma16816(c, af[ci], wp[0], wp[4]);
         }
-        const float4 pr = s_p[(nt + u) * 4 + tg];
-        float y0, y1, y2, y3, d0, d1, d2, d3;
-        bf16_round2(c[0], c[1]);   // (one F2FP per pair instead of two XU-pipe F2F: the GELU already saturates the XU)
+        const float4 pr = s_p[(cg * 8 + nt) * 4 + tg];
+        bf16_round2(c[0], c[1]);   // autocast: the conv output is bf16 before GroupNorm (fp32) sees it
         bf16_round2(c[2], c[3]);
-        gelu_fast2(fmaf(c[0], pr.x, pr.y), y0, d0);
-        gelu_fast2(fmaf(c[1], pr.z, pr.w), y1, d1);
-        gelu_fast2(fmaf(c[2], pr.x, pr.y), y2, d2);
-        gelu_fast2(fmaf(c[3], pr.z, pr.w), y3, d3);
-        y[u][0] = pack_bf16x2(y0, y1); y[u][1] = pack_bf16x2(y2, y3);
-        d[u][0] = pack_bf16x2(d0, d1); d[u][1] = pack_bf16x2(d2, d3);
+        ya[nt] = gelu_h2(fmaf(c[0], pr.x, pr.y), fmaf(c[1], pr.z, pr.w));
+        yb[nt] = gelu_h2(fmaf(c[2], pr.x, pr.y), fmaf(c[3], pr.z, pr.w));
       }
-      // pair exchange inside the quad: even tg keeps tile 0 and receives the neighbour's tile-0 pair; odd tg likewise
-      // for tile 1 -> every lane owns 4 consecutive channels of one row
-      const bool odd = tg & 1;
-#pragma unroll
-      for (int r = 0; r < 2; ++r) {
-        const uint32_t ys = odd ? y[0][r] : y[1][r], ds = odd ? d[0][r] : d[1][r];
-        const uint32_t yr = __shfl_xor_sync(0xffffffffu, ys, 1), dr = __shfl_xor_sync(0xffffffffu, ds, 1);
-        const uint2 yo = odd ? make_uint2(yr, y[1][r]) : make_uint2(y[0][r], yr);
-        const uint2 dd = odd ? make_uint2(dr, d[1][r]) : make_uint2(d[0][r], dr);
-        const int t = r == 0 ? ta : tb;
-        if (r == 0 ? va : vb) {
-          const size_t o = (static_cast<size_t>(b) * a.L_out + t) * a.C + nt * 8 + ccol;
-          *reinterpret_cast<uint2*>(out + o) = yo;
-          if (dgelu != nullptr) *reinterpret_cast<uint2*>(dgelu + o) = dd;
-        }
+      if (va) {
+        *reinterpret_cast<uint4*>(oa + cg * 64) = make_uint4(ya[0], ya[1], ya[2], ya[3]);
+        *reinterpret_cast<uint4*>(oa + cg * 64 + 8) = make_uint4(ya[4], ya[5], ya[6], ya[7]);
+      }
+      if (vb) {
+        *reinterpret_cast<uint4*>(ob + cg * 64) = make_uint4(yb[0], yb[1], yb[2], yb[3]);
+        *reinterpret_cast<uint4*>(ob + cg * 64 + 8) = make_uint4(yb[4], yb[5], yb[6], yb[7]);
       }
     }
   }
 }
 
 // Backward, the one pass over dY: red[b, 0, c] += S1, red[b, 1, c] += S2, red[b, 2 + a, c] += P[a].
-// Warp w owns channels [64 w, 64 w + 64) (8 n-tiles) and walks every 16-output block of the CTA's time range:
-// conv (mma) -> hhat; dz = dY * saved GELU'; S1 += dz, S2 += dz hhat; P^T[tap][ch] += X^T[tap][t] dz[t][ch] (mma, dz
-// rounded to bf16 like autograd's bf16 conv weight gradient, transposed into a B fragment with movmatrix).
+// Warp w owns the 64-channel group w (8 n-tiles, mapping above) and walks every 16-output block of the CTA's time
+// range: conv (mma) -> hhat -> z -> gelu'(z); dz = dY * gelu'(z); S1 += dz, S2 += dz hhat;
+// P^T[tap][ch] += X^T[tap][t] dz[t][ch] (mma, dz rounded to bf16 like autograd's bf16 conv weight gradient, transposed
+// into a B fragment with movmatrix).  dY arrives as 2 x 16-byte loads per row per lane.
 template <int CIN>
 __global__ void __launch_bounds__(256, 2) conv0_bwd_kernel(Conv0Args a, const float* __restrict__ stats,
-                                                           const bf16* __restrict__ dy, const bf16* __restrict__ dgelu,
+                                                           const float* __restrict__ gamma,
+                                                           const float* __restrict__ beta, const bf16* __restrict__ dy,
                                                            float* __restrict__ red, int chunks_per_block) {
   constexpr int NA = CIN * kC0K;
   __shared__ __align__(16) bf16 s_x[CIN * kC0WinB];
-  __shared__ float4 s_mr[256];   // (mean0, rstd0, mean1, rstd1) of channel pair i (C = 512)
+  __shared__ float4 s_mr[256];   // (mean0, rstd0, mean1, rstd1) of channel pair i (C = 512), FRAGMENT order [warp][nt][tg]
+  __shared__ float4 s_gb[256];   // (gamma0, beta0, gamma1, beta1)
   const int b = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tg = lane & 3;
   const int c_base = warp * 64;
-  // weights of this warp's 8 n-tiles as B fragments (bf16-rounded), (mean, rstd) of its channel pairs
+  // weights of this warp's 8 n-tiles as B fragments (bf16-rounded), (mean, rstd, gamma, beta) of its channel pairs
   uint32_t wb[CIN][8][2];
-  for (int i = threadIdx.x; i < a.C / 2; i += blockDim.x)
-    s_mr[i] = *reinterpret_cast<const float4*>(stats + (static_cast<size_t>(b) * a.C + 2 * i) * 2);
+  for (int i = threadIdx.x; i < a.C / 2; i += blockDim.x) {
+    const int c = c0_chan(i >> 5, (i >> 2) & 7, 2 * (i & 3));
+    s_mr[i] = *reinterpret_cast<const float4*>(stats + (static_cast<size_t>(b) * a.C + c) * 2);
+    s_gb[i] = make_float4(gamma[c], beta[c], gamma[c + 1], beta[c + 1]);
+  }
 #pragma unroll
   for (int nt = 0; nt < 8; ++nt) {
-    const int c = c_base + nt * 8 + g;
+    const int c = c0_chan(warp, nt, g);
 #pragma unroll
     for (int ci = 0; ci < CIN; ++ci) {
       const float* wr = a.w + (static_cast<size_t>(c) * CIN + ci) * kC0K;
@@ -289,27 +291,32 @@ __global__ void __launch_bounds__(256, 2) conv0_bwd_kernel(Conv0Args a, const fl
       }
       const int ta = t0 + tl0 + g, tb = ta + 8;
       const bool va = ta < a.L_out, vb = tb < a.L_out;
-      const size_t oa = (static_cast<size_t>(b) * a.L_out + ta) * a.C + c_base + 2 * tg;
-      const size_t ob = oa + static_cast<size_t>(8) * a.C;
+      const bf16* pa = dy + (static_cast<size_t>(b) * a.L_out + ta) * a.C + c_base + tg * 16;
+      const bf16* pb = pa + static_cast<size_t>(8) * a.C;
+      uint32_t da[8], db[8];   // dY of this lane's 16 consecutive channels, rows ta / tb (bf16x2 per n-tile; 0 past the end)
+      {
+        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+        const uint4 a0 = va ? *reinterpret_cast<const uint4*>(pa) : z, a1 = va ? *reinterpret_cast<const uint4*>(pa + 8) : z;
+        const uint4 b0 = vb ? *reinterpret_cast<const uint4*>(pb) : z, b1 = vb ? *reinterpret_cast<const uint4*>(pb + 8) : z;
+        da[0] = a0.x; da[1] = a0.y; da[2] = a0.z; da[3] = a0.w; da[4] = a1.x; da[5] = a1.y; da[6] = a1.z; da[7] = a1.w;
+        db[0] = b0.x; db[1] = b0.y; db[2] = b0.z; db[3] = b0.w; db[4] = b1.x; db[5] = b1.y; db[6] = b1.z; db[7] = b1.w;
+      }
 #pragma unroll
       for (int nt = 0; nt < 8; ++nt) {
         float c[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int ci = 0; ci < CIN; ++ci) mma16816(c, af[ci], wb[ci][nt][0], wb[ci][nt][1]);
-        const uint32_t dya = va ? *reinterpret_cast<const uint32_t*>(dy + oa + nt * 8) : 0u;
-        const uint32_t dyb = vb ? *reinterpret_cast<const uint32_t*>(dy + ob + nt * 8) : 0u;
-        const uint32_t dga = va ? *reinterpret_cast<const uint32_t*>(dgelu + oa + nt * 8) : 0u;
-        const uint32_t dgb = vb ? *reinterpret_cast<const uint32_t*>(dgelu + ob + nt * 8) : 0u;
-        const float2 ya = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&dya));
-        const float2 yb = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&dyb));
-        const float2 ga = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&dga));
-        const float2 gb = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&dgb));
-        const float z0 = ya.x * ga.x, z1 = ya.y * ga.y, z2 = yb.x * gb.x, z3 = yb.y * gb.y;   // dz (0 past the end)
-        const float4 mr = s_mr[(c_base >> 1) + nt * 4 + tg];
+        const float2 ya = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&da[nt]));
+        const float2 yb = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&db[nt]));
+        const float4 mr = s_mr[(warp * 8 + nt) * 4 + tg];
+        const float4 gb = s_gb[(warp * 8 + nt) * 4 + tg];
         bf16_round2(c[0], c[1]);
         bf16_round2(c[2], c[3]);
         const float h0 = (c[0] - mr.x) * mr.y, h1 = (c[1] - mr.z) * mr.w;
         const float h2 = (c[2] - mr.x) * mr.y, h3 = (c[3] - mr.z) * mr.w;
+        const float2 ga = dgelu_h2(fmaf(h0, gb.x, gb.y), fmaf(h1, gb.z, gb.w));
+        const float2 gbv = dgelu_h2(fmaf(h2, gb.x, gb.y), fmaf(h3, gb.z, gb.w));
+        const float z0 = ya.x * ga.x, z1 = ya.y * ga.y, z2 = yb.x * gbv.x, z3 = yb.y * gbv.y;   // dz (0 past the end)
         s1[nt][0] += z0 + z2; s1[nt][1] += z1 + z3;
         s2[nt][0] = fmaf(z0, h0, fmaf(z2, h2, s2[nt][0]));
         s2[nt][1] = fmaf(z1, h1, fmaf(z3, h3, s2[nt][1]));
@@ -319,8 +326,9 @@ __global__ void __launch_bounds__(256, 2) conv0_bwd_kernel(Conv0Args a, const fl
       }
     }
   }
-  // S1 / S2: sum over the 8 lanes (g) that share a channel pair; P^T: fragments already hold sums over outputs
-  float* r = red + static_cast<size_t>(b) * (2 + NA) * a.C + c_base;
+  // S1 / S2: sum over the 8 lanes (g) that share a channel pair; P^T: fragments already hold sums over outputs.
+  // Accumulator columns (2 tg, 2 tg + 1) of n-tile nt are channels c_base + tg * 16 + nt * 2 + {0, 1}.
+  float* r = red + static_cast<size_t>(b) * (2 + NA) * a.C + c_base + tg * 16;
 #pragma unroll
   for (int nt = 0; nt < 8; ++nt) {
 #pragma unroll
@@ -332,13 +340,13 @@ __global__ void __launch_bounds__(256, 2) conv0_bwd_kernel(Conv0Args a, const fl
         v2 += __shfl_xor_sync(0xffffffffu, v2, o);
       }
       if (g == 0) {
-        atomicAdd(r + nt * 8 + 2 * tg + e, v1);
-        atomicAdd(r + a.C + nt * 8 + 2 * tg + e, v2);
+        atomicAdd(r + nt * 2 + e, v1);
+        atomicAdd(r + a.C + nt * 2 + e, v2);
       }
     }
 #pragma unroll
     for (int ci = 0; ci < CIN; ++ci) {
-      float* rp = r + static_cast<size_t>(2 + ci * kC0K) * a.C + nt * 8 + 2 * tg;
+      float* rp = r + static_cast<size_t>(2 + ci * kC0K) * a.C + nt * 2;
       atomicAdd(rp + static_cast<size_t>(g) * a.C, pt[ci][nt][0]);
       atomicAdd(rp + static_cast<size_t>(g) * a.C + 1, pt[ci][nt][1]);
       if (g < 2) {
@@ -437,16 +445,16 @@ extern "C" int wj_conv0_gn_gelu_fwd(const void* x_bf16, const float* w, const fl
   const int cpb = 4;
   dim3 grid((chunks + cpb - 1) / cpb, B);
   bf16* out = reinterpret_cast<bf16*>(out_bf16);
-  bf16* dg = reinterpret_cast<bf16*>(dgelu_bf16);
+  (void)dgelu_bf16;   // (ABI of round 1: the backward now recomputes GELU' from the input window; nothing is saved)
   const size_t smem = static_cast<size_t>(Cin) * C * 16 * 2 + static_cast<size_t>(C / 2) * 16 + static_cast<size_t>(Cin) * kC0WinB * 2 + 16;
   if (Cin == 1) {
     conv0_moments_kernel<1><<<B, 512, 0, st>>>(a, moments);
     conv0_stats_kernel<1><<<B, C, 0, st>>>(a, moments, eps, stats);
-    conv0_fwd_kernel<1><<<grid, 256, smem, st>>>(a, stats, gamma, beta, out, dg, cpb);
+    conv0_fwd_kernel<1><<<grid, 256, smem, st>>>(a, stats, gamma, beta, out, cpb);
   } else {
     conv0_moments_kernel<2><<<B, 512, 0, st>>>(a, moments);
     conv0_stats_kernel<2><<<B, C, 0, st>>>(a, moments, eps, stats);
-    conv0_fwd_kernel<2><<<grid, 256, smem, st>>>(a, stats, gamma, beta, out, dg, cpb);
+    conv0_fwd_kernel<2><<<grid, 256, smem, st>>>(a, stats, gamma, beta, out, cpb);
   }
   return check_launch("conv0_gn_gelu_fwd", 3);
 }
@@ -458,8 +466,7 @@ extern "C" int wj_conv0_gn_gelu_bwd(const void* x_bf16, const float* w, const fl
   if (B <= 0) return WJ_OK;
   int rc = check_conv0(Cin, C, k, stride);
   if (rc) return rc;
-  if (dgelu_bf16 == nullptr) { set_error("conv0 backward needs the GELU' saved by the forward"); return WJ_ERR_ARG; }
-  (void)eps; (void)beta;
+  (void)eps; (void)dgelu_bf16;   // GELU' is recomputed (see the kernel); the argument is kept for ABI stability
   cudaStream_t st = WJ_STREAM(stream);
   Conv0Args a;
   a.x = reinterpret_cast<const bf16*>(x_bf16); a.w = w; a.B = B; a.Cin = Cin; a.L = L; a.C = C;
@@ -470,13 +477,12 @@ extern "C" int wj_conv0_gn_gelu_bwd(const void* x_bf16, const float* w, const fl
   const int cpb = 13;   // 2 + na accumulators per channel flushed with atomics at the end: few, long blocks
   dim3 grid((chunks + cpb - 1) / cpb, B);
   const bf16* dy = reinterpret_cast<const bf16*>(dy_bf16);
-  const bf16* dg = reinterpret_cast<const bf16*>(dgelu_bf16);
   dim3 fgrid((C + 31) / 32), fblock(32, 8);
   if (Cin == 1) {
-    conv0_bwd_kernel<1><<<grid, C / 2, 0, st>>>(a, stats, dy, dg, red_scratch, cpb);
+    conv0_bwd_kernel<1><<<grid, C / 2, 0, st>>>(a, stats, gamma, beta, dy, red_scratch, cpb);
     conv0_bwd_finalize_kernel<1><<<fgrid, fblock, 0, st>>>(a, moments, stats, gamma, red_scratch, dw, dgamma, dbeta);
   } else {
-    conv0_bwd_kernel<2><<<grid, C / 2, 0, st>>>(a, stats, dy, dg, red_scratch, cpb);
+    conv0_bwd_kernel<2><<<grid, C / 2, 0, st>>>(a, stats, gamma, beta, dy, red_scratch, cpb);
     conv0_bwd_finalize_kernel<2><<<fgrid, fblock, 0, st>>>(a, moments, stats, gamma, red_scratch, dw, dgamma, dbeta);
   }
   return check_launch("conv0_gn_gelu_bwd", 2);

@@ -78,8 +78,15 @@ constexpr int BK = 64;
 constexpr int kThreads = 640;
 constexpr int kEpiWarp0 = 4;
 constexpr int kEpiWarps = 16;
-constexpr int kEpiRegs = 104;     // setmaxnreg targets: launch allocation is <= 96 / thread (640 threads)
-constexpr int kCtrlRegs = 40;
+// setmaxnreg targets.  The pool a CTA re-distributes is its LAUNCH allocation (640 threads x 96 registers), not the
+// SM's register file: 128 * ctrl + 512 * epi must stay <= 61440 or setmaxnreg.inc waits forever.
+constexpr int kLaunchRegs = 96;
+template <bool WIDE>
+struct RegSplit {   // WIDE: the two-output GELU epilogue holds 64 accumulator + 32 result registers
+  static constexpr int EPI = WIDE ? 112 : 104;
+  static constexpr int CTRL = WIDE ? 24 : 40;
+  static_assert(128 * CTRL + 512 * EPI <= kThreads * kLaunchRegs, "setmaxnreg split exceeds the CTA's register pool");
+};
 
 template <int BN>
 struct Cfg {
@@ -304,6 +311,31 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t t_ba
 // the per-element addressing, transposes and predicates of the generic path: tcgen05.ld.32x32b (row per lane) -> math
 // -> 4 x st.shared.v4 into a 64B-swizzled 32 x 32 staging tile (2 KB per warp) -> ONE TMA store per 32 x 32 chunk
 // (the hardware clips rows >= L and columns >= N).  ~5x fewer issued instructions per element than the generic path.
+// (Measured alternatives, all slower on B200: reading the staged tile back transposed and writing it with coalesced
+// st.global.v4 instead of the TMA store -- 0.247 vs 0.209 ms on the 172k x 1536 x 384 GEMM; draining both 32-column
+// chunks from TMEM and releasing the accumulator before any math -- 0.353 vs 0.302 ms with the two-output GELU.)
+__device__ __forceinline__ void stage_rows(uint8_t* stg, int lane, const uint32_t (&w)[16]) {
+  uint8_t* srow = stg + lane * 64;          // staging row = lane (64 B); 16-byte chunk c lives at c ^ ((row >> 1) & 3)
+  const int sw = (lane >> 1) & 3;           // (CU_TENSOR_MAP_SWIZZLE_64B)
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+    *reinterpret_cast<uint4*>(srow + ((c ^ sw) << 4)) = make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
+}
+
+// staged 32 x 32 bf16 chunk -> global memory through one TMA store
+__device__ __forceinline__ void chunk_to_global(const CUtensorMap* map, uint8_t* stg, int lane, const uint32_t (&w)[16],
+                                                int n0, int row0, int b) {
+  if (lane == 0) bulk_wait_read0();   // the previous TMA store of this warp has finished reading the staging tile
+  __syncwarp();
+  stage_rows(stg, lane, w);
+  fence_proxy_async_smem();
+  __syncwarp();
+  if (lane == 0) {
+    tma_store_3d(map, stg, n0, row0, b);
+    bulk_commit();
+  }
+}
+
 template <int BN, bool HEAVY, typename Arrive>
 __device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const OutMaps& om, uint32_t t_base, uint8_t* stg,
                                                   int lane, int lane_grp, int col_q, int n_blk, int b, int row_in_batch0,
@@ -318,8 +350,6 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const Out
     return;
   }
   const int row0 = row_in_batch0 + lane_grp * 32;
-  uint8_t* srow = stg + lane * 64;          // staging row = lane (64 B); 16-byte chunk c lives at c ^ ((row >> 1) & 3)
-  const int sw = (lane >> 1) & 3;           // (CU_TENSOR_MAP_SWIZZLE_64B)
   uint32_t v[32];
   tmem_ld_32x32(t_base, v);
 #pragma unroll 1
@@ -350,13 +380,9 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const Out
     uint32_t w[16];
     uint32_t w2[HEAVY ? 16 : 1];
     if constexpr (!HEAVY) {
-      if (p.act == 1) {   // autocast semantics: the linear/conv output is bf16 and GELU is evaluated on that bf16 value
+      if (p.act == 1) {   // GELU of the Linear / conv output, two values per instruction (see ptx.cuh: gelu_h2)
 #pragma unroll
-        for (int j = 0; j < 32; j += 2) {
-          float x0 = f[j], x1 = f[j + 1];
-          bf16_round2(x0, x1);
-          w[j >> 1] = pack_bf16x2(gelu_fast(x0), gelu_fast(x1));
-        }
+        for (int j = 0; j < 32; j += 2) w[j >> 1] = gelu_h2(f[j], f[j + 1]);
       } else {
 #pragma unroll
         for (int j = 0; j < 32; j += 2) w[j >> 1] = pack_bf16x2(f[j], f[j + 1]);
@@ -364,45 +390,17 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const Out
     } else {
       if (p.act == 1) {
 #pragma unroll
-        for (int j = 0; j < 32; j += 2) {
-          float g0, d0, g1, d1;
-          float x0 = f[j], x1 = f[j + 1];
-          bf16_round2(x0, x1);
-          gelu_fast2(x0, g0, d0);
-          gelu_fast2(x1, g1, d1);
-          w[j >> 1] = pack_bf16x2(g0, g1);
-          w2[j >> 1] = pack_bf16x2(d0, d1);
-        }
+        for (int j = 0; j < 32; j += 2) gelu_h2_save(f[j], f[j + 1], w[j >> 1], w2[j >> 1]);
       } else {
 #pragma unroll
         for (int j = 0; j < 32; j += 2) w[j >> 1] = pack_bf16x2(f[j], f[j + 1]);
       }
     }
-    if (lane == 0) bulk_wait_read0();   // the previous TMA store of this warp has finished reading the staging tile
-    __syncwarp();
-#pragma unroll
-    for (int c = 0; c < 4; ++c)
-      *reinterpret_cast<uint4*>(srow + ((c ^ sw) << 4)) = make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
-    fence_proxy_async_smem();
-    __syncwarp();
-    if (lane == 0) {
-      tma_store_3d(&om.o, stg, n0, row0, b);
-      bulk_commit();
-    }
+    chunk_to_global(&om.o, stg, lane, w, n0, row0, b);
     if constexpr (HEAVY) {
       if (p.act == 1 && p.out2 != nullptr) {
         __syncwarp();
-        if (lane == 0) bulk_wait_read0();
-        __syncwarp();
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-          *reinterpret_cast<uint4*>(srow + ((c ^ sw) << 4)) = make_uint4(w2[4 * c], w2[4 * c + 1], w2[4 * c + 2], w2[4 * c + 3]);
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) {
-          tma_store_3d(&om.o2, stg, n0, row0, b);
-          bulk_commit();
-        }
+        chunk_to_global(&om.o2, stg, lane, w2, n0, row0, b);
       }
     }
   }
@@ -548,7 +546,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
   };
 
-  if (warp < kEpiWarp0) reg_dealloc<kCtrlRegs>();
+  using RS = RegSplit<(MODE == 0 && HEAVY)>;
+  if (warp < kEpiWarp0) reg_dealloc<RS::CTRL>();
   if (warp == 0) {
     // ======================================================================================= TMA producer
     if (lane == 0) {
@@ -665,7 +664,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     // 16-byte vectors with 64-128 contiguous bytes per row per instruction.  Work unit = 16 TMEM lanes x 32 columns;
     // the next unit's TMEM load is in flight during the math of the current one.  16 warps (4 per scheduler) hide the
     // shuffle / global-load latencies; registers come from the producer/MMA warpgroup via setmaxnreg.
-    reg_alloc<kEpiRegs>();
+    reg_alloc<RS::EPI>();
     const int ew = warp - kEpiWarp0;
     const int lane_grp = warp & 3;            // TMEM lanes [32*lane_grp, +32) are accessible to this warp
     const int col_q = ew >> 2;                // which quarter of the BN columns this warp handles
@@ -733,12 +732,14 @@ struct CfgPair {
   static constexpr int B_BYTES = (BN / 2) * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (BN == 256) ? 6 : 8;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int STAGING_OFF = STAGES * STAGE_BYTES + 1024;   // barriers live in the 1 KB before it
+  static constexpr int SMEM_BYTES = STAGING_OFF + 1024 /*align slack*/ + kEpiWarps * 2048 /*TMA-store staging*/;
 };
 
-template <int BN, int MODE>
+template <int BN, int MODE, bool HEAVY>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
-gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ OutMaps om, const GemmParams p) {
   using C = CfgPair<BN>;
   constexpr bool WGRAD = (MODE == 1);
   constexpr bool B_MN = (MODE != 0);
@@ -794,7 +795,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   };
 
-  if (warp < kEpiWarp0) reg_dealloc<kCtrlRegs>();
+  using RS = RegSplit<(MODE == 0 && HEAVY)>;
+  if (warp < kEpiWarp0) reg_dealloc<RS::CTRL>();
   if (warp == 0) {
     // ======================================================================================= TMA producer (both CTAs)
     if (lane == 0) {
@@ -896,7 +898,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else if (warp >= kEpiWarp0) {
     // ======================================================================================= epilogue (both CTAs)
-    reg_alloc<kEpiRegs>();
+    reg_alloc<RS::EPI>();
     const int ew = warp - kEpiWarp0;
     const int lane_grp = warp & 3;
     const int col_q = ew >> 2;
@@ -923,10 +925,18 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       tc_fence_after();
       const uint32_t t_base = tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16) + acc * BN;
       const uint32_t te = mapa_shared(smem_u32(&tempty_bar[acc]), 0);
+      if constexpr (!WGRAD) {
+        if (p.tma_store) {   // bf16 outputs: the same staged TMA-store epilogues as the single-CTA kernel
+          epilogue_tile_tma<BN, HEAVY>(p, om, t_base + col_q * (CHUNKS * 32), smem + C::STAGING_OFF + ew * 2048, lane,
+                                       lane_grp, col_q, n_blk, b, row_in_batch0, [&]() { mbar_arrive_cluster(te); });
+          continue;
+        }
+      }
       epilogue_tile<BN, WGRAD>(p, t_base, lane, lane_grp, col_q, n_blk, b, row_in_batch0,
                                static_cast<long long>(m_blk) * BMP + static_cast<long long>(rank) * BM, have_k,
                                [&]() { mbar_arrive_cluster(te); });
     }
+    if (p.tma_store && lane == 0) bulk_wait0();   // all TMA stores of this warp are complete before smem goes away
   }
 
   tc_fence_before();
@@ -1095,10 +1105,11 @@ static int launch_variant(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
   return check_launch("gemm_tcgen05 launch");
 }
 
-template <int BN, int MODE>
-static int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t st) {
+template <int BN, int MODE, bool HEAVY>
+static int launch_pair_variant(const CUtensorMap& tmA, const CUtensorMap& tmB, const OutMaps& om, const GemmParams& p,
+                               cudaStream_t st) {
   static bool attr_set = false;
-  auto kern = gemm_pair_kernel<BN, MODE>;
+  auto kern = gemm_pair_kernel<BN, MODE, HEAVY>;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgPair<BN>::SMEM_BYTES);
     if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(pair): %s", cudaGetErrorString(e)); return WJ_ERR_RUNTIME; }
@@ -1106,8 +1117,15 @@ static int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
   }
   int pairs = num_sms() / 2;
   if (p.total_tiles < pairs) pairs = p.total_tiles;
-  kern<<<2 * pairs, kThreads, CfgPair<BN>::SMEM_BYTES, st>>>(tmA, tmB, p);
+  kern<<<2 * pairs, kThreads, CfgPair<BN>::SMEM_BYTES, st>>>(tmA, tmB, om, p);
   return check_launch("gemm_tcgen05 pair launch");
+}
+
+template <int BN, int MODE>
+static int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const OutMaps& om, const GemmParams& p,
+                       cudaStream_t st) {
+  if (p.tma_store && p.out2 != nullptr) return launch_pair_variant<BN, MODE, true>(tmA, tmB, om, p, st);
+  return launch_pair_variant<BN, MODE, false>(tmA, tmB, om, p, st);
 }
 
 template <int BN, int MODE>
@@ -1175,8 +1193,11 @@ extern "C" int wj_gemm_bf16(const wj_operand_t* A, const void* W, int64_t ldw, i
     fill_seg(p.seg, A);
     fill_epilogue(p, epi);
     cudaStream_t stp = reinterpret_cast<cudaStream_t>(stream);
-    if (block_n == 256) return launch_pair<256, 0>(tmA, tmB, p, stp);
-    return launch_pair<128, 0>(tmA, tmB, p, stp);
+    OutMaps omp;
+    rc = setup_out_maps(p, omp, N, L, batch);
+    if (rc) return rc;
+    if (block_n == 256) return launch_pair<256, 0>(tmA, tmB, omp, p, stp);
+    return launch_pair<128, 0>(tmA, tmB, omp, p, stp);
   }
   p.mb_per_batch = (L + BM - 1) / BM;
   p.m_blocks = batch * p.mb_per_batch;

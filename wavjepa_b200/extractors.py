@@ -110,9 +110,9 @@ def conv_stack_forward(spec, x16: torch.Tensor, w0: torch.Tensor, gn_w: torch.Te
         raise WavJepaLibError("input shorter than the first conv kernel")
     a = torch.empty(B, L0, C, device=dev, dtype=torch.bfloat16)
     moments, stats = ops.conv0_workspaces(B, Cin, C, dev)
-    d0 = torch.empty(B, L0, C, device=dev, dtype=torch.bfloat16) if save else None   # GELU'(z) of block 0
-    ops.conv0_fwd(x16, w0, gn_w, gn_b, a, moments, stats, d0, eps=gn_eps)
-    acts, pre = [a], [d0]
+    # (block 0 saves nothing the size of its output: its backward recomputes GELU'(z) from the input window)
+    ops.conv0_fwd(x16, w0, gn_w, gn_b, a, moments, stats, eps=gn_eps)
+    acts, pre = [a], [None]
     for i, (_, k, _) in enumerate(spec[1:], start=1):
         x = acts[-1]
         L_in = x.shape[1]
@@ -166,7 +166,7 @@ def conv_stack_backward(spec, sv: ConvSaved, dh_last: torch.Tensor, w0, gn_w, gn
         if on_layer_done is not None:
             on_layer_done(i)
     red = torch.empty(B, 2 + sv.x16.shape[1] * 10, C, device=dev, dtype=torch.float32)
-    ops.conv0_bwd(sv.x16, w0, gn_w, gn_b, sv.moments, sv.stats, dh, sv.pre[0], red, g_w0, g_gn_w, g_gn_b, eps=gn_eps)
+    ops.conv0_bwd(sv.x16, w0, gn_w, gn_b, sv.moments, sv.stats, dh, red, g_w0, g_gn_w, g_gn_b, eps=gn_eps)
     if on_layer_done is not None:
         on_layer_done(0)
 

@@ -100,6 +100,9 @@ def gemm(a: Operand, w: torch.Tensor, L: int, batch: int, out: torch.Tensor, *, 
     lib = _lib.load()
     if _lib._profile is not None:
         _lib._profile.meta = (2.0 * L * batch * N * K, L * batch, N, K, e.act, int(e.out_f32))
+        _lib._profile.nbytes = (L * batch * K * 2 + N * K * 2 + L * batch * N * (esz + 2 * (out2 is not None)) +
+                                (L * batch * N * resid.element_size() if resid is not None and resid_mod == 0 else 0) +
+                                (L * batch * N * 2 if aux is not None else 0))
     check(lib.wj_gemm_bf16(C.byref(a), C.c_void_p(_ptr(w)), C.c_int64(w.stride(0)), L, batch, N, K, C.byref(e),
                            block_n, _stream()))
 
@@ -115,6 +118,7 @@ def gemm_wgrad(dy: Operand, x: Operand, L: int, batch: int, out: torch.Tensor, *
     lib = _lib.load()
     if _lib._profile is not None:
         _lib._profile.meta = (2.0 * L * batch * M * N, L * batch, M, N, 0, 1)
+        _lib._profile.nbytes = L * batch * (M + N) * 2 + M * N * 4
     check(lib.wj_gemm_wgrad_bf16(C.byref(dy), C.byref(x), L, batch, M, N, C.c_void_p(_ptr(out) + out_offset * 4),
                                  C.c_int64(ld), 1 if accumulate else 0, splits, _stream()))
 
@@ -153,6 +157,9 @@ def gemm_dgrad(a: Operand, w: torch.Tensor, L: int, batch: int, out: torch.Tenso
     lib = _lib.load()
     if _lib._profile is not None:
         _lib._profile.meta = (2.0 * L * batch * N * K, L * batch, N, K, e.act, int(e.out_f32))
+        _lib._profile.nbytes = (L * batch * K * 2 + N * K * 2 + L * batch * N * esz +
+                                (L * batch * N * resid.element_size() if resid is not None else 0) +
+                                (L * batch * N * 2 if aux is not None else 0))
     check(lib.wj_gemm_dgrad_bf16(C.byref(a), C.c_void_p(_ptr(w) + w_col_offset * 2), C.c_int64(w.stride(0)),
                                  w.shape[0], w_cols, seg, L, batch, N, K, C.byref(e), block_n, _stream()))
 
@@ -256,28 +263,33 @@ def conv0_workspaces(B: int, Cin: int, C: int, device, backward: bool = False):
 
 
 def conv0_fwd(x: torch.Tensor, w: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, out: torch.Tensor,
-              moments: torch.Tensor, stats: torch.Tensor, dgelu: Optional[torch.Tensor] = None, k: int = 10,
-              stride: int = 5, eps: float = 1e-5) -> None:
-    """dgelu (bf16, same shape as out): receives GELU'(z) for the backward; None = inference."""
+              moments: torch.Tensor, stats: torch.Tensor, k: int = 10, stride: int = 5, eps: float = 1e-5) -> None:
+    """Conv1d(Cin->C, 10, 5) + GroupNorm(C, C) + GELU -> out [B, L_out, C] bf16; moments / stats feed the backward."""
     B, Cin, L = x.shape
     assert x.dtype == torch.bfloat16 and x.is_contiguous() and w.dtype == torch.float32
     assert moments.dtype == torch.float64 and stats.dtype == torch.float32
     lib = _lib.load()
+    if _lib._profile is not None:
+        L_out = (L - k) // stride + 1
+        _lib._profile.nbytes = B * (Cin * L * 2 + L_out * w.shape[0] * 2)
     check(lib.wj_conv0_gn_gelu_fwd(C.c_void_p(_ptr(x)), C.c_void_p(_ptr(w)), C.c_void_p(_ptr(gamma)),
                                    C.c_void_p(_ptr(beta)), B, Cin, L, w.shape[0], k, stride, C.c_float(eps),
                                    C.c_void_p(_ptr(moments)), C.c_void_p(_ptr(stats)), C.c_void_p(_ptr(out)),
-                                   C.c_void_p(_ptr(dgelu)), _stream()))
+                                   None, _stream()))
 
 
-def conv0_bwd(x, w, gamma, beta, moments, stats, dy, dgelu, red_scratch, dw, dgamma, dbeta, k: int = 10, stride: int = 5,
+def conv0_bwd(x, w, gamma, beta, moments, stats, dy, red_scratch, dw, dgamma, dbeta, k: int = 10, stride: int = 5,
               eps: float = 1e-5) -> None:
+    """Backward of conv0_fwd from dy (bf16 [B, L_out, C]); GELU' is recomputed from x, nothing else is read."""
     B, Cin, L = x.shape
     assert red_scratch.dtype == torch.float32 and red_scratch.numel() >= B * (2 + Cin * 10) * w.shape[0]
-    assert dgelu.dtype == torch.bfloat16 and dgelu.shape == dy.shape and dgelu.is_contiguous() and dy.is_contiguous()
+    assert dy.dtype == torch.bfloat16 and dy.is_contiguous()
     lib = _lib.load()
     p = lambda t: C.c_void_p(_ptr(t))
+    if _lib._profile is not None:
+        _lib._profile.nbytes = B * Cin * L * 2 + dy.numel() * 2
     check(lib.wj_conv0_gn_gelu_bwd(p(x), p(w), p(gamma), p(beta), B, Cin, L, w.shape[0], k, stride, C.c_float(eps),
-                                   p(moments), p(stats), p(dy), p(dgelu), p(red_scratch), p(dw), p(dgamma), p(dbeta),
+                                   p(moments), p(stats), p(dy), None, p(red_scratch), p(dw), p(dgamma), p(dbeta),
                                    _stream()))
 
 
@@ -289,6 +301,7 @@ def layernorm_fwd(x: torch.Tensor, gamma, beta, eps: float, out_f32=None, out_bf
     p = lambda t: C.c_void_p(_ptr(t))
     if _lib._profile is not None:
         _lib._profile.meta = (0.0, M, D, str(x.dtype)[6:], out_f32 is not None, out_bf16 is not None)
+        _lib._profile.nbytes = M * D * (x.element_size() + 4 * (out_f32 is not None) + 2 * (out_bf16 is not None))
     check(lib.wj_layernorm_fwd(p(x), 1 if x.dtype == torch.bfloat16 else 0, p(gamma), p(beta), C.c_float(eps), M, D,
                                p(out_f32), p(out_bf16), p(stats), p(rowsum), _stream()))
 
@@ -301,6 +314,7 @@ def layernorm_bwd(dy: torch.Tensor, x: torch.Tensor, stats, gamma, dx_f32=None, 
     p = lambda t: C.c_void_p(_ptr(t))
     if _lib._profile is not None:
         _lib._profile.meta = (0.0, M, D, colsum is not None)
+        _lib._profile.nbytes = M * D * (4 + x.element_size() + 4 * (dx_f32 is not None) + 2 * (dx_bf16 is not None))
     check(lib.wj_layernorm_bwd(p(dy), p(x), 1 if x.dtype == torch.bfloat16 else 0, p(stats), p(gamma), M, D, p(dx_f32),
                                p(dx_bf16), p(dgamma), p(dbeta), p(colsum), _stream()))
 
@@ -315,6 +329,7 @@ def add_layernorm_fwd(x: torch.Tensor, add: Optional[torch.Tensor], gamma, beta,
     p = lambda t: C.c_void_p(_ptr(t))
     if _lib._profile is not None:
         _lib._profile.meta = (0.0, M, D, add is not None, out_f32 is not None, out_bf16 is not None)
+        _lib._profile.nbytes = M * D * (4 + 2 * (add is not None) + 4 * (out_f32 is not None) + 2 * (out_bf16 is not None))
     check(lib.wj_add_layernorm_fwd(p(x), p(add), p(gamma), p(beta), C.c_float(eps), M, D, p(out_f32), p(out_bf16),
                                    p(stats), p(rowsum), _stream()))
 
@@ -332,6 +347,8 @@ def add_layernorm_bwd(dy_f32: Optional[torch.Tensor], dy_bf16: Optional[torch.Te
     p = lambda t: C.c_void_p(_ptr(t))
     if _lib._profile is not None:
         _lib._profile.meta = (0.0, M, D, dy_f32 is not None, dy_bf16 is not None, colsum is not None)
+        _lib._profile.nbytes = M * D * (4 * (dy_f32 is not None) + 2 * (dy_bf16 is not None) + 4 + 2 * (add is not None) +
+                                        4 * (dx_f32 is not None) + 2 * (dx_bf16 is not None))
     check(lib.wj_add_layernorm_bwd(p(dy_f32), p(dy_bf16), p(x), p(add), p(stats), p(gamma), M, D, p(dx_f32), p(dx_bf16),
                                    p(dgamma), p(dbeta), p(colsum), _stream()))
 
@@ -350,6 +367,9 @@ def crop_norm(audio: torch.Tensor, starts: Optional[torch.Tensor], crops_per_cli
     assert audio.dtype == torch.float32 and audio.is_contiguous()
     lib = _lib.load()
     p = lambda t: C.c_void_p(_ptr(t))
+    if _lib._profile is not None:   # crop read 3x by design? no: algorithmic = read the crops once, write them once
+        n_out = n_clips * crops_per_clip * ch * crop_len
+        _lib._profile.nbytes = n_out * (4 + 2 * (out_bf16 is not None) + 4 * (out_f32 is not None))
     check(lib.wj_crop_norm(p(audio), p(starts), p(gain), n_clips, ch, C.c_int64(clip_len), crops_per_clip, crop_len,
                            p(out_bf16), p(out_f32), _stream()))
 
@@ -375,6 +395,8 @@ def target_accum(x: torch.Tensor, rowsum, B: int, T: int, D: int, scale: float, 
                  eps: float = 1e-5):
     lib = _lib.load()
     p = lambda t: C.c_void_p(_ptr(t))
+    if _lib._profile is not None:   # read x, read-modify-write targets (write only for the first layer)
+        _lib._profile.nbytes = B * T * D * (4 + (4 if first else 8))
     check(lib.wj_target_accum(p(x), p(rowsum), B, T, D, C.c_float(eps), C.c_float(scale), 1 if first else 0,
                               p(inst_stats), p(targets), _stream()))
 
@@ -429,6 +451,8 @@ def predictor_assemble_bwd(dx0, vis_src, N: int, D: int, d_ctx, d_mask_token):
 def masked_mse(pred_bf16, targets, tgt_rows, Nt: int, D: int, loss, dpred_bf16=None):
     lib = _lib.load()
     p = lambda t: C.c_void_p(_ptr(t))
+    if _lib._profile is not None:
+        _lib._profile.nbytes = Nt * D * (2 + 4 + 2 * (dpred_bf16 is not None))
     check(lib.wj_masked_mse(p(pred_bf16), p(targets), p(tgt_rows), Nt, D, p(loss), p(dpred_bf16), _stream()))
 
 
@@ -436,6 +460,8 @@ def ema_update(teacher_flat: torch.Tensor, student_flat: torch.Tensor, decay: fl
     assert teacher_flat.numel() == student_flat.numel()
     lib = _lib.load()
     p = lambda t: C.c_void_p(_ptr(t))
+    if _lib._profile is not None:
+        _lib._profile.nbytes = teacher_flat.numel() * 12
     check(lib.wj_ema_update(p(teacher_flat), p(student_flat), C.c_int64(teacher_flat.numel()), C.c_double(decay),
                             _stream()))
 
@@ -443,12 +469,16 @@ def ema_update(teacher_flat: torch.Tensor, student_flat: torch.Tensor, decay: fl
 def sumsq(x: torch.Tensor, scale: float, out_f64: torch.Tensor):
     lib = _lib.load()
     p = lambda t: C.c_void_p(_ptr(t))
+    if _lib._profile is not None:
+        _lib._profile.nbytes = x.numel() * 4
     check(lib.wj_sumsq(p(x), C.c_int64(x.numel()), C.c_float(scale), p(out_f64), _stream()))
 
 
 def adamw_step(p_, g, m, v, lr, beta1, beta2, eps, wd, step, grad_scale=1.0, max_norm=0.0, grad_sumsq=None, p_bf16=None):
     lib = _lib.load()
     p = lambda t: C.c_void_p(_ptr(t))
+    if _lib._profile is not None:
+        _lib._profile.nbytes = p_.numel() * (28 + 2 * (p_bf16 is not None))
     check(lib.wj_adamw_step(p(p_), p(g), p(m), p(v), C.c_int64(p_.numel()), C.c_float(lr), C.c_float(beta1),
                             C.c_float(beta2), C.c_float(eps), C.c_float(wd), int(step), C.c_float(grad_scale),
                             C.c_float(max_norm), p(grad_sumsq), p(p_bf16), _stream()))
@@ -460,6 +490,8 @@ def adamw_ema_step(p_, g, m, v, lr, beta1, beta2, eps, wd, step, grad_scale, max
     lib = _lib.load()
     p = lambda t: C.c_void_p(_ptr(t))
     assert teacher.numel() == ema_hi - ema_lo
+    if _lib._profile is not None:   # p, m, v read+write, g read, bf16 copy; teacher read+write + bf16 copy
+        _lib._profile.nbytes = p_.numel() * (28 + 2 * (p_bf16 is not None)) + teacher.numel() * (8 + 2 * (teacher_bf16 is not None))
     check(lib.wj_adamw_ema_step(p(p_), p(g), p(m), p(v), C.c_int64(p_.numel()), C.c_float(lr), C.c_float(beta1),
                                 C.c_float(beta2), C.c_float(eps), C.c_float(wd), int(step), C.c_float(grad_scale),
                                 C.c_float(max_norm), p(grad_sumsq), p(p_bf16), p(teacher), p(teacher_bf16),
@@ -478,6 +510,7 @@ def colsum(x: torch.Tensor, out: torch.Tensor, M: Optional[int] = None):
     p = lambda t: C.c_void_p(_ptr(t))
     if _lib._profile is not None:
         _lib._profile.meta = (0.0, M, x.shape[1], str(x.dtype)[6:])
+        _lib._profile.nbytes = M * x.shape[1] * x.element_size()
     check(lib.wj_colsum(p(x), 1 if x.dtype == torch.bfloat16 else 0, C.c_int64(M), x.shape[1], C.c_int64(x.stride(0)),
                         p(out), _stream()))
 
