@@ -208,6 +208,13 @@ int wj_attn_varlen_bwd(const void* qkv_bf16, const void* out_bf16, const void* d
                        const int* cu_seqlens, int n_seqs, int max_len, int64_t total_tokens, int D, int H,
                        void* dqkv_bf16, void* stream);
 
+/* The same backward with the bias gradient of the in_proj Linear folded in: dbias[3 D] += column sums of the stored
+ * (bf16) dqkv rows -- in the tcgen05 kernel's epilogue (head dim 32, <= 128 tokens, D <= 384), otherwise by a wj_colsum
+ * pass after the mma.sync kernel.  dbias may be NULL. */
+int wj_attn_varlen_bwd_bias(const void* qkv_bf16, const void* out_bf16, const void* dout_bf16, const float* lse2,
+                            const int* cu_seqlens, int n_seqs, int max_len, int64_t total_tokens, int D, int H,
+                            void* dqkv_bf16, float* dbias, void* stream);
+
 /* Row gather: out[i, :] = src[idx[i], :] (idx NULL = identity, i.e. a cast); fp32 and/or bf16 outputs.
  * contextual_features[~ctx_masks] (wavjepa/jepa.py:399). */
 int wj_gather_rows(const void* src, int src_is_bf16, const int* idx, int N, int D, float* out_f32, void* out_bf16,

@@ -438,6 +438,13 @@ def test_attention_fwd_bwd(D, H, lens):
     dqkv = torch.full((tot, 3 * D), float("nan"), device=DEV, dtype=torch.bfloat16)
     ops.attn_bwd(qkv, out, do, lse, cu, len(lens), max(lens), D, H, dqkv)
     assert rel(dqkv, qr.grad) < 1.5e-2
+    # the same call with the in_proj bias gradient (column sums of the stored dqkv) folded in: identical dqkv
+    dq2 = torch.full((tot, 3 * D), float("nan"), device=DEV, dtype=torch.bfloat16)
+    db = torch.ones(3 * D, device=DEV)
+    ops.attn_bwd(qkv, out, do, lse, cu, len(lens), max(lens), D, H, dq2, dbias=db)
+    assert torch.equal(dq2, dqkv)
+    cs = dqkv.float().sum(0)
+    assert (db - 1.0 - cs).abs().max().item() <= 2e-3 * cs.abs().max().item() + 1e-3
 
 
 # ------------------------------------------------------------------------------------------------------- elementwise

@@ -393,20 +393,27 @@ extern "C" int wj_attn_varlen_fwd(const void* qkv_bf16, const int* cu_seqlens, i
 
 namespace wj {
 int attn_bwd_tc_launch(const void* qkv, const void* out, const void* dout, const float* lse2, const int* cu, int n_seqs,
-                       int max_len, long long total_tokens, int D, int H, void* dqkv, cudaStream_t st);
+                       int max_len, long long total_tokens, int D, int H, void* dqkv, float* dbias, cudaStream_t st);
 }
 
 extern "C" int wj_attn_varlen_bwd(const void* qkv_bf16, const void* out_bf16, const void* dout_bf16, const float* lse2,
                                   const int* cu_seqlens, int n_seqs, int max_len, int64_t total_tokens, int D, int H,
                                   void* dqkv_bf16, void* stream) {
+  return wj_attn_varlen_bwd_bias(qkv_bf16, out_bf16, dout_bf16, lse2, cu_seqlens, n_seqs, max_len, total_tokens, D, H,
+                                 dqkv_bf16, nullptr, stream);
+}
+
+extern "C" int wj_attn_varlen_bwd_bias(const void* qkv_bf16, const void* out_bf16, const void* dout_bf16,
+                                       const float* lse2, const int* cu_seqlens, int n_seqs, int max_len,
+                                       int64_t total_tokens, int D, int H, void* dqkv_bf16, float* dbias, void* stream) {
   if (n_seqs <= 0 || max_len <= 0) return WJ_OK;
   const int dh = D / H;
   if (D % H != 0 || (dh != 32 && dh != 64)) { set_error("wj_attn_varlen_bwd: head dim must be 32 or 64"); return WJ_ERR_ARG; }
   {
     // head dim 32, <= 128 tokens: tcgen05 kernel (attention_tc.cu); everything else: the mma.sync kernel below
     const int rc = wj::attn_bwd_tc_launch(qkv_bf16, out_bf16, dout_bf16, lse2, cu_seqlens, n_seqs, max_len, total_tokens, D, H,
-                                          dqkv_bf16, WJ_STREAM(stream));
-    if (rc <= 0) return rc;
+                                          dqkv_bf16, dbias, WJ_STREAM(stream));
+    if (rc <= 0) return rc;   // (the tcgen05 kernel forms the column sums in its epilogue)
   }
   const int npad = (max_len + 15) & ~15;
   const size_t smem = static_cast<size_t>(4) * npad * (dh + 8) * 2 + static_cast<size_t>(2) * ((npad + 63) & ~63) * 4;
@@ -428,5 +435,7 @@ extern "C" int wj_attn_varlen_bwd(const void* qkv_bf16, const void* out_bf16, co
     if (e != cudaSuccess) { set_error("attn_bwd attr: %s", cudaGetErrorString(e)); return WJ_ERR_RUNTIME; }
     attn_bwd_kernel<32><<<grid, 128, smem, WJ_STREAM(stream)>>>(q, o, d_o, lse2, cu_seqlens, D, H, npad, scale, scale_log2, dq);
   }
-  return check_launch("attn_varlen_bwd");
+  const int rc = check_launch("attn_varlen_bwd");
+  if (rc != WJ_OK || dbias == nullptr) return rc;
+  return wj_colsum(dqkv_bf16, 1, total_tokens, 3 * D, 3 * D, dbias, stream);
 }

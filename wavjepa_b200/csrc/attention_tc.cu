@@ -338,6 +338,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const AttnTcParams p
 //        (TMEM columns [0,32), [32,64), [64,96) over the consumed S block)
 //   epilogue: rows < n of dQ*scale, dK*scale, dV -> dqkv[token, {0, D, 2D} + head*32 ...], transposed through the
 //        warp's own (consumed) corner of the P tile so that four lanes store one 64-byte row
+//        optionally the column sums of the stored rows (the bias gradient of the in_proj Linear, which autograd takes
+//        over the bf16 dqkv): 5-step reduce-scatter across the warp's 32 rows, shared-memory accumulators [3 D] per CTA,
+//        one global atomic per column per CTA at the end -- replaces a separate pass over dqkv (398 MB per layer)
 //   delta: the O tile rides along with the TMA loads; every gradient thread reduces its own row of O * dO out of
 //        smem while the S / dP products run.  lse is fetched one item ahead into a register.
 //
@@ -351,12 +354,15 @@ struct AttnBwdParams {
   const bf16* dout;
   const float* lse2;
   bf16* dqkv;
+  float* dbias;   // optional [3 D]: += column sums of the stored dqkv rows (the in_proj bias gradient)
 };
 
 constexpr int kBwdTile = kAtQ * 32 * 2;                  // 8 KB: [128 x 32] bf16, 64B swizzle
 constexpr int kBwdPs = 2 * kAtQ * 128;                   // 32 KB: [2 key blocks][128 queries][64 keys] bf16, 128B swizzle
 constexpr int kBwdBarOff = 5 * kBwdTile + 2 * kBwdPs;    // Q | K | V | dO | O | P | dS | barriers
-constexpr int kBwdSmem = kBwdBarOff + 128 + 1024;
+constexpr int kBwdCsOff = kBwdBarOff + 128;             // fp32 [3 D] column sums of this CTA's items (D <= kBwdCsMaxD)
+constexpr int kBwdCsMaxD = 384;
+constexpr int kBwdSmem = kBwdCsOff + 3 * kBwdCsMaxD * 4 + 1024;
 
 __global__ void __launch_bounds__(288, 2) attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
                                                              const __grid_constant__ CUtensorMap tmDO,
@@ -373,7 +379,10 @@ __global__ void __launch_bounds__(288, 2) attn_bwd_tc_kernel(const __grid_consta
   uint64_t* bar_g = bar_load + 3;      // dV, dK, dQ complete
   uint64_t* bar_done = bar_load + 4;   // gradients read out of TMEM (8 warps)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_load + 5);
+  float* s_cs = reinterpret_cast<float*>(smem + kBwdCsOff);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (p.dbias != nullptr)
+    for (int i = threadIdx.x; i < 3 * p.D; i += blockDim.x) s_cs[i] = 0.f;
 
   if (warp == 8) {
     if (lane == 0) {
@@ -560,6 +569,28 @@ __global__ void __launch_bounds__(288, 2) attn_bwd_tc_kernel(const __grid_consta
             w.z = pack_bf16x2(__uint_as_float(g[8 * q + 4]) * sc, __uint_as_float(g[8 * q + 5]) * sc);
             w.w = pack_bf16x2(__uint_as_float(g[8 * q + 6]) * sc, __uint_as_float(g[8 * q + 7]) * sc);
             *reinterpret_cast<uint4*>(stage + t * 2048 + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4)) = w;
+            if (p.dbias != nullptr) {   // keep the values as stored (bf16) for the column sums
+              g[8 * q] = w.x << 16; g[8 * q + 1] = w.x & 0xffff0000u; g[8 * q + 2] = w.y << 16; g[8 * q + 3] = w.y & 0xffff0000u;
+              g[8 * q + 4] = w.z << 16; g[8 * q + 5] = w.z & 0xffff0000u; g[8 * q + 6] = w.w << 16; g[8 * q + 7] = w.w & 0xffff0000u;
+            }
+          }
+          if (p.dbias != nullptr) {
+            // rows >= n hold stale bits (key chunks past the sequence are never written to the P / dS tiles): select
+            float c32[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) c32[j] = live ? __uint_as_float(g[j]) : 0.f;
+#pragma unroll
+            for (int sft = 16; sft >= 1; sft >>= 1) {
+              const bool up = (lane & sft) != 0;
+#pragma unroll
+              for (int i = 0; i < sft; ++i) {
+                const float mine = up ? c32[sft + i] : c32[i];
+                const float other = up ? c32[i] : c32[sft + i];
+                c32[i] = mine + __shfl_xor_sync(0xffffffffu, other, sft);
+              }
+            }
+            const int col = half == 0 ? (t == 0 ? 0 : 2 * p.D) : p.D;
+            atomicAdd(s_cs + col + head * DH + lane, c32[0]);
           }
         }
       }
@@ -588,6 +619,8 @@ __global__ void __launch_bounds__(288, 2) attn_bwd_tc_kernel(const __grid_consta
   }
   tc_fence_before();
   __syncthreads();
+  if (p.dbias != nullptr)
+    for (int i = threadIdx.x; i < 3 * p.D; i += blockDim.x) atomicAdd(p.dbias + i, s_cs[i]);
   if (warp == 8) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 256);
@@ -642,9 +675,10 @@ int attn_fwd_tc_launch(const void* qkv, const int* cu, int n_seqs, int max_len, 
 
 // Returns WJ_OK and launches when the problem fits (head dim 32, <= 128 tokens); 1 -> caller uses the mma.sync kernel.
 int attn_bwd_tc_launch(const void* qkv, const void* out, const void* dout, const float* lse2, const int* cu, int n_seqs,
-                       int max_len, long long total_tokens, int D, int H, void* dqkv, cudaStream_t st) {
+                       int max_len, long long total_tokens, int D, int H, void* dqkv, float* dbias, cudaStream_t st) {
   const int dh = D / H;
   if (max_len > 128 || dh != 32 || D % 8 != 0 || total_tokens <= 0) return 1;
+  if (dbias != nullptr && D > kBwdCsMaxD) return 1;   // (no room for the column-sum accumulators: the caller sums separately)
   static PFN_encodeTiledA enc = nullptr;
   if (enc == nullptr) {
     void* sym = nullptr;
@@ -679,6 +713,7 @@ int attn_bwd_tc_launch(const void* qkv, const void* out, const void* dout, const
   p.scale_log2 = p.scale * 1.4426950408889634f;
   p.out = reinterpret_cast<const bf16*>(out); p.dout = reinterpret_cast<const bf16*>(dout); p.lse2 = lse2;
   p.dqkv = reinterpret_cast<bf16*>(dqkv);
+  p.dbias = dbias;
   cudaError_t e = cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem);
   if (e != cudaSuccess) { set_error("attn_bwd_tc attr: %s", cudaGetErrorString(e)); return WJ_ERR_RUNTIME; }
   int grid = 2 * sm_count();

@@ -129,8 +129,7 @@ class TransformerStack:
             datt = _empty((M, d), bf, dev)
             ops.gemm_dgrad(ops.plain_operand(dy1_16), w.w_o, M, 1, datt, K=d, N=d)
             dqkv = _empty((M, 3 * d), bf, dev)
-            ops.attn_bwd(s.qkv, s.att, datt, s.lse, cu, n_seqs, max_len, d, H, dqkv)
-            ops.colsum(dqkv, gw.b_in)
+            ops.attn_bwd(s.qkv, s.att, datt, s.lse, cu, n_seqs, max_len, d, H, dqkv, dbias=gw.b_in)
             ops.gemm_wgrad(ops.plain_operand(dqkv), ops.plain_operand(s.x16), M, 1, gw.w_in, accumulate=True)
             dx_b = _empty((M, d), bf, dev)
             ops.gemm_dgrad(ops.plain_operand(dqkv), w.w_in, M, 1, dx_b, K=3 * d, N=d)

@@ -411,13 +411,15 @@ def attn_fwd(qkv: torch.Tensor, cu: torch.Tensor, n_seqs: int, max_len: int, D: 
     check(lib.wj_attn_varlen_fwd(p(qkv), p(cu), n_seqs, max_len, C.c_int64(qkv.shape[0]), D, H, p(out), p(lse2), _stream()))
 
 
-def attn_bwd(qkv, out, dout, lse2, cu, n_seqs: int, max_len: int, D: int, H: int, dqkv):
+def attn_bwd(qkv, out, dout, lse2, cu, n_seqs: int, max_len: int, D: int, H: int, dqkv, dbias=None):
+    """dbias (optional, fp32 [3 D]) += column sums of dqkv: the in_proj bias gradient, formed in the kernel's epilogue."""
     lib = _lib.load()
     p = lambda t: C.c_void_p(_ptr(t))
     if _lib._profile is not None:
         _lib._profile.meta = (0.0, n_seqs, max_len, D, H, qkv.shape[0])
-    check(lib.wj_attn_varlen_bwd(p(qkv), p(out), p(dout), p(lse2), p(cu), n_seqs, max_len, C.c_int64(qkv.shape[0]), D, H,
-                                 p(dqkv), _stream()))
+    assert dbias is None or (dbias.dtype == torch.float32 and dbias.numel() == 3 * D)
+    check(lib.wj_attn_varlen_bwd_bias(p(qkv), p(out), p(dout), p(lse2), p(cu), n_seqs, max_len, C.c_int64(qkv.shape[0]),
+                                      D, H, p(dqkv), p(dbias), _stream()))
 
 
 # ----------------------------------------------------------------------------------------------------- misc
