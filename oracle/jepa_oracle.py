@@ -327,6 +327,56 @@ def hear_timestamp_embeddings(audio: torch.Tensor, sd, cfg: Cfg, sr: int = 16000
     return emb, ts
 
 
+def hear_nat_feature(audio: torch.Tensor) -> torch.Tensor:
+    """feature_helper.py:27-88 with in_channels = 2, for a batch [B, L] / [B, C, L]: loudness over the whole (C, L) clip,
+    mono duplicated (:57-58), stereo kept (:68-69), first of four channels duplicated (:75-77)."""
+    out = []
+    for a in audio:
+        if a.ndim == 1:
+            a = a.unsqueeze(0)
+        rms = torch.sqrt(torch.mean(a ** 2))
+        if rms != 0:
+            a = a * 10 ** ((-14.0 - 20 * torch.log10(rms)) / 20)
+        if a.shape[0] == 1:
+            a = torch.cat((a, a), dim=0)
+        elif a.shape[0] == 4:
+            a = torch.cat((a[:1], a[:1]), dim=0)
+        out.append(a)
+    return torch.stack(out)
+
+
+def hear_nat_timestamp_embeddings(audio: torch.Tensor, sd, cfg: Cfg, sr: int = 16000):
+    """hear_api/runtime_natjepa.py:102-151 (RuntimeNatJEPA.get_timestamp_embeddings) for the 2-channel model (cfg.per_channel,
+    cfg.in_channels == 2): chunks normalised over (C, T) jointly (:12-16), the time mask repeated over the channel-major
+    tokens (`B E -> B (C E)`, :142), per-channel embeddings averaged (`B (C S) E -> B C S E`, mean over C, :144-147)."""
+    B = audio.shape[0]
+    C = cfg.in_channels
+    unit = cfg.target_length
+    steps = cfg.total_patches // C          # tokens per channel (:83-86)
+    x = hear_nat_feature(audio)
+    L = x.shape[-1]
+    pad, n_chunks, cut_off, _ = hear_geometry(L, unit, sr, steps)
+    x = F.pad(x, (0, pad))
+    total_steps = steps * int(((L + pad) / sr) / (unit // sr))
+    mask = torch.zeros(B, max(total_steps, n_chunks * steps), dtype=torch.bool)
+    mask[:, cut_off:total_steps] = True
+    embs = []
+    for i in range(n_chunks):
+        chunk = x[..., i * unit:(i + 1) * unit]
+        mu = chunk.mean(dim=(-2, -1), keepdim=True)
+        sdv = chunk.std(dim=(-2, -1), keepdim=True)
+        chunk = (chunk - mu) / (sdv + 1e-5)
+        m = mask[:, i * steps:(i + 1) * steps].repeat(1, C)
+        loc = local_features(chunk, sd, cfg)
+        e = run_stack(loc, sd, "encoder", cfg.layers, cfg.nhead, m)
+        embs.append(e.view(B, C, steps, -1).mean(dim=1))
+    emb = torch.cat(embs, dim=1)[:, :cut_off]
+    n = emb.shape[1]
+    step_ms = (L / sr) / n * 1000
+    ts = torch.tensor([step_ms * i for i in range(n)]).unsqueeze(0).repeat(B, 1)
+    return emb, ts
+
+
 def arch_get_embeddings(audio: torch.Tensor, sd, cfg: Cfg, sr: int = 16000) -> torch.Tensor:
     """ARCH/configs/wavjepa_wrapper.py:67-110 for one clip [L]: loudness-normalise, pad, per-chunk normalise + encode with
     the padded frames key-masked, keep the unmasked frames, mean over all kept frames -> [D]."""

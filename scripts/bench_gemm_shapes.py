@@ -87,6 +87,13 @@ if "--pair" in sys.argv:
         run(f"{tag} pred fc1 plain", 172433, 1536, 384, bn=bn)
         run(f"{tag} pred fc1 gelu+save", 172433, 1536, 384, act=1, out2=True, bn=bn)
         run(f"{tag} conv-like M1.6M N512 K1536", 1645568, 512, 1536, act=1, bias=False, bn=bn, reps=5)
+        run(f"{tag} conv-like gelu+save", 1645568, 512, 1536, act=1, out2=True, bias=False, bn=bn, reps=5)
+        run(f"{tag} conv2-like gelu+save", 822272, 512, 1536, act=1, out2=True, bias=False, bn=bn, reps=5)
+        run(f"{tag} teacher fc2 plain bf16", 102400, 768, 3072, bn=bn)
+        run(f"{tag} teacher outproj plain bf16", 102400, 768, 768, bn=bn)
+        run(f"{tag} student fc1 gelu+save", 19906, 3072, 768, act=1, out2=True, bn=bn)
+        run(f"{tag} student fc2 plain", 19906, 768, 3072, bn=bn)
+        run(f"{tag} student qkv plain", 19906, 2304, 768, bn=bn)
     for bn in (0, -128):
         tag = "pair128" if bn < 0 else "1cta"
         run(f"{tag} pred qkv plain", 172433, 1152, 384, bn=bn)

@@ -157,6 +157,39 @@ def golden_hear():
     np.savez_compressed(os.path.join(HERE, "hear.npz"), **out)
 
 
+def golden_hear_nat():
+    """hear_api/runtime_natjepa.py, executed: `RuntimeNatJEPA.__init__` cannot run against the JEPA of this checkout (it
+    passes in_channels= / is_spectrogram= through **kwargs into LightningModule.__init__ and later reads
+    `self.model.in_channels`, which JEPA never defines -- the file targets another revision), so the instance is assembled
+    by hand around an unmodified Nat JEPA and the UNMODIFIED get_timestamp_embeddings / get_scene_embeddings run on it."""
+    import hear_api.feature_helper as fh
+    import hear_api.runtime_natjepa as rn
+    fh.FeatureExtractor.forward = lambda self, x: self._wav2feature(x)  # the reference hard-codes .cuda() (:87)
+    cfg = jo.Cfg(in_channels=2, per_channel=True)
+    sd = jo.make_state_dict(cfg, seed=3)
+    jepa = build_ref(cfg, sd)
+    jepa.eval()
+    jepa.in_channels = 2                     # the attribute the runtime expects (:86, :142, :145)
+    rt = object.__new__(rn.RuntimeNatJEPA)
+    torch.nn.Module.__init__(rt)
+    rt.sample_rate = 16000
+    rt.model = jepa
+    rt.unit_frames = int(2.01 * 16000)
+    rt.output_steps = jepa.extract_audio.total_patches(rt.unit_frames) // 2
+    rt.feature_extractor = fh.FeatureExtractor(in_channels=2)
+    out = {}
+    g = torch.Generator().manual_seed(17)
+    for tag, audio in (("stereo", torch.rand(2, 2, 48000, generator=g) * 2 - 1), ("mono", oi.hear_inputs(2, 40000, seed=19))):
+        emb, ts = rt.get_timestamp_embeddings(audio)
+        out[f"{tag}_emb"] = oi.subsample(emb)
+        out[f"{tag}_shape"] = np.asarray(emb.shape)
+        out[f"{tag}_ts"] = ts[0].numpy()
+        out[f"{tag}_l2"] = np.float64(emb.norm())
+        print("hear_nat", tag, tuple(emb.shape))
+    out["stereo_scene"] = rt.get_scene_embeddings(torch.rand(2, 2, 48000, generator=torch.Generator().manual_seed(17)) * 2 - 1).numpy()
+    np.savez_compressed(os.path.join(HERE, "hear_nat.npz"), **out)
+
+
 def golden_interop():
     """Rows of SURVEY.md 8(f)-3, executed on the unmodified reference: the ARCH wrapper (with a stub `arch_eval` base
     class -- the vendored harness needs pyannote), the 7-layer wav2vec2 extractor HEAR model (process_seconds=4.02) and
@@ -282,7 +315,7 @@ def golden_denoiser():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["masks", "keys", "train", "nat", "hear", "interop", "denoiser"]
+    which = sys.argv[1:] or ["masks", "keys", "train", "nat", "hear", "hear_nat", "interop", "denoiser"]
     if "masks" in which:
         golden_masks()
     if "keys" in which:
@@ -294,6 +327,8 @@ if __name__ == "__main__":
         golden_train("train_nat", jo.Cfg(in_channels=2, per_channel=True), n_clips=1, crops=2, seed=55)
     if "hear" in which:
         golden_hear()
+    if "hear_nat" in which:
+        golden_hear_nat()
     if "interop" in which:
         golden_interop()
     if "denoiser" in which:

@@ -196,6 +196,25 @@ def test_masks_time_inverse_bit_exact():
     assert np.array_equal(att.cpu().numpy(), ra)
 
 
+def test_masks_bit_exact_100k_rows():
+    """>= 1e5 rows per masker, bit for bit against the numpy oracle (row blocks spread over the 32-bit row
+    space, including the per-rank offsets bench.py uses)."""
+    from oracle import masks_oracle as mo
+
+    T, n = 200, 25000
+    for row0 in (0, 1 << 24, 7 * (1 << 24) + 12345, (1 << 31) - n - 1):
+        ctx, tgt, vis, att, err = ops.masks_generate(0, n, T, 1, False, 4, 0.65, 10, 0.25, 10, 0.1, 0, 99, row0, DEV)
+        assert err.item() == 0
+        rc, rt, rv, ra = mo.time_inverse_masks(99, row0, n, T)
+        assert np.array_equal(ctx.cpu().numpy(), rc) and np.array_equal(tgt.cpu().numpy(), rt)
+        assert np.array_equal(vis.cpu().numpy(), rv) and np.array_equal(att.cpu().numpy(), ra)
+        ctx, tgt, vis, att, err = ops.masks_generate(1, n, T, 1, False, 4, 0.0, 1, 0.1, 10, 0.5, 5, 31, row0, DEV)
+        assert err.item() == 0
+        rc, rt, rv, ra = mo.speech_masks(31, row0, n, T, n_targets=4, tgt_prob=0.1, tgt_len=10, cutoff=0.5, min_context_len=5)
+        assert np.array_equal(ctx.cpu().numpy(), rc) and np.array_equal(tgt.cpu().numpy(), rt)
+        assert np.array_equal(vis.cpu().numpy(), rv) and np.array_equal(att.cpu().numpy(), ra)
+
+
 def test_masks_speech_and_binaural_bit_exact():
     from oracle import masks_oracle as mo
 

@@ -450,3 +450,283 @@ def test_generate_scene_cases():
     t = torchaudio.functional.resample(audio.unsqueeze(1), 32000, 16000, lowpass_filter_width=64, rolloff=0.9475937167399596,
                                        resampling_method="sinc_interp_kaiser", beta=14.769656459379492)
     assert tuple(r.shape) == tuple(t.shape) and rel(r.cpu().numpy(), t.numpy()) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------------- round-2 additions
+GRAD_CASES = [("audioset", dict(), 3, 2024), ("librispeech", dict(), 2, 77), ("audioset", dict(in_channels=2, per_channel=True), 2, 5)]
+
+
+@pytest.mark.parametrize("masker,cfgkw,crops,seed", GRAD_CASES)
+def test_every_parameter_gradient_elementwise_against_live_oracle(masker, cfgkw, crops, seed):
+    """Direction, not only norm: the FULL gradient tensor of EVERY trainable parameter (rel-L2 over all elements) against
+    the fp32 CPU oracle (itself pinned to the executed reference by tests/golden) on inputs that are not in the fixtures.
+    The key third of in_proj_bias has an exactly-zero true gradient (softmax is invariant to a constant key shift); both
+    sides only hold rounding noise there, so it is compared as part of the whole bias tensor."""
+    torch.set_num_threads(os.cpu_count())
+    cfg = jo.Cfg(**cfgkw)
+    sd = jo.make_state_dict(cfg, seed=seed)
+    inp = oi.training_inputs(cfg, 1, crops, seed=seed, masker=masker)
+    ref_sd = {k: v.clone().requires_grad_(not k.startswith(("teacher_encoder.", "pos_encoding"))) for k, v in sd.items()}
+    ref = jo.forward(inp["audio"], inp["ctx_masks"], inp["target_indices"], inp["ctx_and_target_masks"], ref_sd, cfg)
+    ref["loss"].backward()
+    model = build_model(cfg, sd)
+    c_m, t_m, v_m = (inp[k].to(DEV) for k in ("ctx_masks", "target_indices", "ctx_and_target_masks"))
+    out = model(inp["audio"].to(DEV).bfloat16(), c_m, t_m, v_m)
+    assert abs(out["loss"].item() - ref["loss"].item()) / ref["loss"].item() < LOSS_TOL
+    out["loss"].backward()
+    worst, n_checked = ("", 0.0), 0
+    for n_, p_ in model.named_parameters():
+        if not p_.requires_grad:
+            continue
+        g_ref = ref_sd[n_].grad
+        assert g_ref is not None and p_.grad is not None, n_
+        e = rel(p_.grad.cpu().numpy(), g_ref.numpy())
+        worst = max(worst, (n_, e), key=lambda t: t[1])
+        n_checked += 1
+        assert e < GRAD_TOL, (n_, e)
+    assert n_checked >= 300, n_checked
+    print(f"worst per-tensor gradient rel-L2: {worst}")
+
+
+def test_parity_at_b512_on_sampled_instances():
+    """BASELINE.json configs[1] size (512 instances): instances are independent, so the features / targets / predictions
+    of a few instances of the full batch must equal the oracle run on just those instances."""
+    torch.set_num_threads(os.cpu_count())
+    cfg = jo.Cfg()
+    sd = jo.make_state_dict(cfg, seed=8)
+    B = 512
+    g = torch.Generator().manual_seed(123)
+    audio = torch.randn(B, 1, cfg.target_length, generator=g).bfloat16()
+    mk = w.TimeInverseBlockMasker(4, 0.65, 10, 0.25, 10, 0.1, seed=4, row0=0)
+    c_m, t_m, v_m = mk(batch_size=B, n_times=200, in_channels=1)
+    model = build_model(cfg, sd)
+    with torch.no_grad():
+        out = model(audio.to(DEV), c_m, t_m, v_m)
+    pick = [0, 137, 300, 511]
+    with torch.no_grad():
+        ref = jo.forward(audio[pick].float(), c_m[pick].cpu(), t_m[pick].cpu(), v_m[pick].cpu(), sd, cfg)
+    assert rel(out["local_features"][pick].cpu().numpy(), ref["local_features"].numpy()) < FEAT_TOL
+    assert rel(out["targets"][pick].cpu().numpy(), ref["targets"].numpy()) < FEAT_TOL
+    G, T = t_m.shape[1], t_m.shape[2]
+    ours = out["preds"].view(B, G, T, -1)[pick][t_m[pick]].float().cpu().numpy()
+    theirs = ref["preds"].view(len(pick), G, T, -1)[t_m[pick].cpu()].numpy()
+    assert rel(ours, theirs) < FEAT_TOL
+    assert torch.isfinite(out["loss"]).item()
+
+
+def test_optimizer_state_round_trip():
+    """a fused-path run must be resumable.  checkpoint() after two steps -> load_checkpoint() into a fresh
+    model -> the third step matches the uninterrupted run (same LR / EMA schedule position, same Adam moments)."""
+    cfg = jo.Cfg()
+    sd = jo.make_state_dict(cfg, seed=21)
+    inp = oi.training_inputs(cfg, 1, 2, seed=9, masker="audioset")
+    audio = inp["audio"].to(DEV).bfloat16()
+    c_m, t_m, v_m = (inp[k].to(DEV) for k in ("ctx_masks", "target_indices", "ctx_and_target_masks"))
+    a = build_model(cfg, sd)
+    a.global_step = 60000
+    for _ in range(2):
+        a.train_step(audio, c_m, t_m, v_m)
+    ck = a.checkpoint()
+    assert ck["global_step"] == 60002 and len(ck["optimizer_states"][0]["state"]) == len(a._train_names)
+    b = build_model(cfg, None)
+    b.load_checkpoint(ck)
+    assert b.global_step == 60002
+    assert torch.equal(b._adam_m, a._adam_m) and torch.equal(b._adam_v, a._adam_v)
+    # .to() of an already-initialised model keeps the moments (they used to be dropped with the flat buffers)
+    m_before = b._adam_m.clone()
+    b.to("cpu")
+    b.to(DEV)
+    b._ensure_ready()
+    assert b._adam_m is not None and torch.equal(b._adam_m, m_before)
+    la = a.train_step(audio, c_m, t_m, v_m)
+    lb = b.train_step(audio, c_m, t_m, v_m)
+    assert abs(la.item() - lb.item()) < 1e-5
+    pa, pb = dict(a.named_parameters()), dict(b.named_parameters())
+    for n_ in pa:   # (fp32 atomics in two backward kernels make two runs differ by rounding noise, not more)
+        d = (pa[n_].detach() - pb[n_].detach()).abs().max().item()
+        assert d <= 1e-5 * (pa[n_].detach().abs().max().item() + 1e-12) + 1e-8, (n_, d)
+    ta, tb = dict(a.teacher_encoder.named_parameters()), dict(b.teacher_encoder.named_parameters())
+    for n_ in ta:
+        assert torch.allclose(ta[n_], tb[n_], rtol=0, atol=1e-7), n_
+    # a restart WITHOUT the optimizer state is visibly different (this is what the API prevents)
+    c = build_model(cfg, {k: v for k, v in ck["state_dict"].items()})
+    assert c.global_step == 0 and c.lr_at(c.global_step) == 0.0
+
+
+def test_stock_optimizer_path_advances_global_step():
+    """forward() + loss.backward() + configure_optimizers(): without a Lightning trainer the optimizer's step
+    hook advances global_step, so the EMA decay anneals (wavjepa/jepa.py:186-191)."""
+    cfg = jo.Cfg()
+    model = build_model(cfg, jo.make_state_dict(cfg, seed=1))
+    inp = oi.training_inputs(cfg, 1, 2, seed=3, masker="audioset")
+    c_m, t_m, v_m = (inp[k].to(DEV) for k in ("ctx_masks", "target_indices", "ctx_and_target_masks"))
+    opt = model.configure_optimizers()["optimizer"]
+    d0 = model._get_ema_decay()
+    for _ in range(2):
+        out = model.training_step((inp["audio"].to(DEV).bfloat16(), c_m, t_m, v_m), 0)
+        out["loss"].backward()
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+    assert model.global_step == 2 and model._get_ema_decay() > d0
+
+
+def test_denoiser_default_clip_is_the_reference_trainers():
+    """the reference trains the denoiser stage with gradient_clip_val=1.0 (denoise.py:125-126).  The fused
+    step == clip_grad_norm_(1.0) + torch.optim.AdamW on the same gradients."""
+    m = _denoiser(0.25, nr=2)
+    assert m._core.grad_clip == 1.0
+    m.global_step = 5000
+    g = torch.Generator().manual_seed(3)
+    clean = torch.randn(4, 1, 32159, generator=g).bfloat16().to(DEV)
+    gen = (clean.float() + 0.5 * torch.randn(4, 1, 32159, generator=g).to(DEV)).bfloat16()
+    before = {n: p.detach().clone() for n, p in m.named_parameters() if p.requires_grad and not n.startswith("teacher.")}
+    _, grads = m.forward_backward(gen, clean)
+    grads = {n: gr.clone() for n, gr in grads.items()}
+    total = torch.sqrt(sum((gr.double() ** 2).sum() for gr in grads.values())).item()
+    assert total > 1.0, "the test needs a gradient norm above the clip value"
+    twins = {n: torch.nn.Parameter(before[n].clone()) for n in grads}
+    for n, gr in grads.items():
+        twins[n].grad = gr.clone()
+    opt = torch.optim.AdamW(list(twins.values()), lr=m.lr_at(5000), betas=m.hparams.adam_betas, eps=m.hparams.adam_eps,
+                            weight_decay=m.hparams.adam_weight_decay)
+    for p_ in twins.values():
+        opt.state[p_] = dict(step=torch.tensor(5000.0), exp_avg=torch.zeros_like(p_), exp_avg_sq=torch.zeros_like(p_))
+    torch.nn.utils.clip_grad_norm_(list(twins.values()), 1.0)
+    opt.step()
+    m.train_step(gen, clean)
+    now = dict(m.named_parameters())
+    for n in grads:   # (the second backward differs from the first by atomics noise only)
+        d = (now[n].detach() - twins[n].detach()).abs().max().item()
+        assert d <= 1e-2 * m.lr_at(5000) + 2e-6 * twins[n].detach().abs().max().item(), (n, d)
+
+
+def test_shared_conv_weights_are_announced_once_final():
+    """with share_weights_over_channels=True both channel passes add into the same conv gradients; a bucket
+    must not be announced (and all-reduced) before the last pass.  A recording reducer checks that nothing changes in
+    flat[offset:] after ready(offset)."""
+    cfg = jo.Cfg(in_channels=2, per_channel=True)
+    ex = w.ConvChannelFeatureExtractor(conv_layers_spec=cfg.spec, in_channels=2, share_weights_over_channels=True)
+    model = w.JEPA(feature_extractor=ex, transformer_encoder_cfg=w.TransformerEncoderCFG.create(),
+                   transformer_encoder_layers_cfg=w.TransformerLayerCFG.create(),
+                   transformer_decoder_cfg=w.TransformerEncoderCFG.create(),
+                   transformer_decoder_layers_cfg=w.TransformerLayerCFG.create(d_model=384),
+                   process_audio_seconds=2.01, nr_samples_per_audio=2, average_top_k_layers=8).to(DEV)
+    model.global_step = 1000
+
+    class Recorder:
+        world_size = 1
+
+        def __init__(self):
+            self.flat, self.log = None, []
+
+        def begin(self, flat):
+            self.flat, self.log = flat, []
+
+        def ready(self, offset):
+            self.log.append((offset, self.flat[offset:].double().sum().item(), self.flat[offset:].abs().double().sum().item()))
+
+        def finish(self):
+            pass
+
+    rec = Recorder()
+    model.attach_data_parallel(rec, sync=False)
+    g = torch.Generator().manual_seed(1)
+    audio = torch.randn(2, 2, cfg.target_length, generator=g).bfloat16().to(DEV)
+    mk = w.TimeInverseBlockMasker(4, 0.65, 10, 0.25, 10, 0.1, channel_based_masking=True, seed=2, row0=0)
+    c_m, t_m, v_m = mk(batch_size=2, n_times=400, in_channels=2)
+    flat = model._flat_g if model._flat_p is not None else None
+    model.train_step(audio, c_m, t_m, v_m)
+    flat = model._flat_g
+    assert len(rec.log) > 20
+    offs = [o for o, _, _ in rec.log]
+    assert offs == sorted(offs, reverse=True), "ready() offsets must move from the end of the buffer to its start"
+    for off, s1, s2 in rec.log:
+        assert flat[off:].double().sum().item() == s1 and flat[off:].abs().double().sum().item() == s2, off
+
+
+def test_hear_nat_runtime_matches_reference_goldens():
+    """VERDICT r1 missing 5: the binaural HEAR runtime (hear_api/runtime_natjepa.py: channel fix-up, joint normalisation,
+    channel-major mask, channel mean) against fixtures made by EXECUTING the reference's get_timestamp_embeddings
+    (tests/golden/make_golden.py::golden_hear_nat) and against the live oracle on fresh inputs."""
+    torch.set_num_threads(os.cpu_count())
+    g = np.load(os.path.join(GOLD, "hear_nat.npz"))
+    cfg = jo.Cfg(in_channels=2, per_channel=True)
+    sd = jo.make_state_dict(cfg, seed=3)
+    model = hear.load_model_nat({"state_dict": sd})
+    assert model.output_steps == 200 and model.unit_frames == 32159 and model.embedding_size == 768
+    gen = torch.Generator().manual_seed(17)
+    stereo = torch.rand(2, 2, 48000, generator=gen) * 2 - 1
+    emb, ts = hear.get_timestamp_embeddings(stereo.to(DEV), model)
+    assert list(emb.shape) == list(g["stereo_shape"]) and np.allclose(ts[0].cpu().numpy(), g["stereo_ts"], rtol=1e-6)
+    assert rel(oi.subsample(emb.cpu()), g["stereo_emb"]) < FEAT_TOL
+    assert abs(float(emb.norm()) - float(g["stereo_l2"])) / float(g["stereo_l2"]) < 2e-3
+    scene = hear.get_scene_embeddings(stereo.to(DEV), model)
+    assert rel(scene.cpu().numpy(), g["stereo_scene"]) < FEAT_TOL
+    mono = oi.hear_inputs(2, 40000, seed=19)
+    emb, ts = model.get_timestamp_embeddings(mono.to(DEV))       # mono input is duplicated onto both channels
+    assert list(emb.shape) == list(g["mono_shape"]) and rel(oi.subsample(emb.cpu()), g["mono_emb"]) < FEAT_TOL
+    # live oracle, exact multiple of the unit (a whole extra padded chunk) and a 4-channel clip
+    four = torch.rand(1, 4, 64318, generator=gen) * 2 - 1
+    with torch.no_grad():
+        ref, rts = jo.hear_nat_timestamp_embeddings(four, sd, cfg)
+    emb, ts = model.get_timestamp_embeddings(four.to(DEV))
+    assert tuple(emb.shape) == tuple(ref.shape) == (1, 400, 768)
+    assert rel(emb.cpu().numpy(), ref.numpy()) < FEAT_TOL and np.allclose(ts.cpu().numpy(), rts.numpy(), rtol=1e-6)
+    with pytest.raises(_lib.WavJepaLibError):
+        hear.RuntimeJEPA(in_channels=2, weights={"state_dict": sd}, is_spectrogram=False, process_seconds=2.01,
+                         extractor=w.ConvChannelFeatureExtractor(conv_layers_spec=cfg.spec, in_channels=2), model_size="base", sr=16000)
+
+
+def test_hf_call_shape(tmp_path):
+    """VERDICT r1 missing 3 / SURVEY H5: AutoFeatureExtractor / AutoModel call shape of README.md:72-108 and
+    hear_configs/WavJEPA_huggingface.py (values = the HEAR runtime's, which the goldens pin)."""
+    from wavjepa_b200 import hf
+    g = np.load(os.path.join(GOLD, "hear.npz"))
+    cfg = jo.Cfg()
+    path = os.path.join(tmp_path, "ckpt.pt")
+    torch.save({"state_dict": {k.replace("encoder.", "encoder._orig_mod.", 1) if k.startswith("encoder.") else k: v
+                               for k, v in jo.make_state_dict(cfg, seed=3).items()}}, path)
+    model = hf.WavJEPAModel.from_pretrained(path, trust_remote_code=True).to(DEV)
+    ext = hf.WavJEPAFeatureExtractor.from_pretrained("labhamlet/wavjepa-base", trust_remote_code=True)
+    audio = oi.hear_inputs(2, 160000, seed=11)
+    feats = ext(audio.to(DEV), return_tensors="pt")["input_values"]
+    emb, ts = model(feats)
+    assert tuple(emb.shape) == (2, 996, 768) and tuple(ts.shape) == (2, 996)
+    assert rel(oi.subsample(emb.cpu()), g["10s_emb"]) < FEAT_TOL and np.allclose(ts[0].cpu().numpy(), g["10s_ts"], rtol=1e-6)
+    m2 = hf.load_model(path)
+    assert m2.sample_rate == 16000
+    e2, _ = hf.get_timestamp_embeddings([audio[0], audio[1, :150000]], m2)   # ragged list -> zero-padded batch
+    assert tuple(e2.shape) == (2, 996, 768)
+    assert tuple(hf.get_scene_embeddings(audio.to(DEV), m2).shape) == (2, 768)
+    # the Nat pair: [B, 2, L] in, same call
+    nat_sd = jo.make_state_dict(jo.Cfg(in_channels=2, per_channel=True), seed=3)
+    nat = hf.WavJEPAModel.from_pretrained({"state_dict": nat_sd})
+    assert isinstance(nat.runtime, hear.RuntimeNatJEPA)
+    emb, ts = nat(hf.WavJEPAFeatureExtractor.from_pretrained("labhamlet/wavjepa-nat-base")(torch.zeros(1, 2, 48000))["input_values"])
+    assert tuple(emb.shape) == (1, 299, 768)
+
+
+def test_gpu_batch_assembler_tuple_contract():
+    """VERDICT r1 missing 8: the 4-tuple of WebAudioDataModule._retrieve_sample + .batched (WebAudioDataModule.py:43-74)
+    assembled on the device: audio == the CPU preprocessing of the data module, masks == the seeded masker's."""
+    import torchaudio
+    from wavjepa_b200.data import GpuBatchAssembler
+    g = torch.Generator().manual_seed(3)
+    samples = [(torch.randn(2, 44100 * 3, generator=g) * 0.1, 44100), (torch.randn(16000 * 12, generator=g) * 0.3, 16000),
+               (torch.randn(48000 * 5, generator=g) * 0.05, 48000)]
+    mk = w.TimeInverseBlockMasker(4, 0.65, 10, 0.25, 10, 0.1, seed=11, row0=5, device=DEV)
+    asm = GpuBatchAssembler(mk, nr_samples_per_audio=8, nr_time_points=200, in_channels=1, device=DEV)
+    audio, c_m, t_m, v_m = asm(samples)
+    assert tuple(audio.shape) == (3, 1, 160000) and tuple(c_m.shape) == (3, 8, 200) and tuple(t_m.shape) == (3, 8, 4, 200)
+    for i, (wv, sr) in enumerate(samples):
+        ref = jo.data_pre_process(wv, sr)[0]
+        assert rel(audio[i, 0].cpu().numpy(), ref.numpy()) < 1e-4, i
+    rc, rt, rv, _ = mo.time_inverse_masks(11, 5, 24, 200)
+    assert np.array_equal(c_m.reshape(24, 200).cpu().numpy(), rc) and np.array_equal(v_m.reshape(24, 4, 200).cpu().numpy(), rv)
+    # the tuple feeds the training hook unchanged
+    model = build_model(jo.Cfg(), jo.make_state_dict(jo.Cfg(), seed=3))
+    x16, c2, t2, v2 = model.on_after_batch_transfer((audio, c_m, t_m, v_m), 0)
+    assert tuple(x16.shape) == (24, 1, 32159) and tuple(c2.shape) == (24, 200) and tuple(t2.shape) == (24, 4, 200)
+    model.shuffle_crops = True      # reference behaviour: audio rows permuted, masks untouched (jepa.py:314-316)
+    x16s, c3, _, _ = model.on_after_batch_transfer((audio, c_m, t_m, v_m), 0)
+    assert torch.equal(c3, c2) and x16s.shape == x16.shape

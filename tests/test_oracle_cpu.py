@@ -277,3 +277,86 @@ def test_denoiser_state_dict_is_the_references():
     assert list(m.state_dict().keys()) == keys
     assert all(not p.requires_grad for p in m.teacher.parameters())
     assert abs(m.lr_at(2500) - 0.5e-4) < 1e-12 and m.lr_at(0) == 0.0      # 5000 warm-up steps (denoiser.py:208-209)
+
+
+# ------------------------------------------------------------------------------------------------- round-2 additions
+def test_oracle_hear_nat_matches_reference():
+    """oracle restatement of hear_api/runtime_natjepa.py against fixtures made by executing the reference's (unmodified)
+    RuntimeNatJEPA.get_timestamp_embeddings (tests/golden/make_golden.py::golden_hear_nat)."""
+    torch.set_num_threads(os.cpu_count())
+    g = np.load(os.path.join(GOLD, "hear_nat.npz"))
+    cfg = jo.Cfg(in_channels=2, per_channel=True)
+    sd = jo.make_state_dict(cfg, seed=3)
+    stereo = torch.rand(2, 2, 48000, generator=torch.Generator().manual_seed(17)) * 2 - 1
+    with torch.no_grad():
+        emb, ts = jo.hear_nat_timestamp_embeddings(stereo, sd, cfg)
+    assert list(emb.shape) == list(g["stereo_shape"]) and np.allclose(ts[0].numpy(), g["stereo_ts"], rtol=1e-6)
+    assert rel(oi.subsample(emb), g["stereo_emb"]) < 2e-4
+    assert rel(emb.mean(dim=1).numpy(), g["stereo_scene"]) < 2e-4
+
+
+def test_lightning_base_is_used_when_available():
+    """VERDICT r1 missing 4: JEPA / Denoiser derive from pytorch_lightning.LightningModule when Lightning is importable
+    (checked in a fresh interpreter with a stand-in `pytorch_lightning` package, since the image has none), and from the
+    shim otherwise; either way the members the reference's loop touches exist."""
+    import subprocess
+    import sys
+    import textwrap
+    code = textwrap.dedent("""
+        import sys, types, torch
+        from torch import nn
+        pl = types.ModuleType("pytorch_lightning")
+        class LightningModule(nn.Module):
+            def __init__(self):
+                super().__init__(); self._hp = {}; self._trainer = None
+            def save_hyperparameters(self, *a, **k):
+                for x in a: self._hp.update(x)
+            @property
+            def hparams(self):
+                return types.SimpleNamespace(**self._hp)
+            @property
+            def trainer(self):
+                if self._trainer is None: raise RuntimeError("not attached")
+                return self._trainer
+            @trainer.setter
+            def trainer(self, t): self._trainer = t
+            @property
+            def global_step(self): return self.trainer.global_step
+            def log_dict(self, *a, **k): pass
+        pl.LightningModule = LightningModule
+        sys.modules["pytorch_lightning"] = pl
+        import wavjepa_b200 as w
+        from wavjepa_b200 import _lightning
+        assert _lightning.HAVE_LIGHTNING and issubclass(w.JEPA, LightningModule) and issubclass(w.Denoiser, LightningModule)
+        spec = [(512, 10, 5)] + [(512, 3, 2)] * 4 + [(512, 2, 2)]
+        m = w.JEPA(feature_extractor=w.ConvFeatureExtractor(conv_layers_spec=spec, in_channels=1),
+                   transformer_encoder_cfg=w.TransformerEncoderCFG.create(num_layers=1),
+                   transformer_encoder_layers_cfg=w.TransformerLayerCFG.create(),
+                   transformer_decoder_cfg=w.TransformerEncoderCFG.create(num_layers=1),
+                   transformer_decoder_layers_cfg=w.TransformerLayerCFG.create(d_model=384))
+        assert m.hparams.lr == 0.0002 and m.global_step == 0          # detached: our own counter
+        m.trainer = types.SimpleNamespace(global_step=123, max_steps=10)
+        assert m.global_step == 123 and abs(m._get_ema_decay() - (0.99999 - 0.00099 * (1 - 123 / 100000))) < 1e-12
+        print("OK")
+    """)
+    r = subprocess.run([sys.executable, "-c", code], cwd=ROOT, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "OK" in r.stdout, r.stderr[-2000:]
+    from wavjepa_b200 import _lightning
+    import wavjepa_b200 as w
+    assert issubclass(w.JEPA, _lightning.Base) and hasattr(w.JEPA, "log_dict") and hasattr(w.JEPA, "save_hyperparameters")
+
+
+def test_hf_feature_extractor_and_reference_staging():
+    from wavjepa_b200 import hf
+    ext = hf.WavJEPAFeatureExtractor.from_pretrained("labhamlet/wavjepa-base", trust_remote_code=True)
+    out = ext([torch.ones(5), torch.ones(8)], return_tensors="pt")
+    assert tuple(out["input_values"].shape) == (2, 8) and out.input_values[0, 5:].abs().sum() == 0
+    assert tuple(ext(torch.zeros(160000))["input_values"].shape) == (1, 160000)
+    with pytest.raises(ValueError):
+        ext(torch.zeros(10), sampling_rate=44100)
+    # the staged reference copy (bench.py's reference arms on the GPU box) is byte-identical to the checkout
+    from oracle import stage_reference
+    if os.path.isdir("/root/reference/wavjepa"):
+        dest = stage_reference.stage("/root/reference", os.path.join(ROOT, "baseline", "_ref"))
+        man = json.load(open(os.path.join(dest, "MANIFEST.json")))["files"]
+        assert "wavjepa/jepa.py" in man and "hear_api/runtime.py" in man and len(man) > 20

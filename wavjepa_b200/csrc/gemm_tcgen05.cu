@@ -1170,8 +1170,19 @@ extern "C" int wj_gemm_bf16(const wj_operand_t* A, const void* W, int64_t ldw, i
   if (L <= 0 || batch <= 0) return WJ_OK;
   if (K % BK != 0 || N % 8 != 0) { set_error("wj_gemm_bf16: K must be a multiple of 64 and N of 8 (K=%d N=%d)", K, N); return WJ_ERR_ARG; }
   if (A->seg_width > 0 && (A->seg_width % BK != 0 || K > 4 * A->seg_width)) { set_error("wj_gemm_bf16: bad segment width"); return WJ_ERR_ARG; }
-  const bool pair = block_n < 0;   // -128 / -256: CTA-pair kernel (256-row tiles, tcgen05 cta_group::2)
+  bool pair = block_n < 0;   // -128 / -256: CTA-pair kernel (256-row tiles, tcgen05 cta_group::2)
   if (pair) block_n = -block_n;
+  // automatic choice: CTA pairs (each SM stages its own 128 rows of A and HALF of the 256 B columns) for bf16 outputs
+  // on the TMA-store epilogue with K >= 768 -- measured +5..11 % on the teacher / student / conv forward shapes
+  // (1257 vs 1170, 1275 vs 1190, 1360 vs 1271, 1377 vs 1235 TFLOP/s); the K = 384 shapes and the generic fp32 epilogue
+  // are faster on single CTAs (607 vs 696 TFLOP/s on the predictor's fc1)
+  if (block_n == 0 && K >= 768 && N % 256 == 0 && static_cast<long long>(L) * batch >= 4096 && epi != nullptr &&
+      !epi->out_f32 && !epi->accumulate && epi->resid == nullptr && epi->out_rows == nullptr && epi->colsum == nullptr &&
+      (epi->act == 0 || epi->act == 1) && epi->ld_out % 8 == 0 && reinterpret_cast<uintptr_t>(epi->out) % 16 == 0 &&
+      (epi->out2 == nullptr || (epi->ld_out2 % 8 == 0 && reinterpret_cast<uintptr_t>(epi->out2) % 16 == 0))) {
+    pair = true;
+    block_n = 256;
+  }
   // N = 384-like fp32-output GEMMs: 192-column tiles (a 128-column B tile leaves the main loop smem-bandwidth bound)
   const bool ok192 = !pair && tile192_ok(epi, N);
   if (block_n == 0) block_n = (ok192 && N % 256 != 0 && N <= 768) ? 192 : ((N % 256 == 0 || N > 1024) ? 256 : 128);

@@ -31,7 +31,8 @@ from . import ops
 from ._lib import WavJepaLibError
 from .extractors import ConvFeatureExtractor
 from .hear import fix_state_dict_keys
-from .jepa import JEPA, _AttrDict
+from ._lightning import Base as _ModuleBase
+from .jepa import JEPA
 from .preprocess import sinc_resample_table
 from .types import ForwardReturn, TransformerEncoderCFG, TransformerLayerCFG
 
@@ -118,7 +119,7 @@ def resample(audio: torch.Tensor, resample_sr: int, original_sr: int = ORIGINAL_
 
 
 # ------------------------------------------------------------------------------------------------- the module
-class Denoiser(nn.Module):
+class Denoiser(_ModuleBase):
     """reference wavjepa/denoiser.py:43-376."""
     TARGET_SECONDS: int = 10
     ORIGINAL_SR = ORIGINAL_SR
@@ -127,8 +128,10 @@ class Denoiser(nn.Module):
                  transformer_encoder_cfg: TransformerEncoderCFG, lr: float = 0.0001, adam_betas: tuple = (0.9, 0.98),
                  adam_eps: float = 1e-06, adam_weight_decay: float = 0.0, resample_sr: int = 16000,
                  process_audio_seconds: float = 2.01, nr_samples_per_audio: int = 16, size: str = "base",
-                 alpha: float = 0.0, max_steps: int = 375000, grad_clip: float = 0.0, **kwargs: Any):
+                 alpha: float = 0.0, max_steps: int = 375000, grad_clip: float = 1.0, **kwargs: Any):
         super().__init__()
+        # grad_clip: the reference trains this stage with gradient_clip_val=1.0, gradient_clip_algorithm='norm'
+        # (denoise.py:125-126); 0 disables clipping
         self.alpha = alpha
         self.sr = resample_sr
         self.target_audio_length = self.TARGET_SECONDS * self.sr
@@ -136,12 +139,11 @@ class Denoiser(nn.Module):
         self.nr_samples_per_audio = nr_samples_per_audio
         self.target_length = int(resample_sr * process_audio_seconds)
         self.total_patches = feature_extractor.total_patches(self.target_length)
-        self.hparams = _AttrDict(lr=lr, adam_betas=tuple(adam_betas), adam_eps=adam_eps,
-                                 adam_weight_decay=adam_weight_decay, resample_sr=resample_sr,
-                                 process_audio_seconds=process_audio_seconds,
-                                 nr_samples_per_audio=nr_samples_per_audio, size=size, alpha=alpha)
+        self.save_hyperparameters(dict(lr=lr, adam_betas=tuple(adam_betas), adam_eps=adam_eps,
+                                       adam_weight_decay=adam_weight_decay, resample_sr=resample_sr,
+                                       process_audio_seconds=process_audio_seconds,
+                                       nr_samples_per_audio=nr_samples_per_audio, size=size, alpha=alpha))
         self.max_steps = max_steps
-        self.trainer = None
         core = JEPA(feature_extractor=feature_extractor, transformer_encoder_cfg=transformer_encoder_cfg,
                     transformer_encoder_layers_cfg=transformer_encoder_layers_cfg,
                     transformer_decoder_cfg=TransformerEncoderCFG.create(num_layers=1),
@@ -341,8 +343,15 @@ class Denoiser(nn.Module):
                  if p.requires_grad and not n.startswith("teacher.")}
         return out, grads
 
-    def attach_data_parallel(self, reducer) -> None:
-        self._core.attach_data_parallel(reducer)
+    def attach_data_parallel(self, reducer, sync: bool = True) -> None:
+        self._core.attach_data_parallel(reducer, sync=sync)
+
+    def optimizer_state_dict(self) -> dict:
+        """Adam moments + global_step of the fused optimizer path (see JEPA.optimizer_state_dict)."""
+        return self._core.optimizer_state_dict()
+
+    def load_optimizer_state_dict(self, sd: dict) -> None:
+        self._core.load_optimizer_state_dict(sd)
 
     def reserve_workspace(self, n_bytes: int) -> int:
         return self._core.reserve_workspace(n_bytes)

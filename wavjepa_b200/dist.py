@@ -29,6 +29,24 @@ class BucketedAllReduce:
         self._handles: List = []
         self.launched: List[tuple] = []  # (lo, hi) of every bucket of the last step, for tests / reporting
 
+    # ---- setup-time helpers (not on the step's critical path)
+    def broadcast_(self, tensors) -> None:
+        """In-place broadcast of rank 0's tensors to every rank of the group."""
+        for t in tensors:
+            dist.broadcast(t, src=dist.get_global_rank(self.group, 0) if self.group is not None else 0, group=self.group)
+
+    def broadcast_int(self, value: int) -> int:
+        dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(self.group) == "nccl" else torch.device("cpu")
+        t = torch.tensor([int(value)], dtype=torch.int64, device=dev)
+        self.broadcast_([t])
+        return int(t.item())
+
+    def any_rank(self, flag: bool) -> bool:
+        dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(self.group) == "nccl" else torch.device("cpu")
+        t = torch.tensor([1 if flag else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+        return bool(t.item())
+
     def begin(self, flat_grads: torch.Tensor) -> None:
         self._flat = flat_grads
         self._hi = flat_grads.numel()

@@ -60,7 +60,8 @@ def get_timestamps(sample_rate: int, B: int, input_audio_len: int, n_frames: int
 
 
 @torch.no_grad()
-def embed_chunks(model: JEPA, a: torch.Tensor, gain: Optional[torch.Tensor], unit: int, steps: int, sr: int):
+def embed_chunks(model: JEPA, a: torch.Tensor, gain: Optional[torch.Tensor], unit: int, steps: int, sr: int,
+                 channel_tokens: int = 1):
     """The chunk loop of hear_api/runtime.py:107-142 (and ARCH/configs/wavjepa_wrapper.py:67-110) as ONE batched pass:
     a [B, C, L] fp32 on the device, gain [B] or None.  Chunk i of clip b = gain * a[b, :, i*unit:(i+1)*unit] (zeros past
     L), normalised per chunk (mean / unbiased std including the zero padding, runtime.py:12-16); the frames that fall
@@ -74,8 +75,14 @@ def embed_chunks(model: JEPA, a: torch.Tensor, gain: Optional[torch.Tensor], uni
     mask = torch.zeros(B, max(total_steps, n_chunks * steps), dtype=torch.bool, device=dev)
     mask[:, cut_off:total_steps] = True
     mask = mask[:, :n_chunks * steps].reshape(B * n_chunks, steps)
-    emb = model.get_audio_representation(x16, mask)          # [B*n_chunks, steps, D] fp32
-    return emb.view(B, n_chunks * steps, -1)[:, :cut_off], cut_off
+    if channel_tokens > 1:
+        # WavJEPA-Nat (hear_api/runtime_natjepa.py:142-147): the model emits channel-major tokens [c0 t0.., c1 t0..]; the
+        # time mask is repeated "B E -> B (C E)" and the per-channel embeddings are averaged
+        emb = model.get_audio_representation(x16, mask.repeat(1, channel_tokens))   # [B*n_chunks, C*steps, D]
+        emb = emb.view(B * n_chunks, channel_tokens, steps, -1).mean(dim=1)
+    else:
+        emb = model.get_audio_representation(x16, mask)          # [B*n_chunks, steps, D] fp32
+    return emb.reshape(B, n_chunks * steps, -1)[:, :cut_off], cut_off
 
 
 class RuntimeJEPA(nn.Module):
@@ -86,8 +93,8 @@ class RuntimeJEPA(nn.Module):
         super().__init__()
         if is_spectrogram:
             raise WavJepaLibError("spectrogram front-ends are not part of WavJEPA")
-        if in_channels != 1:
-            raise WavJepaLibError("RuntimeJEPA is built for the mono model (in_channels=1)")
+        if in_channels != 1 and not isinstance(self, RuntimeNatJEPA):
+            raise WavJepaLibError("RuntimeJEPA is the mono runtime (in_channels=1); use RuntimeNatJEPA for WavJEPA-Nat")
         self.sample_rate = sr
         self.in_channels = in_channels
         self.model = JEPA(feature_extractor=extractor, transformer_encoder_cfg=TransformerEncoderCFG.create(),
@@ -146,6 +153,48 @@ class RuntimeJEPA(nn.Module):
         return self.get_timestamp_embeddings(input_values)
 
 
+class RuntimeNatJEPA(RuntimeJEPA):
+    """reference hear_api/runtime_natjepa.py:39-155: the binaural WavJEPA-Nat runtime.  Same geometry as the mono runtime
+    with (1) the channel fix-up of FeatureExtractor(in_channels=2) (feature_helper.py:55-81: mono is duplicated, stereo
+    passes, the first of 4 channels is duplicated), (2) output_steps = tokens per CHANNEL (:83-86), (3) per-chunk
+    normalisation over both channels jointly (:12-16), (4) the time mask repeated over the channel-major token layout and
+    the two channels' embeddings averaged (:142-147)."""
+
+    def __init__(self, in_channels: int, weights, is_spectrogram: bool, process_seconds: float, extractor,
+                 model_size: str, sr: int, device: Optional[str] = None, **kwargs) -> None:
+        if in_channels != 2:
+            raise WavJepaLibError("RuntimeNatJEPA is built for the binaural model (in_channels=2)")
+        super().__init__(in_channels, weights, is_spectrogram, process_seconds, extractor, model_size, sr, device, **kwargs)
+        self.output_steps = self.model.extract_audio.total_patches(self.unit_frames) // in_channels
+
+    def to_feature(self, audio: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        dev = self.model.device
+        a = torch.as_tensor(audio).to(dev, torch.float32)
+        if a.dim() == 2:
+            a = a.unsqueeze(1)
+        if a.dim() != 3:
+            raise ValueError("audio input tensor must be (n_sounds, num_samples) or (n_sounds, n_channels, num_samples)")
+        if a.shape[1] > 100 and a.shape[2] <= 100:
+            a = a.transpose(1, 2)
+        a = a.contiguous()
+        gain = ops.clip_gain(a, -14.0)                   # RMS over the whole (C, L) clip BEFORE the channel fix-up
+        if a.shape[1] == 1:
+            a = a.expand(-1, 2, -1).contiguous()           # feature_helper.py:57-58
+        elif a.shape[1] == 4:
+            a = a[:, :1].expand(-1, 2, -1).contiguous()    # :75-77
+        elif a.shape[1] != 2:
+            raise WavJepaLibError("Unknown channel count")
+        return a, gain
+
+    @torch.no_grad()
+    def get_timestamp_embeddings(self, audio: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        a, gain = self.to_feature(audio)
+        B, C, L = a.shape
+        emb, _ = embed_chunks(self.model, a, gain, self.unit_frames, self.output_steps, self.sample_rate, channel_tokens=C)
+        ts = get_timestamps(self.sample_rate, B, L, emb.shape[1])
+        return emb, ts
+
+
 def _load_weights(args):
     if len(args) == 0:
         return None
@@ -170,6 +219,16 @@ def load_model_w2v2(*args, **kwargs) -> RuntimeJEPA:
     extractor = ConvFeatureExtractor(conv_layers_spec=W2V2_SPEC, in_channels=1)
     return RuntimeJEPA(in_channels=1, process_seconds=4.02, weights=_load_weights(args), sr=SR, model_size="base",
                        is_spectrogram=False, extractor=extractor, **kwargs)
+
+
+def load_model_nat(*args, share_weights_over_channels: bool = False, **kwargs) -> RuntimeNatJEPA:
+    """WavJEPA-Nat counterpart of load_model (README.md:93-108 `labhamlet/wavjepa-nat-base`): per-channel extractors
+    (wavjepa/extractors/audio_channel_feature_extractor.py), 2 x 200 tokens per 2.01 s window."""
+    from .extractors import ConvChannelFeatureExtractor
+    extractor = ConvChannelFeatureExtractor(conv_layers_spec=BASE_SPEC, in_channels=2,
+                                            share_weights_over_channels=share_weights_over_channels)
+    return RuntimeNatJEPA(in_channels=2, process_seconds=2.01, weights=_load_weights(args), sr=SR, model_size="base",
+                          is_spectrogram=False, extractor=extractor, **kwargs)
 
 
 def get_scene_embeddings(audio, model):

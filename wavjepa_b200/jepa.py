@@ -27,6 +27,8 @@ from torch import nn
 
 from . import ops
 from ._lib import WavJepaLibError, require_device
+from ._lightning import Base as _ModuleBase
+from ._lightning import attached_trainer
 from .engine import LayerG, LayerW, TransformerStack
 from .extractors import (ConvChannelFeatureExtractor, ConvFeatureExtractor, conv_stack_backward, conv_stack_forward,
                          kmajor_weight)
@@ -127,7 +129,9 @@ class _LossBridge(torch.autograd.Function):
 
 
 # =================================================================================================== model
-class JEPA(nn.Module):
+class JEPA(_ModuleBase):
+    """A `pytorch_lightning.LightningModule` when Lightning is installed (drop-in for `pl.Trainer.fit`, train.py:244),
+    a plain nn.Module with the same members otherwise (wavjepa_b200/_lightning.py)."""
     teacher_encoder: nn.Module
 
     def __init__(self, feature_extractor, transformer_encoder_layers_cfg: TransformerLayerCFG,
@@ -147,17 +151,17 @@ class JEPA(nn.Module):
         self.total_patches = feature_extractor.total_patches(self.target_length)
         self.use_compiled_forward = False          # torch.compile is not part of this build
         self.use_gradient_checkpointing = False    # activations fit: 180 GB HBM, packed tokens
-        self.hparams = _AttrDict(lr=lr, adam_betas=tuple(adam_betas), adam_eps=adam_eps,
-                                 adam_weight_decay=adam_weight_decay, ema_decay=ema_decay,
-                                 ema_end_decay=ema_end_decay, ema_anneal_end_step=ema_anneal_end_step,
-                                 average_top_k_layers=average_top_k_layers, resample_sr=resample_sr,
-                                 process_audio_seconds=process_audio_seconds,
-                                 nr_samples_per_audio=nr_samples_per_audio, size=size,
-                                 decoder_embedding_dim=decoder_embedding_dim)
-        self.global_step = 0
+        self.save_hyperparameters(dict(lr=lr, adam_betas=tuple(adam_betas), adam_eps=adam_eps,
+                                       adam_weight_decay=adam_weight_decay, ema_decay=ema_decay,
+                                       ema_end_decay=ema_end_decay, ema_anneal_end_step=ema_anneal_end_step,
+                                       average_top_k_layers=average_top_k_layers, resample_sr=resample_sr,
+                                       process_audio_seconds=process_audio_seconds,
+                                       nr_samples_per_audio=nr_samples_per_audio, size=size,
+                                       decoder_embedding_dim=decoder_embedding_dim))
+        self._step = 0
         self.max_steps = max_steps
         self.grad_clip = grad_clip
-        self.trainer = None
+        self.shuffle_crops = False   # True: shuffle the audio rows after cropping like the reference (jepa.py:314-316)
         if not isinstance(feature_extractor, (ConvFeatureExtractor, ConvChannelFeatureExtractor)):
             raise WavJepaLibError("feature_extractor must be a wavjepa_b200 ConvFeatureExtractor / ConvChannelFeatureExtractor")
 
@@ -230,6 +234,17 @@ class JEPA(nn.Module):
     def device(self) -> torch.device:
         return self.mask_token.device
 
+    @property
+    def global_step(self) -> int:
+        """The trainer's step counter when a pl.Trainer drives the module (wavjepa/jepa.py:186-191 reads
+        LightningModule.global_step), otherwise the counter the fused / stock optimizer paths advance."""
+        t = attached_trainer(self)
+        return int(t.global_step) if t is not None and hasattr(t, "global_step") else self._step
+
+    @global_step.setter
+    def global_step(self, value: int) -> None:
+        self._step = int(value)
+
     def configure_optimizers(self):
         """Stock-PyTorch optimizer over the same parameters (for a Lightning-style loop); `train_step` uses the
         fused AdamW kernel instead."""
@@ -237,6 +252,14 @@ class JEPA(nn.Module):
         opt = torch.optim.AdamW(trainables, lr=self.hparams.lr, betas=self.hparams.adam_betas,
                                 eps=self.hparams.adam_eps, weight_decay=self.hparams.adam_weight_decay)
         sched = torch.optim.lr_scheduler.LambdaLR(opt, lambda s: self.lr_at(s) / self.hparams.lr)
+
+        # In the reference `global_step` is the Lightning trainer's counter; it drives the EMA anneal
+        # (wavjepa/jepa.py:186-191).  Without a trainer nobody would advance it on this path: count optimizer steps.
+        def _count(optimizer, args, kwargs):
+            if attached_trainer(self) is None:
+                self._step += 1
+
+        opt.register_step_post_hook(_count)
         return {"optimizer": opt, "lr_scheduler": {"scheduler": sched, "interval": "step"}}
 
     # ------------------------------------------------------------------------------------------- flat buffers
@@ -275,11 +298,15 @@ class JEPA(nn.Module):
             o, cnt, shp = self._offsets[n]
             flat[o:o + cnt].copy_(params[n].detach().reshape(-1))
             params[n].data = flat[o:o + cnt].view(shp)
+        # Adam moments follow the parameters: a rebuild (first use, .to(), .cuda()) keeps them when the layout is unchanged
+        old_m, old_v = getattr(self, "_adam_m", None), getattr(self, "_adam_v", None)
+        keep = old_m is not None and old_m.numel() == total and getattr(self, "_layout_sig", None) == tuple(order)
+        self._layout_sig = tuple(order)
         self._flat_p = flat
         self._flat_g = torch.zeros(total, device=dev, dtype=torch.float32)
         self._flat_w16 = torch.empty(total, device=dev, dtype=torch.bfloat16)
-        self._adam_m = None
-        self._adam_v = None
+        self._adam_m = old_m.to(dev) if keep else None
+        self._adam_v = old_v.to(dev) if keep else None
         # encoder slice (EMA source) and the teacher's mirror of it
         enc_names = [n for n in order if n.startswith("encoder.")]
         e0 = self._offsets[enc_names[0]][0]
@@ -598,7 +625,10 @@ class JEPA(nn.Module):
                 prefix = exs[0 if ex.share_weights_over_channels else ch][0]
                 sv = conv_saved[ch]
                 dfc = dfeat3[:, ch * Tc:(ch + 1) * Tc].contiguous().view(B * Tc, C)
-                self._conv_backward(prefix, ex.conv_layers_spec, sv, dfc, B, Tc, C, g, ready)
+                # with shared weights every channel pass adds into the SAME gradient region: it is final (and may be
+                # all-reduced) only after the last pass
+                last = (not ex.share_weights_over_channels) or ch == 0
+                self._conv_backward(prefix, ex.conv_layers_spec, sv, dfc, B, Tc, C, g, ready if last else (lambda name: None))
         else:
             self._conv_backward(exs[0][0], ex.conv_layers_spec, conv_saved[0], dfeat, B, T, C, g, ready)
 
@@ -654,7 +684,7 @@ class JEPA(nn.Module):
         """reference wavjepa/jepa.py:275-316: nr_samples_per_audio random crops of target_length per clip,
         per-crop normalisation, bf16, flattened; masks flattened.  One fused kernel (crop + Welford + scale).
         The reference additionally shuffles the audio rows only (masks are i.i.d., so this changes nothing
-        statistically); here the crops stay in clip order."""
+        statistically); here the crops stay in clip order unless `self.shuffle_crops` is set."""
         audio, ctx_masks, target_indices, ctx_and_target_masks = batch
         if audio.dim() != 3:
             audio = audio.unsqueeze(1)
@@ -666,6 +696,8 @@ class JEPA(nn.Module):
         starts = starts.to(self.device, torch.int32).reshape(-1).contiguous()
         x16 = torch.empty(n_clips * S, C, self.target_length, device=self.device, dtype=torch.bfloat16)
         ops.crop_norm(audio, starts, S, self.target_length, x16, None)
+        if self.shuffle_crops:   # the reference permutes the AUDIO rows only (masks stay in place), jepa.py:314-316;
+            x16 = x16[torch.randperm(x16.shape[0], device=self.device)]   # on the device: no host round trip
         return x16, collate_fn(ctx_masks), collate_fn(target_indices), collate_fn(ctx_and_target_masks)
 
     def training_step(self, batch, batch_idx: int = 0) -> ForwardReturn:
@@ -698,9 +730,22 @@ class JEPA(nn.Module):
             del block
         return n
 
-    def attach_data_parallel(self, reducer) -> None:
-        """reducer: wavjepa_b200.dist.BucketedAllReduce (or None)."""
+    def attach_data_parallel(self, reducer, sync: bool = True) -> None:
+        """reducer: wavjepa_b200.dist.BucketedAllReduce (or None).  With sync (default) rank 0's student / teacher
+        parameters, Adam moments and global_step are broadcast first, as Lightning's DDP strategy does at setup
+        (train.py:174-179): the gradient all-reduce alone would never repair replicas that started different."""
         self._ddp = reducer
+        if reducer is not None and sync and self.mask_token.device.type == "cuda":
+            self._ensure_ready()
+            reducer.broadcast_([self._flat_p, self._flat_t])
+            has_m = reducer.any_rank(self._adam_m is not None)
+            if has_m:
+                if self._adam_m is None:
+                    self._adam_m = torch.zeros_like(self._flat_p)
+                    self._adam_v = torch.zeros_like(self._flat_p)
+                reducer.broadcast_([self._adam_m, self._adam_v])
+            self.global_step = reducer.broadcast_int(self.global_step)
+            self._sync_weights(force=True)
 
     @torch.no_grad()
     def train_step(self, x16: torch.Tensor, ctx_masks: torch.Tensor, target_indices: torch.Tensor,
@@ -751,7 +796,50 @@ class JEPA(nn.Module):
                                1.0 / world, self.grad_clip, ss, self._flat_w16, self._flat_t, self._flat_t16, e0, e1,
                                ema_decay)
         self._refresh_conv_weights()
-        self.global_step += 1
+        self._step = self.global_step + 1
+
+    # ------------------------------------------------------------------------------------------- optimizer state
+    def optimizer_state_dict(self) -> dict:
+        """State of the fused optimizer path, in the shape of a Lightning checkpoint's `optimizer_states[0]` plus the
+        step counter that drives the LR and EMA schedules (the reference's checkpoints carry both, train.py
+        ModelCheckpoint): {'global_step', 'state': {name: {'exp_avg', 'exp_avg_sq'}}, 'param_names'}.  Tensors are
+        detached copies on the parameters' device."""
+        self._ensure_ready()
+        st = {}
+        if self._adam_m is not None:
+            for n in self._train_names:
+                st[n] = {"exp_avg": self._view(self._adam_m, n).clone(), "exp_avg_sq": self._view(self._adam_v, n).clone()}
+        return {"global_step": int(self.global_step), "state": st, "param_names": list(self._train_names)}
+
+    def load_optimizer_state_dict(self, sd: dict) -> None:
+        """Inverse of optimizer_state_dict(): restores Adam moments and global_step so that a resumed run continues the
+        warm-up / cosine LR schedule and the EMA anneal where it stopped instead of restarting them at step 0."""
+        self._ensure_ready()
+        self.global_step = int(sd["global_step"])
+        state = sd.get("state", {})
+        if not state:
+            self._adam_m = self._adam_v = None
+            return
+        missing = [n for n in self._train_names if n not in state]
+        if missing:
+            raise KeyError(f"optimizer state lacks {len(missing)} parameters, e.g. {missing[:3]}")
+        self._adam_m = torch.zeros_like(self._flat_p)
+        self._adam_v = torch.zeros_like(self._flat_p)
+        for n in self._train_names:
+            self._view(self._adam_m, n).copy_(state[n]["exp_avg"])
+            self._view(self._adam_v, n).copy_(state[n]["exp_avg_sq"])
+
+    def checkpoint(self) -> dict:
+        """Lightning-shaped checkpoint dict ({'state_dict', 'global_step', 'optimizer_states'}) of a fused-path run."""
+        return {"state_dict": {k: v.detach().clone() for k, v in self.state_dict().items()},
+                "global_step": int(self.global_step), "optimizer_states": [self.optimizer_state_dict()]}
+
+    def load_checkpoint(self, ckpt: dict, strict: bool = True) -> None:
+        self.load_state_dict({k.replace("._orig_mod", ""): v for k, v in ckpt["state_dict"].items()}, strict=strict)
+        if ckpt.get("optimizer_states"):
+            self.load_optimizer_state_dict(ckpt["optimizer_states"][0])
+        elif "global_step" in ckpt:
+            self.global_step = int(ckpt["global_step"])
 
     # ------------------------------------------------------------------------------------------- inference
     @torch.no_grad()
