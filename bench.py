@@ -416,7 +416,7 @@ def run_hear(args):
                   transformer_encoder_cfg=w.TransformerEncoderCFG.create(),
                   transformer_encoder_layers_cfg=w.TransformerLayerCFG.create(),
                   transformer_decoder_cfg=w.TransformerEncoderCFG.create(),
-                  transformer_decoder_layers_cfg=w.TransformerLayerCFG.create(d_model=384))
+                  transformer_decoder_layers_cfg=w.TransformerLayerCFG.create(d_model=384), process_audio_seconds=2.01)
     model = hear.load_model({"state_dict": init.state_dict()})     # random-init weights (no network for checkpoints)
     n, L = HEAR_CLIPS, CLIP_LEN
     host = [(torch.rand(n, L, generator=torch.Generator().manual_seed(7 + 10 * rank + i)) * 2 - 1).pin_memory() for i in range(2)]

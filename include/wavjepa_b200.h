@@ -208,9 +208,11 @@ int wj_attn_varlen_bwd(const void* qkv_bf16, const void* out_bf16, const void* d
                        const int* cu_seqlens, int n_seqs, int max_len, int64_t total_tokens, int D, int H,
                        void* dqkv_bf16, void* stream);
 
-/* The same backward with the bias gradient of the in_proj Linear folded in: dbias[3 D] += column sums of the stored
- * (bf16) dqkv rows -- in the tcgen05 kernel's epilogue (head dim 32, <= 128 tokens, D <= 384), otherwise by a wj_colsum
- * pass after the mma.sync kernel.  dbias may be NULL. */
+/* The same backward with the bias gradient of the in_proj Linear folded in: dbias[3 D] += column sums of dqkv.  On the
+ * tcgen05 path (head dim 32, <= 128 tokens) the query third is reduced in the kernel's epilogue, the value third is added
+ * as the column sums of dout (softmax rows sum to one: sum_k dV[k,:] = sum_q dO[q,:]) and the key third, which is
+ * identically zero in exact arithmetic (softmax ignores a constant key shift), is left untouched; on the mma.sync path a
+ * wj_colsum pass over the stored dqkv follows the kernel.  dbias may be NULL. */
 int wj_attn_varlen_bwd_bias(const void* qkv_bf16, const void* out_bf16, const void* dout_bf16, const float* lse2,
                             const int* cu_seqlens, int n_seqs, int max_len, int64_t total_tokens, int D, int H,
                             void* dqkv_bf16, float* dbias, void* stream);

@@ -149,6 +149,7 @@ def time_hear(n_clips: int = 2, n_samples: int = 160000):
     ext = ref.ConvFeatureExtractor(conv_layers_spec=ref_loader.BASE_SPEC, in_channels=1)
     model = rt.RuntimeJEPA(in_channels=1, weights={"state_dict": jepa.state_dict()}, is_spectrogram=False,
                            process_seconds=2.01, extractor=ext, model_size="base", sr=16000)
+    model.model.cpu()     # (the reference's constructor moves the model to CUDA when there is one: this is the CPU arm)
     audio = torch.rand(n_clips, n_samples, generator=torch.Generator().manual_seed(1234)) * 2 - 1
     with torch.no_grad():
         model.get_timestamp_embeddings(audio)

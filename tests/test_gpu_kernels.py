@@ -462,8 +462,10 @@ def test_attention_fwd_bwd(D, H, lens):
     db = torch.ones(3 * D, device=DEV)
     ops.attn_bwd(qkv, out, do, lse, cu, len(lens), max(lens), D, H, dq2, dbias=db)
     assert torch.equal(dq2, dqkv)
-    cs = dqkv.float().sum(0)
-    assert (db - 1.0 - cs).abs().max().item() <= 2e-3 * cs.abs().max().item() + 1e-3
+    # against the fp32 autograd bias gradient (its key third is zero up to rounding, its value third is colsum(dO))
+    cs = qr.grad.sum(0)
+    assert (db - 1.0 - cs).abs().max().item() <= 1e-2 * cs.abs().max().item() + 1e-3
+    assert rel(db - 1.0, cs) < 1e-2
 
 
 # ------------------------------------------------------------------------------------------------------- elementwise

@@ -413,7 +413,13 @@ extern "C" int wj_attn_varlen_bwd_bias(const void* qkv_bf16, const void* out_bf1
     // head dim 32, <= 128 tokens: tcgen05 kernel (attention_tc.cu); everything else: the mma.sync kernel below
     const int rc = wj::attn_bwd_tc_launch(qkv_bf16, out_bf16, dout_bf16, lse2, cu_seqlens, n_seqs, max_len, total_tokens, D, H,
                                           dqkv_bf16, dbias, WJ_STREAM(stream));
-    if (rc <= 0) return rc;   // (the tcgen05 kernel forms the column sums in its epilogue)
+    if (rc < 0) return rc;
+    if (rc == 0) {
+      // the tcgen05 kernel added the query third in its epilogue; the value third of the bias gradient is the column sum
+      // of dO (softmax rows sum to one), the key third is identically zero (softmax ignores a constant key shift)
+      if (dbias != nullptr) return wj_colsum(dout_bf16, 1, total_tokens, D, D, dbias + 2 * D, stream);
+      return WJ_OK;
+    }
   }
   const int npad = (max_len + 15) & ~15;
   const size_t smem = static_cast<size_t>(4) * npad * (dh + 8) * 2 + static_cast<size_t>(2) * ((npad + 63) & ~63) * 4;

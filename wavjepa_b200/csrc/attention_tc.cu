@@ -338,9 +338,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const AttnTcParams p
 //        (TMEM columns [0,32), [32,64), [64,96) over the consumed S block)
 //   epilogue: rows < n of dQ*scale, dK*scale, dV -> dqkv[token, {0, D, 2D} + head*32 ...], transposed through the
 //        warp's own (consumed) corner of the P tile so that four lanes store one 64-byte row
-//        optionally the column sums of the stored rows (the bias gradient of the in_proj Linear, which autograd takes
-//        over the bf16 dqkv): 5-step reduce-scatter across the warp's 32 rows, shared-memory accumulators [3 D] per CTA,
-//        one global atomic per column per CTA at the end -- replaces a separate pass over dqkv (398 MB per layer)
+//        optionally the column sums of the stored dQ rows (the query third of the in_proj bias gradient, which autograd
+//        takes over the bf16 dqkv): 5-step reduce-scatter across the warp's 32 rows, shared-memory accumulators [D] per
+//        CTA, one global atomic per column per CTA at the end; with the value third = column sums of dO and the key
+//        third = 0 this replaces a separate pass over dqkv (398 MB per layer)
 //   delta: the O tile rides along with the TMA loads; every gradient thread reduces its own row of O * dO out of
 //        smem while the S / dP products run.  lse is fetched one item ahead into a register.
 //
@@ -354,15 +355,15 @@ struct AttnBwdParams {
   const bf16* dout;
   const float* lse2;
   bf16* dqkv;
-  float* dbias;   // optional [3 D]: += column sums of the stored dqkv rows (the in_proj bias gradient)
+  float* dbias;   // optional [3 D]: [0, D) += column sums of the stored dQ rows (query third of the in_proj bias gradient)
 };
 
 constexpr int kBwdTile = kAtQ * 32 * 2;                  // 8 KB: [128 x 32] bf16, 64B swizzle
 constexpr int kBwdPs = 2 * kAtQ * 128;                   // 32 KB: [2 key blocks][128 queries][64 keys] bf16, 128B swizzle
 constexpr int kBwdBarOff = 5 * kBwdTile + 2 * kBwdPs;    // Q | K | V | dO | O | P | dS | barriers
-constexpr int kBwdCsOff = kBwdBarOff + 128;             // fp32 [3 D] column sums of this CTA's items (D <= kBwdCsMaxD)
-constexpr int kBwdCsMaxD = 384;
-constexpr int kBwdSmem = kBwdCsOff + 3 * kBwdCsMaxD * 4 + 1024;
+constexpr int kBwdCsOff = kBwdBarOff + 128;             // fp32 [D] column sums of this CTA's dQ rows (D <= kBwdCsMaxD)
+constexpr int kBwdCsMaxD = 1024;
+constexpr int kBwdSmem = kBwdCsOff + kBwdCsMaxD * 4 + 1024;
 
 __global__ void __launch_bounds__(288, 2) attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
                                                              const __grid_constant__ CUtensorMap tmDO,
@@ -382,7 +383,7 @@ __global__ void __launch_bounds__(288, 2) attn_bwd_tc_kernel(const __grid_consta
   float* s_cs = reinterpret_cast<float*>(smem + kBwdCsOff);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (p.dbias != nullptr)
-    for (int i = threadIdx.x; i < 3 * p.D; i += blockDim.x) s_cs[i] = 0.f;
+    for (int i = threadIdx.x; i < p.D; i += blockDim.x) s_cs[i] = 0.f;
 
   if (warp == 8) {
     if (lane == 0) {
@@ -569,30 +570,37 @@ __global__ void __launch_bounds__(288, 2) attn_bwd_tc_kernel(const __grid_consta
             w.z = pack_bf16x2(__uint_as_float(g[8 * q + 4]) * sc, __uint_as_float(g[8 * q + 5]) * sc);
             w.w = pack_bf16x2(__uint_as_float(g[8 * q + 6]) * sc, __uint_as_float(g[8 * q + 7]) * sc);
             *reinterpret_cast<uint4*>(stage + t * 2048 + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4)) = w;
-            if (p.dbias != nullptr) {   // keep the values as stored (bf16) for the column sums
-              g[8 * q] = w.x << 16; g[8 * q + 1] = w.x & 0xffff0000u; g[8 * q + 2] = w.y << 16; g[8 * q + 3] = w.y & 0xffff0000u;
-              g[8 * q + 4] = w.z << 16; g[8 * q + 5] = w.z & 0xffff0000u; g[8 * q + 6] = w.w << 16; g[8 * q + 7] = w.w & 0xffff0000u;
-            }
-          }
-          if (p.dbias != nullptr) {
-            // rows >= n hold stale bits (key chunks past the sequence are never written to the P / dS tiles): select
-            float c32[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) c32[j] = live ? __uint_as_float(g[j]) : 0.f;
-#pragma unroll
-            for (int sft = 16; sft >= 1; sft >>= 1) {
-              const bool up = (lane & sft) != 0;
-#pragma unroll
-              for (int i = 0; i < sft; ++i) {
-                const float mine = up ? c32[sft + i] : c32[i];
-                const float other = up ? c32[i] : c32[sft + i];
-                c32[i] = mine + __shfl_xor_sync(0xffffffffu, other, sft);
-              }
-            }
-            const int col = half == 0 ? (t == 0 ? 0 : 2 * p.D) : p.D;
-            atomicAdd(s_cs + col + head * DH + lane, c32[0]);
           }
         }
+      }
+      if (p.dbias != nullptr && half == 1) {
+        // Bias gradient of the query projection = column sums of the stored (bf16) dQ rows of this warp's lane quadrant:
+        // 5-step reduce-scatter over the warp's 32 rows (lane l ends with column l), one shared-memory atomic per lane.
+        // Done by the dK warps, which stage one tile where the dQ / dV warps stage two.  (The key third of the bias
+        // gradient is exactly zero -- softmax is invariant to a constant added to every key's logit -- and the value
+        // third equals the column sums of dO because softmax rows sum to one: the host side adds that with one pass over
+        // dO instead of a reduction here.)
+        uint32_t g[32];
+        tmem_ld_32x32(tDQ + lane_addr, g);
+        tmem_ld_wait();
+        float c32[32];
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {   // rows >= n hold stale bits: select, do not multiply
+          const uint32_t w = pack_bf16x2(__uint_as_float(g[j]) * p.scale, __uint_as_float(g[j + 1]) * p.scale);
+          c32[j] = live ? __uint_as_float(w << 16) : 0.f;
+          c32[j + 1] = live ? __uint_as_float(w & 0xffff0000u) : 0.f;
+        }
+#pragma unroll
+        for (int sft = 16; sft >= 1; sft >>= 1) {
+          const bool up = (lane & sft) != 0;
+#pragma unroll
+          for (int i = 0; i < sft; ++i) {
+            const float mine = up ? c32[sft + i] : c32[i];
+            const float other = up ? c32[i] : c32[sft + i];
+            c32[i] = mine + __shfl_xor_sync(0xffffffffu, other, sft);
+          }
+        }
+        atomicAdd(s_cs + head * DH + lane, c32[0]);
       }
       tc_fence_before();
       __syncwarp();
@@ -620,7 +628,7 @@ __global__ void __launch_bounds__(288, 2) attn_bwd_tc_kernel(const __grid_consta
   tc_fence_before();
   __syncthreads();
   if (p.dbias != nullptr)
-    for (int i = threadIdx.x; i < 3 * p.D; i += blockDim.x) atomicAdd(p.dbias + i, s_cs[i]);
+    for (int i = threadIdx.x; i < p.D; i += blockDim.x) atomicAdd(p.dbias + i, s_cs[i]);
   if (warp == 8) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 256);
