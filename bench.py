@@ -183,7 +183,8 @@ def _hbm_kernels(kp, peaks, traffic):
     names = {"wj_conv0_gn_gelu_fwd": "conv0+GroupNorm+GELU fwd", "wj_conv0_gn_gelu_bwd": "conv0+GroupNorm+GELU bwd",
              "wj_add_layernorm_fwd": "residual add + LayerNorm fwd", "wj_add_layernorm_bwd": "residual add + LayerNorm bwd",
              "wj_layernorm_fwd": "LayerNorm fwd (feature/final norms)", "wj_layernorm_bwd": "LayerNorm bwd (feature/final norms)",
-             "wj_target_accum": "teacher-target instance norm + layer mean", "wj_masked_mse": "masked latent MSE fwd+bwd",
+             "wj_target_accum": "teacher-target instance norm + layer mean",
+             "wj_target_combine": "teacher-target instance norm + layer mean (all top-K layers, one pass)", "wj_masked_mse": "masked latent MSE fwd+bwd",
              "wj_adamw_ema_step": "clip + AdamW + EMA teacher", "wj_adamw_step": "clip + AdamW", "wj_ema_update": "EMA teacher",
              "wj_sumsq": "gradient norm", "wj_colsum": "bias-gradient column sums", "wj_crop_norm": "crop + normalise"}
     out = []

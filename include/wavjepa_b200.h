@@ -195,6 +195,12 @@ int wj_rms_gain_rows(float* clips, const double* sumsq, const int64_t* counts, i
 int wj_target_accum(const float* x, const float* rowsum, int B, int T, int D, float eps, float scale, int first,
                     float* inst_stats, float* targets, void* stream);
 
+/* The same targets from all top-K layer outputs in one pass: xs / rowsums are HOST arrays of n_layers (<= 16) device
+ * pointers (layer outputs [B*T, D] fp32 and their wj_layernorm_fwd rowsum [B*T, 2]); inst_stats: [n_layers, B, 2]
+ * workspace.  targets = scale * sum_l instance_norm(x_l): every layer is read once, the targets written once. */
+int wj_target_combine(const float* const* xs, const float* const* rowsums, int n_layers, int B, int T, int D, float eps,
+                      float scale, float* inst_stats, float* targets, void* stream);
+
 /* Variable-length multi-head attention over packed tokens: qkv bf16 [tokens, 3*D] (q|k|v), sequences given by
  * cu_seqlens [n_seqs+1], softmax(q k^T / sqrt(D/H)) v, head dim 32 or 64.  out bf16 [tokens, D];
  * lse2 fp32 [tokens, H] = log2-sum-exp2 of the scaled logits (saved for the backward; may be NULL).

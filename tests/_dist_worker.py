@@ -79,7 +79,7 @@ def main():
             covered += hi - lo
         assert covered == model._flat_g.numel()
         # (2) replicas stay bit-identical (same summed gradients, same fused optimizer + EMA)
-        for t in (model._flat_p, model._flat_t, model._adam_m, model._adam_v, model._flat_w16.view(torch.int16)):
+        for t in (model._flat_p, model._flat_t, model._adam_m, model._adam_v, model._flat_w16.view(torch.uint8)):
             g = gathered(t)
             assert all(torch.equal(g[0], x) for x in g), f"replicas diverged at step {step}"
     # ranks trained on different data: the local gradients must really differ (the check above is not vacuous)

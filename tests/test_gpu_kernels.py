@@ -418,6 +418,16 @@ def test_target_accum():
     stacked = torch.stack([o.view(B, T, D) for o in outs]).transpose(2, 3)
     ref = F.instance_norm(stacked).transpose(2, 3).mean(0)
     assert rel(targets.view(B, T, D), ref) < 1e-5
+    # the one-pass form over all layers (what the teacher forward uses)
+    sums = []
+    for o in outs:
+        rs = torch.empty(B * T, 2, device=DEV)
+        rs[:, 0] = o.sum(1)
+        rs[:, 1] = (o * o).sum(1)
+        sums.append(rs)
+    t2 = torch.full_like(targets, float("nan"))
+    ops.target_combine(outs, sums, B, T, D, 1.0 / K, torch.empty(K, B, 2, device=DEV), t2)
+    assert rel(t2.view(B, T, D), ref) < 1e-5
 
 
 # ------------------------------------------------------------------------------------------------------- attention

@@ -284,6 +284,53 @@ __global__ void __launch_bounds__(256) target_accum_kernel(const float* __restri
   }
 }
 
+// All K layers at once: targets = scale * sum_l (x_l - mean_{l,b}) * rstd_{l,b}: every layer output is read ONCE and the
+// targets are written ONCE ((K + 1) * 4 bytes per element instead of K * 12 with the layer-by-layer accumulation).
+constexpr int kMaxTargetLayers = 16;
+struct TargetLayers {
+  const float* x[kMaxTargetLayers];
+  const float* rowsum[kMaxTargetLayers];
+};
+__global__ void __launch_bounds__(256) instance_stats_multi_kernel(TargetLayers L, int B, int T, int D, float eps,
+                                                                   float* __restrict__ inst_stats) {
+  const int b = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31, l = blockIdx.y;
+  if (b >= B) return;
+  const float* rowsum = L.rowsum[l];
+  double s = 0.0, q = 0.0;
+  for (int t = lane; t < T; t += 32) {
+    s += rowsum[2 * (static_cast<size_t>(b) * T + t)];
+    q += rowsum[2 * (static_cast<size_t>(b) * T + t) + 1];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
+  if (lane == 0) {
+    const double n = static_cast<double>(T) * D;
+    const double mean = s / n;
+    double var = q / n - mean * mean;  // biased (F.instance_norm)
+    if (var < 0.0) var = 0.0;
+    inst_stats[2 * (static_cast<size_t>(l) * B + b)] = static_cast<float>(mean);
+    inst_stats[2 * (static_cast<size_t>(l) * B + b) + 1] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+  }
+}
+template <int K>
+__global__ void __launch_bounds__(256) target_combine_kernel(TargetLayers L, const float* __restrict__ inst_stats, int B,
+                                                             long long n4, int per_inst4, float scale,
+                                                             float* __restrict__ targets) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int b = static_cast<int>(i / per_inst4);
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int l = 0; l < K; ++l) {
+      const float2 st = *reinterpret_cast<const float2*>(inst_stats + 2 * (static_cast<size_t>(l) * B + b));
+      const float rs = st.y * scale;
+      const float4 v = reinterpret_cast<const float4*>(L.x[l])[i];
+      t.x += (v.x - st.x) * rs; t.y += (v.y - st.x) * rs; t.z += (v.z - st.x) * rs; t.w += (v.w - st.x) * rs;
+    }
+    reinterpret_cast<float4*>(targets)[i] = t;
+  }
+}
+
 template <typename TIn>
 static int launch_ln_fwd(const void* x, const float* g, const float* b, float eps, int M, int D, float* of, bf16* ob,
                          float* stats, float* rowsum, cudaStream_t st, const bf16* add = nullptr) {
@@ -368,6 +415,28 @@ extern "C" int wj_crop_norm(const float* audio, const int* starts, const float* 
   crop_norm_kernel<<<n, 512, 0, WJ_STREAM(stream)>>>(audio, starts, channels, clip_len, crops_per_clip, crop_len, gain,
                                                     reinterpret_cast<bf16*>(out_bf16), out_f32);
   return check_launch("crop_norm");
+}
+
+extern "C" int wj_target_combine(const float* const* xs, const float* const* rowsums, int n_layers, int B, int T, int D,
+                                 float eps, float scale, float* inst_stats, float* targets, void* stream) {
+  if (B <= 0 || n_layers <= 0) return WJ_OK;
+  if (D % 4 != 0 || n_layers > kMaxTargetLayers) { set_error("wj_target_combine: D %% 4 != 0 or more than %d layers", kMaxTargetLayers); return WJ_ERR_ARG; }
+  TargetLayers L;
+  for (int l = 0; l < kMaxTargetLayers; ++l) { L.x[l] = l < n_layers ? xs[l] : nullptr; L.rowsum[l] = l < n_layers ? rowsums[l] : nullptr; }
+  cudaStream_t st = WJ_STREAM(stream);
+  instance_stats_multi_kernel<<<dim3((B + 7) / 8, n_layers), 256, 0, st>>>(L, B, T, D, eps, inst_stats);
+  const long long n4 = static_cast<long long>(B) * T * D / 4;
+  long long blocks = (n4 + 255) / 256;
+  const long long cap = static_cast<long long>(sm_count()) * 16;
+  if (blocks > cap) blocks = cap;
+  const int g = static_cast<int>(blocks);
+  switch (n_layers) {
+#define WJ_TC(K) case K: target_combine_kernel<K><<<g, 256, 0, st>>>(L, inst_stats, B, n4, T * D / 4, scale, targets); break;
+    WJ_TC(1) WJ_TC(2) WJ_TC(3) WJ_TC(4) WJ_TC(5) WJ_TC(6) WJ_TC(7) WJ_TC(8) WJ_TC(9) WJ_TC(10) WJ_TC(11) WJ_TC(12)
+    WJ_TC(13) WJ_TC(14) WJ_TC(15) WJ_TC(16)
+#undef WJ_TC
+  }
+  return check_launch("target_combine", 2);
 }
 
 extern "C" int wj_target_accum(const float* x, const float* rowsum, int B, int T, int D, float eps, float scale,

@@ -467,14 +467,18 @@ class JEPA(_ModuleBase):
         cu = torch.arange(0, (B + 1) * T, T, device=dev, dtype=torch.int32)
         targets = torch.empty(B * T, D, device=dev)
         if K > 1:
-            inst = torch.empty(B, 2, device=dev)
             n_used = nl - first_layer
+            inst = torch.empty(n_used, B, 2, device=dev)
+            outs, sums = [], []
 
             def hook(i, x32, rowsum):
-                if i >= first_layer:
-                    ops.target_accum(x32, rowsum, B, T, D, 1.0 / n_used, i == first_layer, inst, targets)
+                if i >= first_layer:   # keep the layer output (it is the next layer's residual anyway) and its row sums
+                    outs.append(x32)
+                    sums.append(rowsum)
 
             self._enc_stack.forward(self._W_tea, local32, local16, cu, B, T, False, hook, rowsum_from=first_layer)
+            # one pass over the K layer outputs instead of K read-modify-write passes over the targets
+            ops.target_combine(outs, sums, B, T, D, 1.0 / n_used, inst, targets)
         else:
             x32, _, _ = self._enc_stack.forward(self._W_tea, local32, local16, cu, B, T, False)
             targets = x32

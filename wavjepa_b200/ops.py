@@ -401,6 +401,19 @@ def target_accum(x: torch.Tensor, rowsum, B: int, T: int, D: int, scale: float, 
                               p(inst_stats), p(targets), _stream()))
 
 
+def target_combine(xs, rowsums, B: int, T: int, D: int, scale: float, inst_stats, targets, eps: float = 1e-5):
+    """targets = scale * sum_l instance_norm(xs[l]) over all layers in one pass (JEPA._make_targets, wavjepa/jepa.py:230-253)."""
+    n = len(xs)
+    assert n == len(rowsums) and inst_stats.numel() >= n * B * 2
+    lib = _lib.load()
+    px = (C.c_void_p * n)(*[_ptr(t) for t in xs])
+    pr = (C.c_void_p * n)(*[_ptr(t) for t in rowsums])
+    if _lib._profile is not None:
+        _lib._profile.nbytes = B * T * D * 4 * (n + 1)
+    check(lib.wj_target_combine(px, pr, n, B, T, D, C.c_float(eps), C.c_float(scale), C.c_void_p(_ptr(inst_stats)),
+                                C.c_void_p(_ptr(targets)), _stream()))
+
+
 # ----------------------------------------------------------------------------------------------------- attention
 def attn_fwd(qkv: torch.Tensor, cu: torch.Tensor, n_seqs: int, max_len: int, D: int, H: int, out: torch.Tensor,
              lse2=None):
