@@ -25,13 +25,15 @@ for name, S, D, H, lo, hi in (("student (visible context)", 512, 768, 12, 20, 73
     dqkv = torch.empty_like(qkv)
     fwd = lambda: ops.attn_fwd(qkv, cu, S, ml, D, H, out, lse)
     bwd = lambda: ops.attn_bwd(qkv, out, do, lse, cu, S, ml, D, H, dqkv)
+    dbias = torch.zeros(3 * D, device=dev)
+    bwd_b = lambda: ops.attn_bwd(qkv, out, do, lse, cu, S, ml, D, H, dqkv, dbias=dbias) if hasattr(ops, "add_bf16") else bwd()
     fwd()
     if ncu:
         bwd()
         torch.cuda.synchronize()
         continue
     res = []
-    for fn in (fwd, bwd):
+    for fn in (fwd, bwd, bwd_b):
         for _ in range(3):
             fn()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -44,4 +46,4 @@ for name, S, D, H, lo, hi in (("student (visible context)", 512, 768, 12, 20, 73
     dh = D // H
     flops = 4.0 * float((lens.double() ** 2).sum()) * dh * H     # QK^T + PV
     print(f"{name:32s} seqs {S} tokens {tot} max {ml} dh {dh}: fwd {res[0]*1e3:7.1f} us ({flops/res[0]/1e9:6.1f} TFLOP/s)   "
-          f"bwd {res[1]*1e3:7.1f} us ({2.5*flops/res[1]/1e9:6.1f} TFLOP/s)")
+          f"bwd {res[1]*1e3:7.1f} us ({2.5*flops/res[1]/1e9:6.1f} TFLOP/s)   bwd + in_proj bias gradient {res[2]*1e3:7.1f} us")

@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libwavjepa_b200.so")
+# WJ_LIB: an alternative build of the same C ABI (A/B timing of two builds on one box; the default is the in-tree library)
+LIB_PATH = os.environ.get("WJ_LIB") or os.path.join(_HERE, "libwavjepa_b200.so")
 
 WJ_OK = 0
 

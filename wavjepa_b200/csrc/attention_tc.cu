@@ -442,6 +442,17 @@ __global__ void __launch_bounds__(288, 2) attn_bwd_tc_kernel(const __grid_consta
         for (int ks = 0; ks < DH / 16; ++ks)
           umma_bf16(tDP, umma_smem_desc(sDO + ks * 32, 0, SBO, SWZ), umma_smem_desc(sV + ks * 32, 0, SBO, SWZ), idesc_s, ks > 0 ? 1u : 0u);
         umma_commit(bar_s);
+        if (item + gridDim.x < p.items) {
+          // the next item's five tiles cannot land in shared memory before this item's last MMAs have read it (one
+          // stage: 104 KB per CTA buys the second CTA per SM), but they can be pulled into L2 now, so that the TMA loads
+          // at the top of the next iteration cost an L2 hit instead of a DRAM round trip on this CTA's critical path
+          const int nitem = item + gridDim.x, ns = nitem / p.H, nh = nitem - ns * p.H, nst = p.cu[ns];
+          tma_prefetch_2d(&tmQ, nh * DH, nst);
+          tma_prefetch_2d(&tmQ, p.D + nh * DH, nst);
+          tma_prefetch_2d(&tmQ, 2 * p.D + nh * DH, nst);
+          tma_prefetch_2d(&tmDO, nh * DH, nst);
+          tma_prefetch_2d(&tmO, nh * DH, nst);
+        }
         mbar_wait(bar_p, ph_p);
         ph_p ^= 1;
         tc_fence_after();
