@@ -93,6 +93,11 @@ int wj_gemm_dgrad_bf16(const wj_operand_t* A, const void* W, int64_t ldw, int w_
                        const int32_t* seg_col_off, int L, int batch, int N, int K, const wj_epilogue_t* epi,
                        int block_n, void* stream);
 
+/* Development aid (profiles/r02_gemm_cycle_counters.txt): `counters` = device buffer of 8 int64 per CTA that the
+ * single-CTA GEMM launches after this call fill with clock64 counters of their MMA / producer / epilogue roles (time spent
+ * waiting for operands, for a free accumulator, for a free stage); NULL (default) switches them off. */
+int wj_gemm_debug(void* counters);
+
 /* dW[m, vc] (+)= sum_{b,t} dY[b, t, m] * X(vc; t, b)   fp32 out [M, N] (leading dim ld_out); both operands are read
  * MN-major straight from the row-major activations; the token reduction is split over `splits` CTAs (0 = auto) and
  * reduced with red.global.add.  Replaces autograd's weight gradients of the Linear / Conv1d layers above. */

@@ -66,6 +66,9 @@ struct GemmParams {
   float* colsum;        // optional: colsum[n] += sum over rows of the stored output (bias gradients)
   int tma_store;        // bf16 outputs without residual / aux / scatter: staged in smem and written by TMA stores
   int transpose_out;    // wgrad: the tile holds out^T (operands swapped so that the wide dimension is BN = 256)
+  long long* dbg;       // optional per-CTA cycle counters (wj_gemm_debug): [0] MMA thread waiting for operands, [1] for a free
+                        // accumulator, [2] its total, [3] producer waiting for a free stage, [4] epilogue warp 4 waiting for
+                        // an accumulator, [5] its total, [6] tiles, [7] unused
 };
 
 struct OutMaps {
@@ -553,6 +556,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      long long dbg_prod = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         if constexpr (!WGRAD) {
           const int m_blk = tile / p.n_blocks;
@@ -561,7 +565,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           const int row0 = (m_blk - b * p.mb_per_batch) * BM;
           const int nkb = p.K / BK;
           for (int kb = 0; kb < nkb; ++kb) {
+            const long long tw = p.dbg ? clock64() : 0;
             mbar_wait_relaxed(&empty_bar[stage], phase ^ 1);
+            if (p.dbg) dbg_prod += clock64() - tw;
             uint8_t* sa = smem + stage * C::STAGE_BYTES;
             uint8_t* sb = sa + C::A_BYTES;
             int c0, q, po;
@@ -617,6 +623,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           }
         }
       }
+      if (p.dbg) p.dbg[blockIdx.x * 8 + 3] = dbg_prod;
     }
   } else if (warp == 1) {
     // ======================================================================================= MMA issuer
@@ -625,15 +632,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
+      long long dbg_full = 0, dbg_empty = 0;
+      const long long dbg_t0 = p.dbg ? clock64() : 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
         const int nkb = num_kb(tile);
+        long long tw = p.dbg ? clock64() : 0;
         mbar_wait_relaxed(&tempty_bar[acc], acc_phase ^ 1);
+        if (p.dbg) dbg_empty += clock64() - tw;
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
         for (int kb = 0; kb < nkb; ++kb) {
+          tw = p.dbg ? clock64() : 0;
           mbar_wait(&full_bar[stage], phase);
+          if (p.dbg) dbg_full += clock64() - tw;
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
           const uint32_t sb = sa + C::A_BYTES;
@@ -654,6 +667,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
         umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
       }
+      if (p.dbg) {
+        p.dbg[blockIdx.x * 8 + 0] = dbg_full;
+        p.dbg[blockIdx.x * 8 + 1] = dbg_empty;
+        p.dbg[blockIdx.x * 8 + 2] = clock64() - dbg_t0;
+        p.dbg[blockIdx.x * 8 + 6] = it;
+      }
     }
   } else if (warp >= kEpiWarp0) {
     // ======================================================================================= epilogue (16 warps)
@@ -670,6 +689,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const int col_q = ew >> 2;                // which quarter of the BN columns this warp handles
     constexpr int CHUNKS = (BN / 32 + 3) / 4; // 32-column chunks per warp (TMA-store paths)
     int it = 0;
+    long long dbg_epi = 0;
+    const long long dbg_e0 = p.dbg ? clock64() : 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
@@ -687,7 +708,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         n_blk = rem - m_blk * p.n_blocks;
         have_k = num_kb(tile) > 0;
       }
+      const long long tw = (p.dbg && warp == kEpiWarp0) ? clock64() : 0;
       mbar_wait(&tfull_bar[acc], acc_phase);
+      if (p.dbg && warp == kEpiWarp0) dbg_epi += clock64() - tw;
       tc_fence_after();
       const uint32_t t_acc = tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16) + acc * BN;
       const uint32_t t_base = t_acc + col_q * (CHUNKS * 32);   // (TMA-store paths: CHUNKS consecutive chunks per warp)
@@ -707,6 +730,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                                static_cast<long long>(m_blk) * BM, have_k, [&]() { mbar_arrive(&tempty_bar[acc]); });
     }
     if (p.tma_store && lane == 0) bulk_wait0();   // all TMA stores of this warp are complete before smem goes away
+    if (p.dbg && warp == kEpiWarp0 && lane == 0) {
+      p.dbg[blockIdx.x * 8 + 4] = dbg_epi;
+      p.dbg[blockIdx.x * 8 + 5] = clock64() - dbg_e0;
+    }
   }
 
   tc_fence_before();
@@ -1152,7 +1179,10 @@ static void fill_seg(SegInfo& s, const wj_operand_t* op) {
   for (int i = 0; i < 4; ++i) { s.q[i] = op->seg_q[i]; s.p[i] = op->seg_p[i]; }
 }
 
+static long long* g_gemm_dbg = nullptr;   // wj_gemm_debug(): per-CTA cycle counters of the NEXT single-CTA GEMM launches
+
 static void fill_epilogue(GemmParams& p, const wj_epilogue_t* e) {
+  p.dbg = g_gemm_dbg;
   p.out = e->out; p.ld_out = e->ld_out; p.out_f32 = e->out_f32; p.accumulate = e->accumulate;
   p.out2 = reinterpret_cast<bf16*>(e->out2); p.ld_out2 = e->ld_out2;
   p.bias = e->bias; p.resid = e->resid; p.resid_f32 = e->resid_f32; p.ld_resid = e->ld_resid;
@@ -1163,6 +1193,13 @@ static void fill_epilogue(GemmParams& p, const wj_epilogue_t* e) {
 }  // namespace wj
 
 using namespace wj;
+
+// Development aid: device buffer of 8 int64 per CTA (>= 8 * #SMs) that the single-CTA GEMM kernels fill with cycle
+// counters (see GemmParams::dbg); NULL switches the counters off (the default).
+extern "C" int wj_gemm_debug(void* counters) {
+  g_gemm_dbg = reinterpret_cast<long long*>(counters);
+  return WJ_OK;
+}
 
 // out[b*L + t, n] = epilogue( sum_vc A(vc; t, b) * W[n, vc] )        W is [N, K] row-major (K contiguous), bf16.
 extern "C" int wj_gemm_bf16(const wj_operand_t* A, const void* W, int64_t ldw, int L, int batch, int N, int K,
