@@ -91,14 +91,19 @@ struct RegSplit {   // WIDE: the two-output GELU epilogue holds 64 accumulator +
   static_assert(128 * CTRL + 512 * EPI <= kThreads * kLaunchRegs, "setmaxnreg split exceeds the CTA's register pool");
 };
 
-template <int BN>
+// AUX: the GELU-backward dgrad (MODE 2, HEAVY): every epilogue warp owns TWO 2 KB tiles (one per 32-column chunk of its
+// tile) that first receive the saved GELU' factors by TMA -- a whole tile ahead of their use -- and then stage the
+// output; the extra 32 KB come out of the operand ring (3 stages: that kernel is epilogue-bound, not operand-bound).
+template <int BN, bool AUX = false>
 struct Cfg {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN == 256) ? 4 : ((BN == 192) ? 4 : ((BN == 128) ? 6 : 8));
+  static constexpr int STAGES = AUX ? ((BN == 256) ? 3 : 4) : ((BN == 256) ? 4 : ((BN == 192) ? 4 : ((BN == 128) ? 6 : 8)));
   static constexpr int STAGING_OFF = STAGES * STAGE_BYTES + 1024;   // barriers live in the 1 KB before it
-  static constexpr int SMEM_BYTES = STAGING_OFF + 1024 /*align slack*/ + kEpiWarps * 2048 /*TMA-store staging*/;
+  static constexpr int WARP_STAGING = AUX ? 4096 : 2048;
+  static constexpr int SMEM_BYTES = STAGING_OFF + 1024 /*align slack*/ + kEpiWarps * WARP_STAGING /*TMA-store staging*/;
+  static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 };
 
 __device__ __forceinline__ void seg_coords(const SegInfo& s, int vc, int& c0, int& q, int& p) {
@@ -410,19 +415,49 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const Out
 }
 
 // Backward of GELU on the TMA-store path (dgrad only): out (bf16) = acc * saved GELU'(h), optional fused column sums
-// (the bias gradient of the Linear whose output was h).  Row per lane: the lane reads its own 64 bytes of the saved
-// factor per 32-column chunk (issued before the TMEM wait), multiplies, packs, stages and TMA-stores like the plain
-// path; the column sums of the stored bf16 values are a 5-step reduce-scatter across the warp (lane l ends with column
-// l) and one atomic per lane.  ~5x fewer issued instructions per element than the generic epilogue.
+// (the bias gradient of the Linear whose output was h).
+//
+// clock64 counters of the three roles (profiles/r02_gemm_cycle_counters.txt) showed this epilogue to be what the K = 384
+// dgrad waits for: 9700 cycles per tile with the MMA thread idle 5200 of them, because every 32 x 32 chunk began with
+// a DRAM round trip for its factors (row-per-lane global loads, consumed ~3000 cycles later); registers for a deeper
+// software pipeline do not exist (64 accumulator + 16 factor + 16 result registers per chunk).  So the factors now come
+// the way the operands do: ONE TMA box per chunk ([32 rows x 32 columns], 64B swizzle = the staging layout) into a
+// shared-memory tile owned by the warp, completion on the warp's own mbarrier, issued a whole tile before use:
+//
+//   tile t, chunk c (tile X_c of this warp):  wait barrier_c -> each lane reads its row's 64 B of factors -> multiply,
+//   pack -> the SAME tile X_c stages the output -> TMA store -> (column sums from registers) -> once the store has read
+//   X_c: TMA load of the factors of (tile t + gridDim, chunk c) into X_c.
+//
+// Two tiles per warp (64 KB per CTA) are paid for with one operand stage (3 instead of 4).
+struct AuxPipe {
+  uint8_t* buf;        // this warp's two 2 KB tiles
+  uint64_t* bar;       // [2] mbarriers, one per tile
+  uint32_t phase[2];
+};
+
+template <int BN>
+__device__ __forceinline__ bool aux_issue(const GemmParams& p, const OutMaps& om, AuxPipe& ap, int lane, int lane_grp,
+                                          int col_q, int tile, int ch) {
+  constexpr int CHUNKS = BN / 32 / 4;
+  if (tile >= p.total_tiles) return false;
+  const int m_blk = tile / p.n_blocks, n_blk = tile - m_blk * p.n_blocks;
+  const int b = m_blk / p.mb_per_batch;
+  const int row0 = (m_blk - b * p.mb_per_batch) * BM + lane_grp * 32;
+  const int n0 = n_blk * BN + (col_q * CHUNKS + ch) * 32;
+  const bool live = n0 < p.N && row0 < p.L;   // warp-uniform; the same predicate gates the consumer
+  if (live && lane == 0) {
+    mbar_arrive_expect_tx(&ap.bar[ch], 2048);   // (TMA always delivers the whole box: out-of-range parts are zero-filled)
+    tma_load_3d(ap.buf + ch * 2048, &om.o2, &ap.bar[ch], n0, row0, b);
+  }
+  return live;
+}
+
 template <int BN, typename Arrive>
-__device__ __forceinline__ void epilogue_tile_tma_aux(const GemmParams& p, const OutMaps& om, uint32_t t_base, uint8_t* stg,
-                                                      int lane, int lane_grp, int col_q, int n_blk, int b,
-                                                      int row_in_batch0, Arrive arrive) {
+__device__ __forceinline__ void epilogue_tile_tma_aux(const GemmParams& p, const OutMaps& om, uint32_t t_base, AuxPipe& ap,
+                                                      int lane, int lane_grp, int col_q, int tile, int n_blk, int b,
+                                                      int row_in_batch0, int next_tile, Arrive arrive) {
   constexpr int CHUNKS = BN / 32 / 4;
   const int row0 = row_in_batch0 + lane_grp * 32;
-  const bool row_ok = row0 + lane < p.L;
-  const bf16* arow = p.aux + (static_cast<long long>(b) * p.L + row0 + lane) * p.ld_aux;
-  uint8_t* srow = stg + lane * 64;
   const int sw = (lane >> 1) & 3;
   uint32_t v[32];
   tmem_ld_32x32(t_base, v);
@@ -430,12 +465,8 @@ __device__ __forceinline__ void epilogue_tile_tma_aux(const GemmParams& p, const
   for (int ch = 0; ch < CHUNKS; ++ch) {
     const int n0 = n_blk * BN + (col_q * CHUNKS + ch) * 32;
     const bool live = n0 < p.N && row0 < p.L;   // warp-uniform
-    uint4 a[4];
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      a[c] = make_uint4(0u, 0u, 0u, 0u);        // rows >= L / columns >= N contribute zeros (N is a multiple of 8)
-      if (live && row_ok && n0 + 8 * c < p.N) a[c] = *reinterpret_cast<const uint4*>(arow + n0 + 8 * c);
-    }
+    uint8_t* stg = ap.buf + ch * 2048;
+    uint8_t* srow = stg + lane * 64;
     tmem_ld_wait();
     float f[32];
 #pragma unroll
@@ -447,47 +478,55 @@ __device__ __forceinline__ void epilogue_tile_tma_aux(const GemmParams& p, const
       __syncwarp();
       if (lane == 0) arrive();
     }
-    if (!live) continue;
-    uint32_t w[16];
+    if (live) {
+      mbar_wait(&ap.bar[ch], ap.phase[ch]);     // the factors of this chunk have landed (issued one tile ago)
+      ap.phase[ch] ^= 1;
+      uint4 a[4];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      const uint32_t aw[4] = {a[c].x, a[c].y, a[c].z, a[c].w};
+      for (int c = 0; c < 4; ++c) a[c] = *reinterpret_cast<const uint4*>(srow + ((c ^ sw) << 4));
+      uint32_t w[16];
 #pragma unroll
-      for (int t = 0; t < 4; ++t)
-        w[4 * c + t] = pack_bf16x2(f[8 * c + 2 * t] * __uint_as_float(aw[t] << 16),
-                                   f[8 * c + 2 * t + 1] * __uint_as_float(aw[t] & 0xffff0000u));
-    }
-    if (lane == 0) bulk_wait_read0();   // the previous TMA store of this warp has finished reading the staging tile
-    __syncwarp();
+      for (int c = 0; c < 4; ++c) {
+        const uint32_t aw[4] = {a[c].x, a[c].y, a[c].z, a[c].w};
 #pragma unroll
-    for (int c = 0; c < 4; ++c)
-      *reinterpret_cast<uint4*>(srow + ((c ^ sw) << 4)) = make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
-    fence_proxy_async_smem();
-    __syncwarp();
-    if (lane == 0) {
-      tma_store_3d(&om.o, stg, n0, row0, b);
-      bulk_commit();
-    }
-    if (p.colsum != nullptr) {
-      // sums of the values as stored (bf16), like autograd's bias gradient: reduce-scatter over the 32 rows of the warp
-      float c32[32];
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        c32[2 * j] = __uint_as_float(w[j] << 16);
-        c32[2 * j + 1] = __uint_as_float(w[j] & 0xffff0000u);
+        for (int t = 0; t < 4; ++t)
+          w[4 * c + t] = pack_bf16x2(f[8 * c + 2 * t] * __uint_as_float(aw[t] << 16),
+                                     f[8 * c + 2 * t + 1] * __uint_as_float(aw[t] & 0xffff0000u));
       }
+      __syncwarp();                           // every lane has read its factors: the tile now stages the output
 #pragma unroll
-      for (int s = 16; s >= 1; s >>= 1) {
-        const bool up = (lane & s) != 0;
+      for (int c = 0; c < 4; ++c)
+        *reinterpret_cast<uint4*>(srow + ((c ^ sw) << 4)) = make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_3d(&om.o, stg, n0, row0, b);
+        bulk_commit();
+      }
+      if (p.colsum != nullptr) {
+        // sums of the values as stored (bf16), like autograd's bias gradient: reduce-scatter over the 32 rows of the warp
+        float c32[32];
 #pragma unroll
-        for (int i = 0; i < s; ++i) {
-          const float mine = up ? c32[s + i] : c32[i];
-          const float other = up ? c32[i] : c32[s + i];
-          c32[i] = mine + __shfl_xor_sync(0xffffffffu, other, s);
+        for (int j = 0; j < 16; ++j) {
+          c32[2 * j] = __uint_as_float(w[j] << 16);
+          c32[2 * j + 1] = __uint_as_float(w[j] & 0xffff0000u);
         }
+#pragma unroll
+        for (int s = 16; s >= 1; s >>= 1) {
+          const bool up = (lane & s) != 0;
+#pragma unroll
+          for (int i = 0; i < s; ++i) {
+            const float mine = up ? c32[s + i] : c32[i];
+            const float other = up ? c32[i] : c32[s + i];
+            c32[i] = mine + __shfl_xor_sync(0xffffffffu, other, s);
+          }
+        }
+        if (n0 + lane < p.N) atomicAdd(p.colsum + n0 + lane, c32[0]);
       }
-      if (n0 + lane < p.N) atomicAdd(p.colsum + n0 + lane, c32[0]);
+      if (lane == 0) bulk_wait_read0();       // the store has read the tile: it may receive the next tile's factors
     }
+    __syncwarp();
+    aux_issue<BN>(p, om, ap, lane, lane_grp, col_q, next_tile, ch);
   }
 }
 
@@ -496,7 +535,8 @@ template <int BN, int MODE, bool HEAVY>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmB1, const __grid_constant__ OutMaps om, const GemmParams p) {
-  using C = Cfg<BN>;
+  constexpr bool AUXQ = (MODE == 2 && HEAVY);   // GELU-backward dgrad: TMA-fed factor tiles (see epilogue_tile_tma_aux)
+  using C = Cfg<BN, AUXQ>;
   constexpr bool WGRAD = (MODE == 1);
   constexpr bool B_MN = (MODE != 0);
   constexpr int STAGES = C::STAGES;
@@ -507,6 +547,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   uint64_t* tfull_bar = empty_bar + STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* aux_bar = full_bar + 64;            // [kEpiWarps][2], 512 bytes into the barrier KB
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -523,6 +564,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], kEpiWarps);
+    }
+    if constexpr (AUXQ) {
+      for (int i = 0; i < 2 * kEpiWarps; ++i) mbar_init(&aux_bar[i], 1);
     }
     fence_mbar_init();
   }
@@ -691,6 +735,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     int it = 0;
     long long dbg_epi = 0;
     const long long dbg_e0 = p.dbg ? clock64() : 0;
+    AuxPipe ap;
+    ap.buf = smem + C::STAGING_OFF + ew * C::WARP_STAGING;
+    ap.bar = aux_bar + ew * 2;
+    ap.phase[0] = ap.phase[1] = 0;
+    if constexpr (AUXQ) {
+      if (p.tma_store) {   // factors of this CTA's first tile
+#pragma unroll
+        for (int ch = 0; ch < BN / 128; ++ch) aux_issue<BN>(p, om, ap, lane, lane_grp, col_q, blockIdx.x, ch);
+      }
+    }
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
@@ -716,12 +770,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const uint32_t t_base = t_acc + col_q * (CHUNKS * 32);   // (TMA-store paths: CHUNKS consecutive chunks per warp)
       if constexpr (!WGRAD) {
         if (p.tma_store) {
-          if constexpr (MODE == 2 && HEAVY) {   // (for dgrad the second instantiation is the GELU-backward path)
-            epilogue_tile_tma_aux<BN>(p, om, t_base, smem + C::STAGING_OFF + ew * 2048, lane, lane_grp, col_q, n_blk, b,
-                                      row_in_batch0, [&]() { mbar_arrive(&tempty_bar[acc]); });
+          if constexpr (AUXQ) {   // (for dgrad the second instantiation is the GELU-backward path)
+            epilogue_tile_tma_aux<BN>(p, om, t_base, ap, lane, lane_grp, col_q, tile, n_blk, b, row_in_batch0,
+                                      tile + static_cast<int>(gridDim.x), [&]() { mbar_arrive(&tempty_bar[acc]); });
           } else {
-            epilogue_tile_tma<BN, HEAVY>(p, om, t_base, smem + C::STAGING_OFF + ew * 2048, lane, lane_grp, col_q, n_blk, b,
-                                         row_in_batch0, [&]() { mbar_arrive(&tempty_bar[acc]); });
+            epilogue_tile_tma<BN, HEAVY>(p, om, t_base, ap.buf, lane, lane_grp, col_q, n_blk, b, row_in_batch0,
+                                         [&]() { mbar_arrive(&tempty_bar[acc]); });
           }
           continue;
         }
@@ -1104,6 +1158,10 @@ static int setup_out_maps(GemmParams& p, OutMaps& om, int N, int L, int batch, b
     rc = encode_out_map(&om.o2, p.out2, N, L, batch, p.ld_out2);
     if (rc) return rc;
   }
+  if (gelu_bwd) {   // the saved factors have the output's shape: same box geometry, read by TMA loads (OutMaps::o2)
+    rc = encode_out_map(&om.o2, p.aux, N, L, batch, p.ld_aux);
+    if (rc) return rc;
+  }
   p.tma_store = 1;
   return WJ_OK;
 }
@@ -1123,12 +1181,13 @@ static int launch_variant(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
                           const GemmParams& p, int grid, cudaStream_t st) {
   static bool attr_set = false;
   auto kern = gemm_kernel<BN, MODE, HEAVY>;
+  constexpr int kSmem = Cfg<BN, (MODE == 2 && HEAVY)>::SMEM_BYTES;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
     if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return WJ_ERR_RUNTIME; }
     attr_set = true;
   }
-  kern<<<grid, kThreads, Cfg<BN>::SMEM_BYTES, st>>>(tmA, tmB, tmB1, om, p);
+  kern<<<grid, kThreads, kSmem, st>>>(tmA, tmB, tmB1, om, p);
   return check_launch("gemm_tcgen05 launch");
 }
 
