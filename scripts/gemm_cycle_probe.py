@@ -62,3 +62,36 @@ probe("pred dgrad plain K384 N1536", 172433, 1536, 384, mode="dgrad")
 probe("pred dgrad x aux K384 N1536", 172433, 1536, 384, mode="dgrad", act=2, aux=True)
 probe("pred dgrad x aux + colsum", 172433, 1536, 384, mode="dgrad", act=2, aux=True, colsum=True)
 probe("teacher fc1 1cta K768 N3072", 102400, 3072, 768, bn=256)
+
+
+def probe_wgrad(name, M, Nw, Kw):
+    dy, x = torch.randn(M, Nw, device=dev).bfloat16(), torch.randn(M, Kw, device=dev).bfloat16()
+    out = torch.zeros(Nw, Kw, device=dev)
+    call = lambda: ops.gemm_wgrad(ops.plain_operand(dy), ops.plain_operand(x), M, 1, out, accumulate=True)
+    for _ in range(3):
+        call()
+    torch.cuda.synchronize()
+    cnt.zero_()
+    lib.wj_gemm_debug(C.c_void_p(cnt.data_ptr()))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    call()
+    e1.record()
+    torch.cuda.synchronize()
+    lib.wj_gemm_debug(None)
+    c = cnt.view(148, 8).double()
+    tiles = c[:, 6].clamp(min=1)
+    tot, wf, we = c[:, 2].mean().item(), c[:, 0].mean().item(), c[:, 1].mean().item()
+    print(f"{name:34s} {e0.elapsed_time(e1)*1e3:7.1f} us ({2.0*M*Nw*Kw/e0.elapsed_time(e1)/1e9:6.0f} TFLOP/s) | MMA thread per CTA (cycles): total {tot:9.0f} = "
+          f"wait operands {wf:9.0f} ({100*wf/tot:4.1f} %) + wait free accumulator {we:7.0f} + issue/other {tot-wf-we:9.0f} | tiles/CTA {tiles.mean().item():.1f}")
+
+
+probe_wgrad("wgrad pred [1536 x 384]", 172433, 1536, 384)
+probe_wgrad("wgrad pred [384 x 1536]", 172433, 384, 1536)
+probe_wgrad("wgrad pred [1152 x 384]", 172433, 1152, 384)
+probe_wgrad("wgrad pred [384 x 384]", 172433, 384, 384)
+probe_wgrad("wgrad student [3072 x 768]", 19906, 3072, 768)
+probe_wgrad("wgrad student [768 x 768]", 19906, 768, 768)
+probe("student dgrad plain K3072 N768", 19906, 768, 3072, mode="dgrad")
+probe("student fc2 fwd 1cta K3072 N768", 19906, 768, 3072, bn=256)
+probe("pred fc2 dgrad K1536 N384", 172433, 384, 1536, mode="dgrad")

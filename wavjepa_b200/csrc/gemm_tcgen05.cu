@@ -1378,6 +1378,7 @@ extern "C" int wj_gemm_wgrad_bf16(const wj_operand_t* dY, const wj_operand_t* X,
   fill_seg(p.seg, X);
   p.b_single = (X->seg_width == 0 || X->seg_width % block_n == 0) ? 1 : 0;
   p.out = out; p.ld_out = ld_out; p.out_f32 = 1;
+  p.dbg = g_gemm_dbg;
   p.accumulate = (accumulate || splits > 1 || transposed) ? 1 : 0;
   p.transpose_out = transposed ? 1 : 0;
   if ((splits > 1 || transposed) && !accumulate) {
