@@ -24,7 +24,7 @@ teacher = w.JEPA(feature_extractor=w.ConvFeatureExtractor(conv_layers_spec=SPEC,
                  transformer_encoder_cfg=w.TransformerEncoderCFG.create(),
                  transformer_encoder_layers_cfg=w.TransformerLayerCFG.create(),
                  transformer_decoder_cfg=w.TransformerEncoderCFG.create(),
-                 transformer_decoder_layers_cfg=w.TransformerLayerCFG.create(d_model=384))
+                 transformer_decoder_layers_cfg=w.TransformerLayerCFG.create(d_model=384), process_audio_seconds=2.01)
 m._set_teacher({"state_dict": teacher.state_dict()})     # random-init weights (there is no network for checkpoints)
 m.to(dev)
 m.global_step = 5000
@@ -39,8 +39,9 @@ batch = (audio, rir, noise, torch.full((B,), T32 // 2, device=dev), torch.full((
          torch.full((B,), 10.0, device=dev))
 
 
-def timed(fn, reps):
-    fn()
+def timed(fn, reps, warmup=1):
+    for _ in range(warmup):
+        fn()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     for _ in range(reps):
@@ -49,7 +50,7 @@ def timed(fn, reps):
     return (time.perf_counter() - t0) / reps * 1e3, out
 
 
-ms_prep, (gen16, clean16) = timed(lambda: m.on_after_batch_transfer(batch, 0), 3)
+ms_prep, (gen16, clean16) = timed(lambda: m.on_after_batch_transfer(batch, 0), 5, warmup=3)
 for _ in range(3):
     m.train_step(gen16, clean16)
 n0 = _lib.kernel_launches()

@@ -70,7 +70,7 @@ else:
                   transformer_encoder_cfg=w.TransformerEncoderCFG.create(),
                   transformer_encoder_layers_cfg=w.TransformerLayerCFG.create(),
                   transformer_decoder_cfg=w.TransformerEncoderCFG.create(),
-                  transformer_decoder_layers_cfg=w.TransformerLayerCFG.create(d_model=384))
+                  transformer_decoder_layers_cfg=w.TransformerLayerCFG.create(d_model=384), process_audio_seconds=2.01)
     model = hear.load_model({"state_dict": init.state_dict()})     # random-init weights (no network for checkpoints)
     n, L = 256, 160000
     audio = (torch.rand(n, L, device=dev) * 2 - 1)
