@@ -200,7 +200,9 @@ def _hbm_kernels(kp, peaks, traffic):
             # fill, scripts/bw_probe.py), not at the 6.5 TB/s of the read+write copy that `hbm_peak_gbs` measures
             e["frac_of_write_peak"] = round(gbs / HBM_WRITE_PEAK_GBS, 4)
             e["write_peak_gbs"] = HBM_WRITE_PEAK_GBS
-        if traffic is not None and name[3:] in traffic.get("by_entry", {}):
+        # (the ncu launch list cannot tell the stand-alone wj_colsum calls from the colsum launches made inside
+        # wj_attn_varlen_bwd_bias, so no traffic figure is attached to that family)
+        if traffic is not None and name != "wj_colsum" and name[3:] in traffic.get("by_entry", {}):
             t = traffic["by_entry"][name[3:]]
             e["traffic"] = t["dram_bytes_per_step"]
             e["traffic_over_algorithmic"] = round(t["dram_bytes_per_step"] / max(nb, 1), 3)

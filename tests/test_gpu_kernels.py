@@ -448,7 +448,10 @@ def _attn_ref(qkv, cu, D, H):
 @pytest.mark.parametrize("D,H,lens", [(768, 12, [39, 72, 20, 1, 64, 65]), (384, 12, [85, 122, 128, 17]),
                                       (768, 12, [200, 200, 200]), (384, 12, [250, 3]), (384, 12, [5, 0, 128, 0, 33]),
                                       (768, 12, [128] * 40 + [7]), (768, 24, [129, 256, 1, 128]), (384, 12, [257, 5]),
-                                      (768, 12, [256, 255, 130, 2]), (384, 12, [64] * 300 + [100] * 300)])
+                                      (768, 12, [256, 255, 130, 2]), (384, 12, [64] * 300 + [100] * 300),
+                                      # 257..512 tokens: four key blocks / query tiles on the 512-column forward
+                                      (768, 12, [400, 400, 37]), (384, 12, [400, 230, 512, 1]),
+                                      (768, 12, [512, 385, 384, 129] * 3), (384, 12, [272, 7] * 40), (384, 12, [600, 5])])
 def test_attention_fwd_bwd(D, H, lens):
     cu_l = [0]
     for n in lens:

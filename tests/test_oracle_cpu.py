@@ -169,6 +169,9 @@ def test_schedules_and_geometry():
     assert m._get_ema_decay(0) == pytest.approx(0.999)
     assert out_length(jo.BASE_SPEC, 32159) == 200 and out_length(jo.BASE_SPEC, 64319) == 401
     assert m.extract_audio.receptive_fields[0] == 240
+    m.global_step = 93750   # wavjepa/jepa.py:272-273: 1 - global_step / max_steps (375000 by default)
+    assert m.get_aug_prob() == pytest.approx(0.75)
+    m.global_step = 0
 
 
 def test_no_cpu_fallback():

@@ -28,9 +28,10 @@ struct AttnTcParams {
   float* lse2;
 };
 
-// KT = keys per item (128 or 256 = TMEM columns of S); sequences of 129..256 tokens run as two query tiles.  With
-// KT = 256 the keys are split into two 128-key halves, each with its own 4 softmax warps (own max / sum, own P and O
-// blocks in TMEM); the epilogue merges the two partial results (flash-decoding style) from (max, sum) pairs in smem.
+// KT = keys per item (128, 256 or 512 = TMEM columns of S); sequences of 129..512 tokens run as 2..4 query tiles.  With
+// KT > 128 the keys are split into 128-key blocks ("halves": 2 or 4), each with its own 4 softmax warps (own max / sum,
+// own P and O blocks in TMEM); the epilogue merges the partial results (flash-decoding style) from (max, sum) pairs in
+// smem.  KT = 512 (the 400-token binaural sequences) takes all of TMEM and 192 KB of smem: one CTA per SM.
 template <int DH, int KT> struct AttnTcCfg {
   static constexpr int TILE = kAtQ * DH * 2;                 // bytes of one [128 x DH] bf16 tile
   static constexpr int HALVES = KT / 128;
@@ -39,8 +40,8 @@ template <int DH, int KT> struct AttnTcCfg {
   static constexpr int STAGE = 3 * HALVES * TILE;            // Q tile(s) | K | V of one (sequence, head)
   static constexpr int STAGES = DH == 32 ? 2 : 1;            // 48 KB (KT 128) / 96 KB (KT 256) either way
   static constexpr int BAR_OFF = STAGES * STAGE;
-  static constexpr int ML_OFF = BAR_OFF + 128;               // (max, sum) [2 item parities][2 halves][128 rows] float2
-  static constexpr int SMEM = ML_OFF + (HALVES == 2 ? 4096 : 0) + 1024;   // + alignment slack
+  static constexpr int ML_OFF = BAR_OFF + 128;               // (max, sum) [2 item parities][HALVES][128 rows] float2
+  static constexpr int SMEM = ML_OFF + (HALVES >= 2 ? 2 * HALVES * kAtQ * 8 : 0) + 1024;   // + alignment slack
   static constexpr int CTAS = 512 / KT;                      // per SM, by TMEM columns
   static constexpr uint32_t SWZ = DH == 64 ? 2u : 4u;        // UMMA layout type: 128B / 64B swizzle
   static constexpr uint32_t SBO = DH == 64 ? 1024u : 512u;   // 8 rows x row pitch
@@ -81,9 +82,17 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t* v) {
       : "r"(taddr)
       : "memory");
 }
-// EC (16 / 32 / 64) consecutive fp32 columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld_32x8(uint32_t taddr, uint32_t* v) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr)
+               : "memory");
+}
+// EC (8 / 16 / 32 / 64) consecutive fp32 columns of this thread's TMEM lane
 template <int EC> __device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t* v) {
-  if constexpr (EC == 16) {
+  if constexpr (EC == 8) {
+    tmem_ld_32x8(taddr, v);
+  } else if constexpr (EC == 16) {
     tmem_ld_32x16(taddr, v);
   } else {
 #pragma unroll
@@ -134,7 +143,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const AttnTcParams p
       auto issue_loads = [&](int unit, int stage) {
         const int s = unit / p.H, head = unit - s * p.H;
         const int start = p.cu[s];
-        const int halves = (QT == 2 && p.cu[s + 1] - start > 128) ? 2 : 1;   // 128-token tiles that hold valid tokens
+        const int halves = min(QT, (p.cu[s + 1] - start + 127) >> 7);   // 128-token tiles that hold valid tokens (>= 1)
         uint8_t* base = smem + stage * Cfg::STAGE;
         mbar_arrive_expect_tx(bar_load + stage, 3 * halves * Cfg::TILE);
         for (int h = 0; h < halves; ++h) {
@@ -151,7 +160,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const AttnTcParams p
         const int s = unit / p.H;
         const int n = p.cu[s + 1] - p.cu[s];
         const int n16 = (n + 15) & ~15;
-        const uint32_t idesc_s = umma_idesc_bf16(kAtQ, n16 > 0 ? n16 : 16, false, false);
+        // S = Q K^T over the n16 valid keys: one UMMA group of N <= 256 per 256-key chunk
+        const int nc0 = n16 > 256 ? 256 : (n16 > 0 ? n16 : 16);
+        const uint32_t idesc_s = umma_idesc_bf16(kAtQ, nc0, false, false);
+        const uint32_t idesc_s1 = umma_idesc_bf16(kAtQ, n16 > 256 ? n16 - 256 : 16, false, false);
         const uint32_t sQ = smem_u32(smem + stage * Cfg::STAGE), sK = sQ + QT * Cfg::TILE, sV = sK + QT * Cfg::TILE;
         const uint64_t vdesc = umma_smem_desc(sV, Cfg::TILE, Cfg::SBO, Cfg::SWZ);
 #pragma unroll 1
@@ -171,6 +183,14 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const AttnTcParams p
           for (int ks = 0; ks < DH / 16; ++ks)
             umma_bf16(tmem_base, umma_smem_desc(sQ + qt * Cfg::TILE + ks * 32, 0, Cfg::SBO, Cfg::SWZ),
                       umma_smem_desc(sK + ks * 32, 0, Cfg::SBO, Cfg::SWZ), idesc_s, ks > 0 ? 1u : 0u);
+          if constexpr (HALVES == 4) {
+            if (n16 > 256) {
+#pragma unroll
+              for (int ks = 0; ks < DH / 16; ++ks)
+                umma_bf16(tmem_base + 256, umma_smem_desc(sQ + qt * Cfg::TILE + ks * 32, 0, Cfg::SBO, Cfg::SWZ),
+                          umma_smem_desc(sK + 2 * Cfg::TILE + ks * 32, 0, Cfg::SBO, Cfg::SWZ), idesc_s1, ks > 0 ? 1u : 0u);
+            }
+          }
           umma_commit(bar_s);
           if (STAGES == 2 && qt == 0 && unit + gridDim.x < p.items) issue_loads(unit + gridDim.x, stage ^ 1);   // lands during the softmax
           mbar_wait(bar_p, ph_p);
@@ -264,7 +284,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const AttnTcParams p
         }
         tmem_st_32x32_x16(tSh + (c0 >> 1), w);
       }
-      if constexpr (HALVES == 2) sML[((it & 1) * 2 + half) * kAtQ + row] = make_float2(ms, l);
+      if constexpr (HALVES >= 2) sML[((it & 1) * HALVES + half) * kAtQ + row] = make_float2(ms, l);
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
@@ -279,7 +299,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const AttnTcParams p
       if constexpr (HALVES == 1) {
         tmem_ld_cols<EC>(tmem_base + lane_addr + Cfg::O_COL, o);
         tmem_ld_wait();
-      } else {
+      } else if constexpr (HALVES == 2) {
         const float2 a = sML[((it & 1) * 2 + 0) * kAtQ + row], b = sML[((it & 1) * 2 + 1) * kAtQ + row];
         const bool hasb = n > 128;                   // warp-uniform
         mtot = hasb ? fmaxf(a.x, b.x) : a.x;
@@ -297,6 +317,38 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const AttnTcParams p
         } else {
           tmem_ld_wait();
         }
+      } else {
+        // merge the partial results of the key blocks that hold valid keys (nb is warp-uniform)
+        const int nb = min(HALVES, (n + 127) >> 7);
+        const float2* ml = sML + (it & 1) * HALVES * kAtQ + row;
+        float mb[HALVES], fb[HALVES];
+        mtot = ml[0].x;
+#pragma unroll
+        for (int b = 0; b < HALVES; ++b) {
+          mb[b] = b < nb ? ml[b * kAtQ].x : -INFINITY;
+          mtot = fmaxf(mtot, mb[b]);
+        }
+        lsum = 0.f;
+#pragma unroll
+        for (int b = 0; b < HALVES; ++b) {
+          fb[b] = b < nb ? ex2_approx(mb[b] - mtot) : 0.f;
+          if (b < nb) lsum += ml[b * kAtQ].y * fb[b];
+        }
+        tmem_ld_cols<EC>(tmem_base + lane_addr + Cfg::O_COL + half * EC, o);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < EC; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) * fb[0]);
+#pragma unroll
+        for (int b = 1; b < HALVES; ++b) {
+          if (b < nb) {
+            uint32_t ob[EC];
+            tmem_ld_cols<EC>(tmem_base + b * 128 + lane_addr + Cfg::O_COL + half * EC, ob);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < EC; ++j) o[j] = __float_as_uint(fmaf(__uint_as_float(ob[j]), fb[b], __uint_as_float(o[j])));
+          }
+        }
+        fa = 1.f;
       }
       tc_fence_before();
       __syncwarp();
@@ -654,7 +706,7 @@ typedef CUresult (*PFN_encodeTiledA)(CUtensorMap*, CUtensorMapDataType, cuuint32
 int attn_fwd_tc_launch(const void* qkv, const int* cu, int n_seqs, int max_len, long long total_tokens, int D, int H,
                        void* out, float* lse2, cudaStream_t st) {
   const int dh = D / H;
-  if (max_len > 256 || D % 64 != 0 || (dh != 32 && dh != 64) || total_tokens <= 0) return 1;
+  if (max_len > 512 || D % 64 != 0 || (dh != 32 && dh != 64) || total_tokens <= 0) return 1;
   static PFN_encodeTiledA enc = nullptr;
   if (enc == nullptr) {
     void* sym = nullptr;
@@ -673,7 +725,7 @@ int attn_fwd_tc_launch(const void* qkv, const int* cu, int n_seqs, int max_len, 
           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
     return 1;
   AttnTcParams p;
-  const int qt = max_len > 128 ? 2 : 1;
+  const int qt = max_len > 256 ? 4 : (max_len > 128 ? 2 : 1);
   p.cu = cu; p.n_seqs = n_seqs; p.D = D; p.H = H; p.items = n_seqs * H;   // units = (sequence, head)
   p.scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(dh));
   p.out = reinterpret_cast<bf16*>(out); p.lse2 = lse2;
@@ -685,6 +737,8 @@ int attn_fwd_tc_launch(const void* qkv, const int* cu, int n_seqs, int max_len, 
     kernel<<<grid, threads, smem, st>>>(tm, p);
     return check_launch("attn_fwd_tc");
   };
+  if (dh == 64 && qt == 4) return go(attn_fwd_tc_kernel<64, 512>, AttnTcCfg<64, 512>::SMEM, AttnTcCfg<64, 512>::CTAS, AttnTcCfg<64, 512>::THREADS);
+  if (qt == 4) return go(attn_fwd_tc_kernel<32, 512>, AttnTcCfg<32, 512>::SMEM, AttnTcCfg<32, 512>::CTAS, AttnTcCfg<32, 512>::THREADS);
   if (dh == 64 && qt == 1) return go(attn_fwd_tc_kernel<64, 128>, AttnTcCfg<64, 128>::SMEM, AttnTcCfg<64, 128>::CTAS, AttnTcCfg<64, 128>::THREADS);
   if (dh == 64) return go(attn_fwd_tc_kernel<64, 256>, AttnTcCfg<64, 256>::SMEM, AttnTcCfg<64, 256>::CTAS, AttnTcCfg<64, 256>::THREADS);
   if (qt == 1) return go(attn_fwd_tc_kernel<32, 128>, AttnTcCfg<32, 128>::SMEM, AttnTcCfg<32, 128>::CTAS, AttnTcCfg<32, 128>::THREADS);

@@ -109,13 +109,15 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
     const float4 t = __ldg(reinterpret_cast<const float4*>(gamma + (i * 32 + lane) * 4));
     g[4 * i] = t.x; g[4 * i + 1] = t.y; g[4 * i + 2] = t.z; g[4 * i + 3] = t.w;
   }
-  for (int r = 0; r < rows_per_warp; ++r) {
-    const int row = gw * rows_per_warp + r;
-    if (row >= M) break;
+  // D = 768: rows are software-pipelined -- the loads of row r + 1 are issued before row r's arithmetic, so each warp
+  // keeps two rows of HBM requests in flight (only one 8-warp block fits an SM there, and one row per warp in flight
+  // left the 19 906-row launches at half the bandwidth of the long ones).  Narrower rows keep two blocks per SM instead
+  // (the second row buffer would cost the second block).
+  constexpr bool PIPE = D == 768;   // (D = 1024 would spill)
+  auto load_row = [&](int row, float (&xs)[PER], float (&d)[PER], float& mean, float& rstd) {
     const size_t base = static_cast<size_t>(row) * D;
-    const float mean = stats[2 * row], rstd = stats[2 * row + 1];
-    float xh[PER], d[PER];
-    float s1 = 0.f, s2 = 0.f;
+    mean = stats[2 * row];
+    rstd = stats[2 * row + 1];
 #pragma unroll
     for (int i = 0; i < PER / 4; ++i) {
       const int col = (i * 32 + lane) * 4;
@@ -142,12 +144,28 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
         const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
         dv.x += a.x; dv.y += a.y; dv.z += b.x; dv.w += b.y;
       }
-      xh[4 * i] = (xv.x - mean) * rstd; xh[4 * i + 1] = (xv.y - mean) * rstd;
-      xh[4 * i + 2] = (xv.z - mean) * rstd; xh[4 * i + 3] = (xv.w - mean) * rstd;
+      xs[4 * i] = xv.x; xs[4 * i + 1] = xv.y; xs[4 * i + 2] = xv.z; xs[4 * i + 3] = xv.w;
       d[4 * i] = dv.x; d[4 * i + 1] = dv.y; d[4 * i + 2] = dv.z; d[4 * i + 3] = dv.w;
     }
+  };
+  const int row_lo = gw * rows_per_warp;
+  const int row_hi = min(row_lo + rows_per_warp, M);
+  float xh[PER], d[PER], mean = 0.f, rstd = 0.f;
+  if constexpr (PIPE) {
+    if (row_lo < row_hi) load_row(row_lo, xh, d, mean, rstd);
+  }
+  for (int row = row_lo; row < row_hi; ++row) {
+    const size_t base = static_cast<size_t>(row) * D;
+    float nx[PER], nd[PER], nmean = 0.f, nrstd = 0.f;
+    if constexpr (PIPE) {
+      if (row + 1 < row_hi) load_row(row + 1, nx, nd, nmean, nrstd);
+    } else {
+      load_row(row, xh, d, mean, rstd);
+    }
+    float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int i = 0; i < PER; ++i) {
+      xh[i] = (xh[i] - mean) * rstd;
       ag[i] += d[i] * xh[i];
       ab[i] += d[i];
       const float gd = g[i] * d[i];
@@ -172,6 +190,12 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
         u.y = pack_bf16x2(o.z, o.w);
         *reinterpret_cast<uint2*>(dx_bf16 + base + col) = u;
       }
+    }
+    if constexpr (PIPE) {
+#pragma unroll
+      for (int i = 0; i < PER; ++i) { xh[i] = nx[i]; d[i] = nd[i]; }
+      mean = nmean;
+      rstd = nrstd;
     }
   }
   // block reduction of the three column accumulators, then one atomic per column per block

@@ -222,6 +222,14 @@ class JEPA(_ModuleBase):
         pct_remaining = 1 - step / self.ema_end_step
         return self.hparams.ema_end_decay - r * pct_remaining
 
+    def get_aug_prob(self) -> float:
+        """wavjepa/jepa.py:272-273 (unused by the reference's own step; kept for API parity).  Reads the attached
+        trainer's max_steps like the reference, else the module's own."""
+        from ._lightning import attached_trainer
+        tr = attached_trainer(self)
+        max_steps = getattr(tr, "max_steps", None) if tr is not None else None
+        return 1 - (self.global_step / (max_steps if max_steps else self.max_steps))
+
     def lr_at(self, step: int) -> float:
         """transformers.get_cosine_schedule_with_warmup(opt, 100000, max_steps) (wavjepa/jepa.py:224-225)."""
         warm = 100000
