@@ -93,6 +93,10 @@ int wj_gemm_dgrad_bf16(const wj_operand_t* A, const void* W, int64_t ldw, int w_
                        const int32_t* seg_col_off, int L, int batch, int N, int K, const wj_epilogue_t* epi,
                        int block_n, void* stream);
 
+/* Routing switches for A/B measurements and tests: key 1 = weight-gradient GEMMs may use the CTA-pair kernel, key 2 = data
+ * gradient GEMMs may (value 1, the default) or stay on single CTAs (value 0). */
+int wj_gemm_option(int key, int value);
+
 /* Development aid (profiles/r02_gemm_cycle_counters.txt): `counters` = device buffer of 8 int64 per CTA that the
  * single-CTA GEMM launches after this call fill with clock64 counters of their MMA / producer / epilogue roles (time spent
  * waiting for operands, for a free accumulator, for a free stage); NULL (default) switches them off. */

@@ -100,6 +100,55 @@ if "--pair" in sys.argv:
         run(f"{tag} pred fc2 resid f32", 172433, 384, 1536, act=3, f32=True, resid=True, bn=bn)
         run(f"{tag} pred outproj resid f32", 172433, 384, 384, act=3, f32=True, resid=True, bn=bn)
     sys.exit(0)
+if "--grads" in sys.argv:
+    # weight / data gradients that may run on CTA pairs: same process, routing switch on / off
+    def timed(fn, reps=20):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    for name, M, Nw, Kw in (("student fc1 wgrad", 19906, 3072, 768), ("student fc2 wgrad", 19906, 768, 3072),
+                            ("student qkv wgrad", 19906, 2304, 768), ("student out_proj wgrad", 19906, 768, 768),
+                            ("teacher-size fc1 wgrad", 102400, 3072, 768)):
+        dy, x = torch.randn(M, Nw, device=dev).bfloat16(), torch.randn(M, Kw, device=dev).bfloat16()
+        out = torch.empty(Nw, Kw, device=dev)
+        res = []
+        for pair in (1, 0):
+            ops.gemm_option("pair_wgrad", pair)
+            res.append(timed(lambda: ops.gemm_wgrad(ops.plain_operand(dy), ops.plain_operand(x), M, 1, out)))
+        ops.gemm_option("pair_wgrad", 1)
+        fl = 2.0 * M * Nw * Kw / 1e9
+        print(f"{name:28s} M{M} [{Nw} x {Kw}]: pairs {res[0]:.3f} ms {fl/res[0]:.0f} TFLOP/s | single {res[1]:.3f} ms {fl/res[1]:.0f} TFLOP/s")
+    B, L_in, C, k = 512, 6430, 512, 3
+    L_out = (L_in - k) // 2 + 1
+    x, dy = torch.randn(B, L_in, C, device=dev).bfloat16(), torch.randn(B, L_out, C, device=dev).bfloat16()
+    out = torch.empty(C, k * C, device=dev)
+    res = []
+    for pair in (1, 0):
+        ops.gemm_option("pair_wgrad", pair)
+        res.append(timed(lambda: ops.gemm_wgrad(ops.make_operand(dy, C, L_out, B), ops.conv_operand(x, k), L_out, B, out), reps=5))
+    ops.gemm_option("pair_wgrad", 1)
+    fl = 2.0 * B * L_out * C * k * C / 1e9
+    print(f"{'conv1 wgrad':28s} B{B} L_out{L_out}: pairs {res[0]:.3f} ms {fl/res[0]:.0f} TFLOP/s | single {res[1]:.3f} ms {fl/res[1]:.0f} TFLOP/s")
+    del x, dy
+    for name, M, N, K in (("student fc2 dgrad", 19906, 3072, 768), ("student fc1 dgrad", 19906, 768, 3072),
+                          ("student qkv dgrad", 19906, 768, 2304), ("student out_proj dgrad", 19906, 768, 768),
+                          ("conv-like dgrad", 1646080, 512, 1024)):
+        a, w = torch.randn(M, K, device=dev).bfloat16(), (torch.randn(K, N, device=dev) * 0.05).bfloat16()
+        out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+        res = []
+        for bn in (-256, 256):
+            res.append(timed(lambda: ops.gemm_dgrad(ops.plain_operand(a), w, M, 1, out, K=K, N=N, block_n=bn), reps=10))
+        fl = 2.0 * M * N * K / 1e9
+        print(f"{name:28s} M{M} N{N} K{K}: pairs {res[0]:.3f} ms {fl/res[0]:.0f} TFLOP/s | single {res[1]:.3f} ms {fl/res[1]:.0f} TFLOP/s")
+    sys.exit(0)
 if "--conv-wgrad" in sys.argv:
     run_conv_wgrad()
     sys.exit(0)

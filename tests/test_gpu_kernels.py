@@ -182,6 +182,59 @@ def test_dgrad_bf16_out(M, N, K):
     assert rel(out, dy.float() @ w.float()) < BF16_TOL
 
 
+@pytest.mark.parametrize("M,Nw,Kw,splits", [(1000, 256, 256, 0), (50000, 768, 3072, 0), (19906, 2304, 768, 0), (700, 512, 768, 3),
+                                              (300, 768, 768, 1)])
+def test_wgrad_cta_pairs_match_single_ctas(M, Nw, Kw, splits):
+    """Weight gradients with whole 256 x 256 tiles run on CTA pairs (tcgen05 cta_group::2) by default: same result as
+    the single-CTA kernel (routing switch off) up to the fp32 order of the split-token reduction."""
+    dy = torch.randn(M, Nw, device=DEV).bfloat16()
+    x = torch.randn(M, Kw, device=DEV).bfloat16()
+    ref = dy.float().t() @ x.float()
+    outs = []
+    try:
+        for pair in (1, 0):
+            ops.gemm_option("pair_wgrad", pair)
+            out = torch.full((Nw, Kw), float("nan"), device=DEV)
+            ops.gemm_wgrad(ops.plain_operand(dy), ops.plain_operand(x), M, 1, out, splits=splits)
+            assert rel(out, ref) < 5e-5
+            ops.gemm_wgrad(ops.plain_operand(dy), ops.plain_operand(x), M, 1, out, splits=splits, accumulate=True)
+            assert rel(out, 2 * ref) < 5e-5
+            outs.append(out)
+    finally:
+        ops.gemm_option("pair_wgrad", 1)
+    assert rel(outs[0], outs[1]) < 1e-5
+
+
+def test_conv_wgrad_cta_pairs():
+    Bn, Cc, L_in, k = 3, 512, 402, 3
+    x = torch.randn(Bn, L_in, Cc, device=DEV).bfloat16()
+    L_out = (L_in - k) // 2 + 1
+    dy = torch.randn(Bn, L_out, Cc, device=DEV).bfloat16()
+    outs = []
+    try:
+        for pair in (1, 0):
+            ops.gemm_option("pair_wgrad", pair)
+            out = torch.zeros(Cc, k * Cc, device=DEV)
+            ops.gemm_wgrad(ops.make_operand(dy, Cc, L_out, Bn), _conv_operand(x, L_in, k), L_out, Bn, out)
+            outs.append(out)
+    finally:
+        ops.gemm_option("pair_wgrad", 1)
+    assert rel(outs[0], outs[1]) < 1e-5
+
+
+@pytest.mark.parametrize("M,N,K", [(256, 256, 768), (5000, 768, 2304), (19906, 768, 3072), (4099, 3072, 768)])
+def test_dgrad_cta_pairs(M, N, K):
+    """Plain bf16 data gradients with K >= 768 and N % 256 == 0: CTA pairs, bit-identical to single CTAs (same k order)."""
+    dy = torch.randn(M, K, device=DEV).bfloat16()
+    w = (torch.randn(K, N, device=DEV) * 0.05).bfloat16()
+    o_pair = torch.full((M, N), float("nan"), device=DEV, dtype=torch.bfloat16)
+    o_single = torch.full((M, N), float("nan"), device=DEV, dtype=torch.bfloat16)
+    ops.gemm_dgrad(ops.plain_operand(dy), w, M, 1, o_pair, K=K, N=N, block_n=-256)
+    ops.gemm_dgrad(ops.plain_operand(dy), w, M, 1, o_single, K=K, N=N, block_n=256)
+    assert rel(o_pair, dy.float() @ w.float()) < BF16_TOL
+    assert torch.equal(o_pair, o_single)
+
+
 # ------------------------------------------------------------------------------------------------------- masks
 def test_masks_time_inverse_bit_exact():
     from oracle import masks_oracle as mo
@@ -465,6 +518,12 @@ def test_attention_fwd_bwd(D, H, lens):
     qr = qkv.float().requires_grad_(True)
     ref = _attn_ref(qr, cu_l, D, H)
     assert rel(out, ref) < 6e-3
+    if max(lens) > (384 if D // H == 64 else 704):
+        # forward-only length (the 400-token binaural teacher has no backward): the backward keeps a whole sequence in
+        # shared memory and must refuse loudly rather than fall back
+        with pytest.raises(_lib.WavJepaLibError):
+            ops.attn_bwd(qkv, out, torch.zeros_like(out), lse, cu, len(lens), max(lens), D, H, torch.empty_like(qkv))
+        return
     do = torch.randn(tot, D, device=DEV).bfloat16()
     ref.backward(do.float())
     dqkv = torch.full((tot, 3 * D), float("nan"), device=DEV, dtype=torch.bfloat16)

@@ -154,6 +154,10 @@ def load(build_if_missing: bool = False) -> "_Proxy":
     cdll.wj_last_error.restype = C.c_char_p
     cdll.wj_kernel_launches.restype = C.c_longlong
     _lib = _Proxy(cdll)
+    if os.environ.get("WJ_GEMM_PAIR_GRADS") == "0" and hasattr(cdll, "wj_gemm_option"):
+        # measurement switch (same-box A/B): keep the weight- / data-gradient GEMMs on single CTAs
+        cdll.wj_gemm_option(1, 0)
+        cdll.wj_gemm_option(2, 0)
     return _lib
 
 

@@ -355,7 +355,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const AttnTcParams p
       if (lane == 0) mbar_arrive(bar_done);
       if (row < nq) {
         const float inv = fa / lsum;
-        bf16* op = p.out + static_cast<long long>(start + row) * p.D + head * DH + (HALVES == 2 ? half * EC : 0);
+        bf16* op = p.out + static_cast<long long>(start + row) * p.D + head * DH + (HALVES >= 2 ? half * EC : 0);
 #pragma unroll
         for (int j = 0; j < EC; j += 8) {
           uint4 w;

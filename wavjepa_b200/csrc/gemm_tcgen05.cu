@@ -902,12 +902,10 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if constexpr (!B_MN) {
               tma_load_2d_pair(sb, &tmB, fb, kb * BK, n_blk * BN + static_cast<int>(rank) * (BN / 2));
             } else {
+              // dgrad: this CTA's BN/2 output columns = BN/128 MN-major atoms, one 3-D TMA (see gemm_kernel)
               const int si = p.seg.width > 0 ? (kb * BK) / p.seg.width : 0;
               const int r0 = kb * BK - si * (p.seg.width > 0 ? p.seg.width : 0);
-#pragma unroll
-              for (int a = 0; a < BN / 128; ++a)
-                tma_load_2d_pair(sb + a * (BK * 128), &tmB, fb,
-                                 p.segB_col[si] + n_blk * BN + static_cast<int>(rank) * (BN / 2) + a * 64, r0);
+              tma_load_3d_pair(sb, &tmB, fb, 0, r0, (p.segB_col[si] + n_blk * BN + static_cast<int>(rank) * (BN / 2)) >> 6);
             }
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
@@ -929,14 +927,14 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             uint8_t* sb = sa + C::A_BYTES;
             const uint32_t fb = mapa_shared(smem_u32(&full_bar[stage]), 0);
             if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * C::STAGE_BYTES);
-#pragma unroll
-            for (int a = 0; a < BM / 64; ++a)
-              tma_load_4d_pair(sa + a * (BK * 128), &tmA, fb, m_blk * BMP + static_cast<int>(rank) * BM + a * 64, 0, row0, b);
-#pragma unroll
-            for (int a = 0; a < BN / 128; ++a) {
+            // A: this CTA's 128 of the pair tile's 256 dY columns (BM/64 MN-major atoms, one 5-D TMA);
+            // B: its BN/2 of the X columns (BN/128 atoms, one 5-D TMA: the host only routes here when a CTA's half tile
+            // lies inside one segment)
+            tma_load_5d_pair(sa, &tmA, fb, 0, row0, (m_blk * BMP + static_cast<int>(rank) * BM) >> 6, 0, b);
+            {
               int c0, q, po;
-              seg_coords(p.seg, n_blk * BN + static_cast<int>(rank) * (BN / 2) + a * 64, c0, q, po);
-              tma_load_4d_pair(sb + a * (BK * 128), &tmB, fb, c0, q, row0 + po, b);
+              seg_coords(p.seg, n_blk * BN + static_cast<int>(rank) * (BN / 2), c0, q, po);
+              tma_load_5d_pair(sb, &tmB, fb, 0, row0 + po, c0 >> 6, q, b);
             }
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
@@ -1210,7 +1208,9 @@ static int launch_pair_variant(const CUtensorMap& tmA, const CUtensorMap& tmB, c
 template <int BN, int MODE>
 static int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const OutMaps& om, const GemmParams& p,
                        cudaStream_t st) {
-  if (p.tma_store && p.out2 != nullptr) return launch_pair_variant<BN, MODE, true>(tmA, tmB, om, p, st);
+  if constexpr (MODE == 0) {
+    if (p.tma_store && p.out2 != nullptr) return launch_pair_variant<BN, MODE, true>(tmA, tmB, om, p, st);
+  }
   return launch_pair_variant<BN, MODE, false>(tmA, tmB, om, p, st);
 }
 
@@ -1252,6 +1252,16 @@ static void fill_epilogue(GemmParams& p, const wj_epilogue_t* e) {
 }  // namespace wj
 
 using namespace wj;
+
+// Routing switches (A/B measurements and tests): WJ_GEMM_OPT_PAIR_WGRAD / WJ_GEMM_OPT_PAIR_DGRAD = 1 (default) lets the
+// weight- / data-gradient GEMMs use the CTA-pair kernel where the shape allows, 0 keeps them on single CTAs.
+static int g_pair_wgrad = 1, g_pair_dgrad = 1;
+extern "C" int wj_gemm_option(int key, int value) {
+  if (key == 1) g_pair_wgrad = value;
+  else if (key == 2) g_pair_dgrad = value;
+  else { set_error("wj_gemm_option: unknown key %d", key); return WJ_ERR_ARG; }
+  return WJ_OK;
+}
 
 // Development aid: device buffer of 8 int64 per CTA (>= 8 * #SMs) that the single-CTA GEMM kernels fill with cycle
 // counters (see GemmParams::dbg); NULL switches the counters off (the default).
@@ -1340,17 +1350,21 @@ extern "C" int wj_gemm_wgrad_bf16(const wj_operand_t* dY, const wj_operand_t* X,
   const int block_n = (N % 256 == 0 || (transposed && N > 512)) ? 256 : ((N % 128 == 0) ? 128 : 0);
   if (block_n == 0) { set_error("wj_gemm_wgrad_bf16: N must be a multiple of 128"); return WJ_ERR_ARG; }
   if (X->seg_width > 0 && X->seg_width % 64 != 0) { set_error("wj_gemm_wgrad_bf16: bad segment width"); return WJ_ERR_ARG; }
+  // CTA pairs (256 x 256 tiles, each SM stages 128 dY columns and 128 X columns per k-block = 32 KB instead of 48 KB):
+  // whole 256-row / 256-column tiles only, and a CTA's half of the B tile inside one segment
+  const bool pair = g_pair_wgrad && !transposed && M % 256 == 0 && N % 256 == 0 &&
+                    (X->seg_width == 0 || X->seg_width % 128 == 0);
   CUtensorMap tmA, tmB, tmB1;
   int rc = encode_map_mn5(&tmA, dY, BM / 64);
   if (rc) return rc;
-  rc = encode_map_mn5(&tmB, X, (uint32_t)(block_n / 64));
+  rc = encode_map_mn5(&tmB, X, (uint32_t)((pair ? block_n / 2 : block_n) / 64));
   if (rc) return rc;
   rc = encode_map_mn5(&tmB1, X, 1);
   if (rc) return rc;
   GemmParams p;
   memset(&p, 0, sizeof(p));
   p.L = L; p.batch = batch; p.N = N; p.M = M;
-  p.m_blocks = M / BM;
+  p.m_blocks = pair ? M / (2 * BM) : M / BM;
   p.n_blocks = (N + block_n - 1) / block_n;
   p.kb_per_batch = (L + BK - 1) / BK;
   const int kb_total = batch * p.kb_per_batch;
@@ -1358,7 +1372,7 @@ extern "C" int wj_gemm_wgrad_bf16(const wj_operand_t* dY, const wj_operand_t* X,
     // (m, n) tiles x splits should fill whole rounds of the persistent grid: pick the split count with the best
     // occupancy over 1..4 rounds (ties: fewer rounds = fewer fp32 reduce-adds)
     const int mn = p.m_blocks * p.n_blocks;
-    const int sms = num_sms();
+    const int sms = pair ? num_sms() / 2 : num_sms();
     double best = -1.0;
     splits = 1;
     for (int r = 1; r <= 4; ++r) {
@@ -1392,6 +1406,7 @@ extern "C" int wj_gemm_wgrad_bf16(const wj_operand_t* dY, const wj_operand_t* X,
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   OutMaps om;
   memset(&om, 0, sizeof(om));
+  if (pair) return launch_pair<256, 1>(tmA, tmB, om, p, st);
   if (block_n == 256) return launch<256, 1>(tmA, tmB, tmB1, om, p, grid, st);
   return launch<128, 1>(tmA, tmB, tmB1, om, p, grid, st);
 }
@@ -1404,18 +1419,45 @@ extern "C" int wj_gemm_dgrad_bf16(const wj_operand_t* A, const void* W, int64_t 
   if (L <= 0 || batch <= 0) return WJ_OK;
   if (K % BK != 0 || N % 64 != 0) { set_error("wj_gemm_dgrad_bf16: K must be a multiple of 64 and N of 64 (K=%d N=%d)", K, N); return WJ_ERR_ARG; }
   if (A->seg_width > 0 && (A->seg_width % BK != 0 || K > 4 * A->seg_width)) { set_error("wj_gemm_dgrad_bf16: bad segment width"); return WJ_ERR_ARG; }
-  const bool ok192 = tile192_ok(epi, N) && (epi->out_f32 || epi->act == 0);
+  const bool auto_bn = block_n == 0;
+  bool pair = block_n < 0;   // -256: CTA-pair kernel requested explicitly (tests)
+  if (pair) block_n = -block_n;
+  const bool ok192 = !pair && tile192_ok(epi, N) && (epi->out_f32 || epi->act == 0);
   if (block_n == 0) block_n = (ok192 && N % 256 != 0 && N <= 768) ? 192 : ((N % 256 == 0 || N > 1024) ? 256 : 128);
   if (block_n != 128 && block_n != 256 && !(block_n == 192 && ok192)) { set_error("wj_gemm_dgrad_bf16: block_n must be 128 or 256 (192: N %% 192 == 0 with an fp32 or plain bf16 output)"); return WJ_ERR_ARG; }
+  // CTA pairs for the plain bf16-output data gradients (TMA-store epilogue) with K >= 768 and whole 256-column tiles: the
+  // same rule as the forward GEMMs (wj_gemm_bf16)
+  const bool pair_ok = epi != nullptr && !epi->out_f32 && !epi->accumulate && epi->resid == nullptr && epi->out_rows == nullptr &&
+                       epi->colsum == nullptr && epi->out2 == nullptr && epi->act == 0 && epi->ld_out % 8 == 0 &&
+                       reinterpret_cast<uintptr_t>(epi->out) % 16 == 0 && N % 256 == 0;
+  if (pair && !(pair_ok && block_n == 256)) { set_error("wj_gemm_dgrad_bf16: the CTA-pair kernel takes plain bf16 outputs with N %% 256 == 0"); return WJ_ERR_ARG; }
+  if (auto_bn && g_pair_dgrad && pair_ok && K >= 768 && static_cast<long long>(L) * batch >= 4096) {
+    pair = true;
+    block_n = 256;
+  }
   CUtensorMap tmA, tmB;
   const uint32_t boxA[4] = {BK, 1, BM, 1};
   int rc = encode_map(&tmA, A, boxA);
   if (rc) return rc;
-  rc = encode_map_mn3(&tmB, W, (uint64_t)w_rows, (uint64_t)w_cols, (uint64_t)ldw * 2, (uint32_t)(block_n / 64));
+  rc = encode_map_mn3(&tmB, W, (uint64_t)w_rows, (uint64_t)w_cols, (uint64_t)ldw * 2, (uint32_t)((pair ? block_n / 2 : block_n) / 64));
   if (rc) return rc;
   GemmParams p;
   memset(&p, 0, sizeof(p));
   p.L = L; p.batch = batch; p.N = N; p.K = K;
+  if (pair) {
+    p.mb_per_batch = (L + 2 * BM - 1) / (2 * BM);
+    p.m_blocks = batch * p.mb_per_batch;
+    p.n_blocks = N / block_n;
+    p.total_tiles = p.m_blocks * p.n_blocks;
+    fill_seg(p.seg, A);
+    for (int i = 0; i < 4; ++i) p.segB_col[i] = seg_col_off ? seg_col_off[i] : 0;
+    fill_epilogue(p, epi);
+    OutMaps omp;
+    rc = setup_out_maps(p, omp, N, L, batch, /*dgrad=*/true);
+    if (rc) return rc;
+    if (!p.tma_store) { set_error("wj_gemm_dgrad_bf16: pair kernel without a TMA-store epilogue"); return WJ_ERR_ARG; }
+    return launch_pair<256, 2>(tmA, tmB, omp, p, reinterpret_cast<cudaStream_t>(stream));
+  }
   p.mb_per_batch = (L + BM - 1) / BM;
   p.m_blocks = batch * p.mb_per_batch;
   p.n_blocks = (N + block_n - 1) / block_n;

@@ -123,6 +123,12 @@ def gemm_wgrad(dy: Operand, x: Operand, L: int, batch: int, out: torch.Tensor, *
                                  C.c_int64(ld), 1 if accumulate else 0, splits, _stream()))
 
 
+def gemm_option(name: str, value: int) -> None:
+    """Routing switch of the GEMM entry points (A/B measurements, tests): 'pair_wgrad' / 'pair_dgrad' = 1 (default) lets
+    the weight- / data-gradient GEMMs use the CTA-pair kernel where the shape allows, 0 keeps them on single CTAs."""
+    check(_lib.load().wj_gemm_option({"pair_wgrad": 1, "pair_dgrad": 2}[name], int(value)))
+
+
 def gemm_dgrad(a: Operand, w: torch.Tensor, L: int, batch: int, out: torch.Tensor, *, K: int, N: int,
                w_col_offset: int = 0, w_cols: Optional[int] = None, seg_col_off: Sequence[int] = (),
                ld_out: Optional[int] = None, out_offset: int = 0, act: int = ACT_NONE,
