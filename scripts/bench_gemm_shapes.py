@@ -138,14 +138,19 @@ if "--grads" in sys.argv:
     fl = 2.0 * B * L_out * C * k * C / 1e9
     print(f"{'conv1 wgrad':28s} B{B} L_out{L_out}: pairs {res[0]:.3f} ms {fl/res[0]:.0f} TFLOP/s | single {res[1]:.3f} ms {fl/res[1]:.0f} TFLOP/s")
     del x, dy
-    for name, M, N, K in (("student fc2 dgrad", 19906, 3072, 768), ("student fc1 dgrad", 19906, 768, 3072),
-                          ("student qkv dgrad", 19906, 768, 2304), ("student out_proj dgrad", 19906, 768, 768),
-                          ("conv-like dgrad", 1646080, 512, 1024)):
+    for name, M, N, K, gelu in (("student fc2 dgrad", 19906, 3072, 768, False), ("student fc1 dgrad", 19906, 768, 3072, False),
+                                ("student qkv dgrad", 19906, 768, 2304, False), ("student out_proj dgrad", 19906, 768, 768, False),
+                                ("conv-like dgrad", 1646080, 512, 1024, False), ("conv-like dgrad K512", 1646080, 512, 512, False),
+                                ("student fc2 dgrad x GELU'", 19906, 3072, 768, True), ("conv-like dgrad x GELU'", 822784, 512, 1024, True),
+                                ("conv-like dgrad K512 x GELU'", 822784, 512, 512, True)):
         a, w = torch.randn(M, K, device=dev).bfloat16(), (torch.randn(K, N, device=dev) * 0.05).bfloat16()
         out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+        aux = torch.randn(M, N, device=dev).bfloat16() if gelu else None
+        cs = torch.zeros(N, device=dev) if gelu else None
         res = []
         for bn in (-256, 256):
-            res.append(timed(lambda: ops.gemm_dgrad(ops.plain_operand(a), w, M, 1, out, K=K, N=N, block_n=bn), reps=10))
+            res.append(timed(lambda: ops.gemm_dgrad(ops.plain_operand(a), w, M, 1, out, K=K, N=N, block_n=bn,
+                                                    act=ops.ACT_DGELU if gelu else 0, aux=aux, colsum=cs), reps=10))
         fl = 2.0 * M * N * K / 1e9
         print(f"{name:28s} M{M} N{N} K{K}: pairs {res[0]:.3f} ms {fl/res[0]:.0f} TFLOP/s | single {res[1]:.3f} ms {fl/res[1]:.0f} TFLOP/s")
     sys.exit(0)

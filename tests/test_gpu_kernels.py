@@ -233,6 +233,18 @@ def test_dgrad_cta_pairs(M, N, K):
     ops.gemm_dgrad(ops.plain_operand(dy), w, M, 1, o_single, K=K, N=N, block_n=256)
     assert rel(o_pair, dy.float() @ w.float()) < BF16_TOL
     assert torch.equal(o_pair, o_single)
+    # the GELU-backward form (out = acc * saved factor, fused bias-gradient column sums) on CTA pairs
+    aux = torch.randn(M, N, device=DEV).bfloat16()
+    cs_pair, cs_single = torch.zeros(N, device=DEV), torch.zeros(N, device=DEV)
+    o_pair.fill_(float("nan"))
+    o_single.fill_(float("nan"))
+    ops.gemm_dgrad(ops.plain_operand(dy), w, M, 1, o_pair, K=K, N=N, act=ops.ACT_DGELU, aux=aux, colsum=cs_pair, block_n=-256)
+    ops.gemm_dgrad(ops.plain_operand(dy), w, M, 1, o_single, K=K, N=N, act=ops.ACT_DGELU, aux=aux, colsum=cs_single, block_n=256)
+    assert rel(o_pair, (dy.float() @ w.float()) * aux.float()) < BF16_TOL
+    assert torch.equal(o_pair, o_single)
+    assert rel(cs_pair, o_pair.float().sum(0)) < 1e-5 and rel(cs_pair, cs_single) < 1e-5
+    ops.gemm_dgrad(ops.plain_operand(dy), w, M, 1, o_pair, K=K, N=N, act=ops.ACT_DGELU, aux=aux, block_n=-256)   # no column sums
+    assert torch.equal(o_pair, o_single)
 
 
 # ------------------------------------------------------------------------------------------------------- masks

@@ -437,12 +437,13 @@ struct AuxPipe {
 
 template <int BN>
 __device__ __forceinline__ bool aux_issue(const GemmParams& p, const OutMaps& om, AuxPipe& ap, int lane, int lane_grp,
-                                          int col_q, int tile, int ch) {
+                                          int col_q, int tile, int ch, int tile_rows = BM, int row_off = 0) {
+  // tile_rows / row_off: rows of an m-block and this CTA's offset inside it (CTA pairs: 256 and rank * 128)
   constexpr int CHUNKS = BN / 32 / 4;
   if (tile >= p.total_tiles) return false;
   const int m_blk = tile / p.n_blocks, n_blk = tile - m_blk * p.n_blocks;
   const int b = m_blk / p.mb_per_batch;
-  const int row0 = (m_blk - b * p.mb_per_batch) * BM + lane_grp * 32;
+  const int row0 = (m_blk - b * p.mb_per_batch) * tile_rows + row_off + lane_grp * 32;
   const int n0 = n_blk * BN + (col_q * CHUNKS + ch) * 32;
   const bool live = n0 < p.N && row0 < p.L;   // warp-uniform; the same predicate gates the consumer
   if (live && lane == 0) {
@@ -455,7 +456,8 @@ __device__ __forceinline__ bool aux_issue(const GemmParams& p, const OutMaps& om
 template <int BN, typename Arrive>
 __device__ __forceinline__ void epilogue_tile_tma_aux(const GemmParams& p, const OutMaps& om, uint32_t t_base, AuxPipe& ap,
                                                       int lane, int lane_grp, int col_q, int tile, int n_blk, int b,
-                                                      int row_in_batch0, int next_tile, Arrive arrive) {
+                                                      int row_in_batch0, int next_tile, Arrive arrive, int tile_rows = BM,
+                                                      int row_off = 0) {
   constexpr int CHUNKS = BN / 32 / 4;
   const int row0 = row_in_batch0 + lane_grp * 32;
   const int sw = (lane >> 1) & 3;
@@ -526,7 +528,7 @@ __device__ __forceinline__ void epilogue_tile_tma_aux(const GemmParams& p, const
       if (lane == 0) bulk_wait_read0();       // the store has read the tile: it may receive the next tile's factors
     }
     __syncwarp();
-    aux_issue<BN>(p, om, ap, lane, lane_grp, col_q, next_tile, ch);
+    aux_issue<BN>(p, om, ap, lane, lane_grp, col_q, next_tile, ch, tile_rows, row_off);
   }
 }
 
@@ -807,21 +809,24 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 // kernel runs out of.  Barrier protocol: both producers signal the LEADER's full barriers (TMA .cta_group::2), the
 // leader's commits are multicast to the empty / accumulator-full barriers of both CTAs, the epilogue warps of both
 // CTAs arrive on the leader's accumulator-empty barrier.
-template <int BN>
+template <int BN, bool AUX = false>
 struct CfgPair {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = (BN / 2) * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN == 256) ? 6 : 8;
+  static constexpr int STAGES = AUX ? 5 : ((BN == 256) ? 6 : 8);   // AUX (GELU-backward dgrad): see Cfg
   static constexpr int STAGING_OFF = STAGES * STAGE_BYTES + 1024;   // barriers live in the 1 KB before it
-  static constexpr int SMEM_BYTES = STAGING_OFF + 1024 /*align slack*/ + kEpiWarps * 2048 /*TMA-store staging*/;
+  static constexpr int WARP_STAGING = AUX ? 4096 : 2048;
+  static constexpr int SMEM_BYTES = STAGING_OFF + 1024 /*align slack*/ + kEpiWarps * WARP_STAGING /*TMA-store staging*/;
+  static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 };
 
 template <int BN, int MODE, bool HEAVY>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ OutMaps om, const GemmParams p) {
-  using C = CfgPair<BN>;
+  constexpr bool AUXQ = (MODE == 2 && HEAVY);   // GELU-backward dgrad: TMA-fed factor tiles (see epilogue_tile_tma_aux)
+  using C = CfgPair<BN, AUXQ>;
   constexpr bool WGRAD = (MODE == 1);
   constexpr bool B_MN = (MODE != 0);
   constexpr int STAGES = C::STAGES;
@@ -833,6 +838,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* tfull_bar = empty_bar + STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* aux_bar = full_bar + 64;            // [kEpiWarps][2], 512 bytes into the barrier KB
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -853,6 +859,9 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], 2 * kEpiWarps);
+    }
+    if constexpr (AUXQ) {
+      for (int i = 0; i < 2 * kEpiWarps; ++i) mbar_init(&aux_bar[i], 1);
     }
     fence_mbar_init();
   }
@@ -983,6 +992,17 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int col_q = ew >> 2;
     constexpr int CHUNKS = BN / 32 / 4;
     int it = 0;
+    AuxPipe ap;
+    ap.buf = smem + C::STAGING_OFF + ew * C::WARP_STAGING;
+    ap.bar = aux_bar + ew * 2;
+    ap.phase[0] = ap.phase[1] = 0;
+    if constexpr (AUXQ) {
+      if (p.tma_store) {   // factors of this pair's first tile (this CTA's 128 rows)
+#pragma unroll
+        for (int ch = 0; ch < BN / 128; ++ch)
+          aux_issue<BN>(p, om, ap, lane, lane_grp, col_q, pair_id, ch, BMP, static_cast<int>(rank) * BM);
+      }
+    }
     for (int tile = pair_id; tile < p.total_tiles; tile += n_pairs, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
@@ -1006,8 +1026,14 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const uint32_t te = mapa_shared(smem_u32(&tempty_bar[acc]), 0);
       if constexpr (!WGRAD) {
         if (p.tma_store) {   // bf16 outputs: the same staged TMA-store epilogues as the single-CTA kernel
-          epilogue_tile_tma<BN, HEAVY>(p, om, t_base + col_q * (CHUNKS * 32), smem + C::STAGING_OFF + ew * 2048, lane,
-                                       lane_grp, col_q, n_blk, b, row_in_batch0, [&]() { mbar_arrive_cluster(te); });
+          if constexpr (AUXQ) {
+            epilogue_tile_tma_aux<BN>(p, om, t_base + col_q * (CHUNKS * 32), ap, lane, lane_grp, col_q, tile, n_blk, b,
+                                      row_in_batch0, tile + n_pairs, [&]() { mbar_arrive_cluster(te); }, BMP,
+                                      static_cast<int>(rank) * BM);
+          } else {
+            epilogue_tile_tma<BN, HEAVY>(p, om, t_base + col_q * (CHUNKS * 32), ap.buf, lane, lane_grp, col_q, n_blk, b,
+                                         row_in_batch0, [&]() { mbar_arrive_cluster(te); });
+          }
           continue;
         }
       }
@@ -1194,14 +1220,15 @@ static int launch_pair_variant(const CUtensorMap& tmA, const CUtensorMap& tmB, c
                                cudaStream_t st) {
   static bool attr_set = false;
   auto kern = gemm_pair_kernel<BN, MODE, HEAVY>;
+  constexpr int kSmem = CfgPair<BN, (MODE == 2 && HEAVY)>::SMEM_BYTES;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgPair<BN>::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
     if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(pair): %s", cudaGetErrorString(e)); return WJ_ERR_RUNTIME; }
     attr_set = true;
   }
   int pairs = num_sms() / 2;
   if (p.total_tiles < pairs) pairs = p.total_tiles;
-  kern<<<2 * pairs, kThreads, CfgPair<BN>::SMEM_BYTES, st>>>(tmA, tmB, om, p);
+  kern<<<2 * pairs, kThreads, kSmem, st>>>(tmA, tmB, om, p);
   return check_launch("gemm_tcgen05 pair launch");
 }
 
@@ -1210,6 +1237,9 @@ static int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const Out
                        cudaStream_t st) {
   if constexpr (MODE == 0) {
     if (p.tma_store && p.out2 != nullptr) return launch_pair_variant<BN, MODE, true>(tmA, tmB, om, p, st);
+  }
+  if constexpr (MODE == 2) {   // GELU-backward data gradient: the TMA-fed factor pipeline
+    if (p.tma_store && p.act == 2) return launch_pair_variant<BN, MODE, true>(tmA, tmB, om, p, st);
   }
   return launch_pair_variant<BN, MODE, false>(tmA, tmB, om, p, st);
 }
@@ -1427,8 +1457,11 @@ extern "C" int wj_gemm_dgrad_bf16(const wj_operand_t* A, const void* W, int64_t 
   if (block_n != 128 && block_n != 256 && !(block_n == 192 && ok192)) { set_error("wj_gemm_dgrad_bf16: block_n must be 128 or 256 (192: N %% 192 == 0 with an fp32 or plain bf16 output)"); return WJ_ERR_ARG; }
   // CTA pairs for the plain bf16-output data gradients (TMA-store epilogue) with K >= 768 and whole 256-column tiles: the
   // same rule as the forward GEMMs (wj_gemm_bf16)
+  // (plain bf16 outputs, or the GELU-backward form out = acc * saved factor with optional fused column sums)
+  const bool pair_gelu = epi != nullptr && epi->act == 2 && epi->aux != nullptr && epi->bias == nullptr &&
+                         epi->ld_aux % 8 == 0 && reinterpret_cast<uintptr_t>(epi->aux) % 16 == 0;
   const bool pair_ok = epi != nullptr && !epi->out_f32 && !epi->accumulate && epi->resid == nullptr && epi->out_rows == nullptr &&
-                       epi->colsum == nullptr && epi->out2 == nullptr && epi->act == 0 && epi->ld_out % 8 == 0 &&
+                       epi->out2 == nullptr && ((epi->act == 0 && epi->colsum == nullptr) || pair_gelu) && epi->ld_out % 8 == 0 &&
                        reinterpret_cast<uintptr_t>(epi->out) % 16 == 0 && N % 256 == 0;
   if (pair && !(pair_ok && block_n == 256)) { set_error("wj_gemm_dgrad_bf16: the CTA-pair kernel takes plain bf16 outputs with N %% 256 == 0"); return WJ_ERR_ARG; }
   if (auto_bn && g_pair_dgrad && pair_ok && K >= 768 && static_cast<long long>(L) * batch >= 4096) {
