@@ -148,11 +148,11 @@ int wj_conv0_gn_gelu_fwd(const void* x_bf16, const float* w, const float* gamma,
                          void* dgelu_bf16, void* stream);
 /* Backward of the block above given dY (bf16 [B, L_out, C]) and the GELU' saved by the forward (dgelu_bf16, same layout;
  * NULL in the forward = inference, nothing saved); accumulates into dw [C, Cin, 10], dgamma, dbeta (fp32).
- * red_scratch: [B, 2 + Cin*10, C] fp32 workspace.  The convolution itself runs on mma.sync tensor-core tiles in both
- * directions (C must be 512). */
+ * red_scratch: [B, 2 + Cin*10, C] fp64 workspace (fp64 atomics: the weight gradient is a difference of large sums).
+ * The convolution itself runs on mma.sync tensor-core tiles in both directions (C must be 512). */
 int wj_conv0_gn_gelu_bwd(const void* x_bf16, const float* w, const float* gamma, const float* beta, int B, int Cin,
                          int L, int C, int k, int stride, float eps, const double* moments, const float* stats,
-                         const void* dy_bf16, const void* dgelu_bf16, float* red_scratch, float* dw, float* dgamma,
+                         const void* dy_bf16, const void* dgelu_bf16, void* red_scratch, float* dw, float* dgamma,
                          float* dbeta, void* stream);
 
 /* LayerNorm over the last dim (D in {128,256,384,512,768,1024}), biased variance, one warp per row.
@@ -249,6 +249,13 @@ int wj_predictor_assemble(const void* ctx_bf16, const float* mask_token, const f
                           const int* vis_pos, int N, int D, float* out_f32, void* out_bf16, void* stream);
 int wj_predictor_assemble_bwd(const float* dx0, const int* vis_src, int N, int D, float* d_ctx, float* d_mask_token,
                               void* stream);
+/* The context part of that backward as a gather with a fixed summation order (no atomics: the same bits in every run):
+ * d_ctx[s] = sum over the G target groups, in order, of dx0[row of context row s in that group's predictor sequence];
+ * written as fp32 and / or bf16 (either may be NULL).  ctx_vrow [Nc * G] int32 is workspace (the inverse of vis_src,
+ * rebuilt by the call); cu_v [n_seqs + 1] are the predictor sequence offsets, n_seqs = B * G.  With this call
+ * wj_predictor_assemble_bwd takes d_ctx = NULL and only accumulates the mask-token gradient. */
+int wj_predictor_ctx_grad(const float* dx0, const int* vis_src, const int* cu_v, int n_seqs, int G, int Nc, int D,
+                          int* ctx_vrow, float* d_ctx_f32, void* d_ctx_bf16, void* stream);
 
 /* *loss += sum_i mean_d (pred[i,d] - targets[tgt_rows[i], d])^2 / (Nt + 1e-8); dpred (optional, bf16) = d loss / d pred.
  * JEPA.masked_loss (wavjepa/jepa.py:335-362) restricted to the target rows (all other rows have zero weight). */

@@ -592,6 +592,38 @@ def test_gather_scatter_assemble():
     assert rel(dctx, rctx) < 1e-5 and rel(dmt, dx0[vsrc < 0].sum(0)) < 1e-4
 
 
+def test_predictor_ctx_grad_is_the_scatter_without_atomics():
+    """Context part of the predictor-input backward as a fixed-order gather: equals the fp32 index_add, is bit-identical
+    from call to call, and the mask-token-only form of predictor_assemble_bwd leaves d_ctx alone."""
+    B, G, T, D = 37, 4, 200, 384
+    g = torch.Generator(device="cpu").manual_seed(3)
+    ctx_vis = torch.rand(B, T, generator=g) < 0.35
+    tgt = torch.rand(B, G, T, generator=g) < 0.2
+    tgt &= ~ctx_vis[:, None]
+    vis = ctx_vis[:, None] | tgt                              # predictor sequences: context + that group's targets
+    n_c = ctx_vis.sum(1)
+    cu_c = torch.zeros(B + 1, dtype=torch.int64); cu_c[1:] = n_c.cumsum(0)
+    n_v = vis.view(B * G, T).sum(1)
+    cu_v = torch.zeros(B * G + 1, dtype=torch.int64); cu_v[1:] = n_v.cumsum(0)
+    Nc, Nv = int(cu_c[-1]), int(cu_v[-1])
+    ctx_row = torch.full((B, T), -1, dtype=torch.int64)
+    ctx_row[ctx_vis] = torch.arange(Nc)
+    vsrc = ctx_row[:, None].expand(B, G, T)[vis].to(torch.int32).to(DEV)      # time order inside each (b, g) sequence
+    dx0 = torch.randn(Nv, D, device=DEV)
+    o32 = torch.full((Nc, D), float("nan"), device=DEV)
+    o16 = torch.full((Nc, D), float("nan"), device=DEV, dtype=torch.bfloat16)
+    cu_v_d = cu_v.to(torch.int32).to(DEV)
+    ops.predictor_ctx_grad(dx0, vsrc, cu_v_d, B * G, G, Nc, D, o32, o16)
+    ref = torch.zeros(Nc, D, device=DEV).index_add_(0, vsrc.clamp(min=0).long(), dx0 * (vsrc >= 0)[:, None])
+    assert rel(o32, ref) < 1e-6 and torch.equal(o16, o32.bfloat16())
+    o32b = torch.empty_like(o32)
+    ops.predictor_ctx_grad(dx0, vsrc, cu_v_d, B * G, G, Nc, D, o32b, None)
+    assert torch.equal(o32, o32b)
+    dmt = torch.zeros(D, device=DEV)
+    ops.predictor_assemble_bwd(dx0, vsrc, Nv, D, None, dmt)
+    assert rel(dmt, dx0[vsrc < 0].sum(0)) < 1e-4
+
+
 def test_masked_mse():
     Nt, D, R = 4321, 768, 2000
     pred = torch.randn(Nt, D, device=DEV).bfloat16()

@@ -243,7 +243,7 @@ template <int CIN>
 __global__ void __launch_bounds__(256, 2) conv0_bwd_kernel(Conv0Args a, const float* __restrict__ stats,
                                                            const float* __restrict__ gamma,
                                                            const float* __restrict__ beta, const bf16* __restrict__ dy,
-                                                           float* __restrict__ red, int chunks_per_block) {
+                                                           double* __restrict__ red, int chunks_per_block) {
   constexpr int NA = CIN * kC0K;
   __shared__ __align__(16) bf16 s_x[CIN * kC0WinB];
   __shared__ float4 s_mr[256];   // (mean0, rstd0, mean1, rstd1) of channel pair i (C = 512), FRAGMENT order [warp][nt][tg]
@@ -328,7 +328,9 @@ __global__ void __launch_bounds__(256, 2) conv0_bwd_kernel(Conv0Args a, const fl
   }
   // S1 / S2: sum over the 8 lanes (g) that share a channel pair; P^T: fragments already hold sums over outputs.
   // Accumulator columns (2 tg, 2 tg + 1) of n-tile nt are channels c_base + tg * 16 + nt * 2 + {0, 1}.
-  float* r = red + static_cast<size_t>(b) * (2 + NA) * a.C + c_base + tg * 16;
+  // (fp64 atomics: the weight gradient is a difference of large sums -- see the finalize kernel -- so fp32 summation-order
+  // noise here showed up as ~4e-3 run-to-run differences of dW; in fp64 it is below fp32 resolution)
+  double* r = red + static_cast<size_t>(b) * (2 + NA) * a.C + c_base + tg * 16;
 #pragma unroll
   for (int nt = 0; nt < 8; ++nt) {
 #pragma unroll
@@ -340,18 +342,18 @@ __global__ void __launch_bounds__(256, 2) conv0_bwd_kernel(Conv0Args a, const fl
         v2 += __shfl_xor_sync(0xffffffffu, v2, o);
       }
       if (g == 0) {
-        atomicAdd(r + nt * 2 + e, v1);
-        atomicAdd(r + a.C + nt * 2 + e, v2);
+        atomicAdd(r + nt * 2 + e, static_cast<double>(v1));
+        atomicAdd(r + a.C + nt * 2 + e, static_cast<double>(v2));
       }
     }
 #pragma unroll
     for (int ci = 0; ci < CIN; ++ci) {
-      float* rp = r + static_cast<size_t>(2 + ci * kC0K) * a.C + nt * 2;
-      atomicAdd(rp + static_cast<size_t>(g) * a.C, pt[ci][nt][0]);
-      atomicAdd(rp + static_cast<size_t>(g) * a.C + 1, pt[ci][nt][1]);
+      double* rp = r + static_cast<size_t>(2 + ci * kC0K) * a.C + nt * 2;
+      atomicAdd(rp + static_cast<size_t>(g) * a.C, static_cast<double>(pt[ci][nt][0]));
+      atomicAdd(rp + static_cast<size_t>(g) * a.C + 1, static_cast<double>(pt[ci][nt][1]));
       if (g < 2) {
-        atomicAdd(rp + static_cast<size_t>(g + 8) * a.C, pt[ci][nt][2]);
-        atomicAdd(rp + static_cast<size_t>(g + 8) * a.C + 1, pt[ci][nt][3]);
+        atomicAdd(rp + static_cast<size_t>(g + 8) * a.C, static_cast<double>(pt[ci][nt][2]));
+        atomicAdd(rp + static_cast<size_t>(g + 8) * a.C + 1, static_cast<double>(pt[ci][nt][3]));
       }
     }
   }
@@ -362,7 +364,7 @@ template <int CIN>
 __global__ void __launch_bounds__(256) conv0_bwd_finalize_kernel(Conv0Args a, const double* __restrict__ mom,
                                                                  const float* __restrict__ stats,
                                                                  const float* __restrict__ gamma,
-                                                                 const float* __restrict__ red, float* __restrict__ dw,
+                                                                 const double* __restrict__ red, float* __restrict__ dw,
                                                                  float* __restrict__ dgamma, float* __restrict__ dbeta) {
   constexpr int NA = CIN * kC0K;
   constexpr int NOUT = NA + NA * NA;
@@ -387,8 +389,8 @@ __global__ void __launch_bounds__(256) conv0_bwd_finalize_kernel(Conv0Args a, co
     __syncthreads();
     if (b < a.B && c_ok) {
       const float mean = stats[(static_cast<size_t>(b) * a.C + c) * 2], rstd = stats[(static_cast<size_t>(b) * a.C + c) * 2 + 1];
-      const float* r = red + static_cast<size_t>(b) * (2 + NA) * a.C + c;
-      const float S1 = r[0], S2 = r[a.C];
+      const double* r = red + static_cast<size_t>(b) * (2 + NA) * a.C + c;
+      const float S1 = static_cast<float>(r[0]), S2 = static_cast<float>(r[a.C]);
       const float k1 = S1 * invL, k2 = S2 * invL * rstd, sc = rstd * ga;
 #pragma unroll
       for (int i = 0; i < NA; ++i) {
@@ -396,7 +398,8 @@ __global__ void __launch_bounds__(256) conv0_bwd_finalize_kernel(Conv0Args a, co
 #pragma unroll
         for (int j = 0; j < NA; ++j) rw = fmaf(s_m[by][NA + i * NA + j], w[j], rw);
         const float q = rw - mean * s_m[by][i];            // Q[i] / rstd
-        acc[i] += sc * (r[static_cast<size_t>(2 + i) * a.C] - k1 * s_m[by][i] - k2 * q);
+        acc[i] += sc * static_cast<float>(r[static_cast<size_t>(2 + i) * a.C] - static_cast<double>(k1) * s_m[by][i] -
+                                          static_cast<double>(k2) * q);
       }
       acc[NA] += S2;
       acc[NA + 1] += S1;
@@ -461,7 +464,7 @@ extern "C" int wj_conv0_gn_gelu_fwd(const void* x_bf16, const float* w, const fl
 
 extern "C" int wj_conv0_gn_gelu_bwd(const void* x_bf16, const float* w, const float* gamma, const float* beta, int B,
                                     int Cin, int L, int C, int k, int stride, float eps, const double* moments,
-                                    const float* stats, const void* dy_bf16, const void* dgelu_bf16, float* red_scratch,
+                                    const float* stats, const void* dy_bf16, const void* dgelu_bf16, void* red_scratch,
                                     float* dw, float* dgamma, float* dbeta, void* stream) {
   if (B <= 0) return WJ_OK;
   int rc = check_conv0(Cin, C, k, stride);
@@ -472,18 +475,19 @@ extern "C" int wj_conv0_gn_gelu_bwd(const void* x_bf16, const float* w, const fl
   a.x = reinterpret_cast<const bf16*>(x_bf16); a.w = w; a.B = B; a.Cin = Cin; a.L = L; a.C = C;
   a.L_out = (L - k) / stride + 1;
   const int na = Cin * kC0K;
-  cudaMemsetAsync(red_scratch, 0, static_cast<size_t>(B) * (2 + na) * C * sizeof(float), st);
+  double* red = reinterpret_cast<double*>(red_scratch);
+  cudaMemsetAsync(red, 0, static_cast<size_t>(B) * (2 + na) * C * sizeof(double), st);
   const int chunks = (a.L_out + kC0TT - 1) / kC0TT;
   const int cpb = 13;   // 2 + na accumulators per channel flushed with atomics at the end: few, long blocks
   dim3 grid((chunks + cpb - 1) / cpb, B);
   const bf16* dy = reinterpret_cast<const bf16*>(dy_bf16);
   dim3 fgrid((C + 31) / 32), fblock(32, 8);
   if (Cin == 1) {
-    conv0_bwd_kernel<1><<<grid, C / 2, 0, st>>>(a, stats, gamma, beta, dy, red_scratch, cpb);
-    conv0_bwd_finalize_kernel<1><<<fgrid, fblock, 0, st>>>(a, moments, stats, gamma, red_scratch, dw, dgamma, dbeta);
+    conv0_bwd_kernel<1><<<grid, C / 2, 0, st>>>(a, stats, gamma, beta, dy, red, cpb);
+    conv0_bwd_finalize_kernel<1><<<fgrid, fblock, 0, st>>>(a, moments, stats, gamma, red, dw, dgamma, dbeta);
   } else {
-    conv0_bwd_kernel<2><<<grid, C / 2, 0, st>>>(a, stats, gamma, beta, dy, red_scratch, cpb);
-    conv0_bwd_finalize_kernel<2><<<fgrid, fblock, 0, st>>>(a, moments, stats, gamma, red_scratch, dw, dgamma, dbeta);
+    conv0_bwd_kernel<2><<<grid, C / 2, 0, st>>>(a, stats, gamma, beta, dy, red, cpb);
+    conv0_bwd_finalize_kernel<2><<<fgrid, fblock, 0, st>>>(a, moments, stats, gamma, red, dw, dgamma, dbeta);
   }
   return check_launch("conv0_gn_gelu_bwd", 2);
 }

@@ -135,10 +135,47 @@ __global__ void __launch_bounds__(256) predictor_assemble_bwd_kernel(const float
     for (int r = r0; r < r1; ++r) {
       const int s = vis_src[r];
       const float v = dx0[static_cast<size_t>(r) * D + c];
-      if (s >= 0) atomicAdd(d_ctx + static_cast<size_t>(s) * D + c, v);
-      else acc += v;
+      if (s >= 0) {
+        if (d_ctx != nullptr) atomicAdd(d_ctx + static_cast<size_t>(s) * D + c, v);
+      } else {
+        acc += v;
+      }
     }
     atomicAdd(d_mask + c, acc);
+  }
+}
+
+// Inverse of vis_src: ctx_vrow[src * G + g] = predictor row of context row `src` in target group g's sequence (-1 when the
+// sequence does not hold it).  One block per predictor sequence.
+__global__ void __launch_bounds__(128) ctx_vrows_kernel(const int* __restrict__ vis_src, const int* __restrict__ cu_v,
+                                                        int G, int* __restrict__ ctx_vrow) {
+  const int s = blockIdx.x, g = s % G;
+  for (int r = cu_v[s] + threadIdx.x; r < cu_v[s + 1]; r += blockDim.x) {
+    const int src = vis_src[r];
+    if (src >= 0) ctx_vrow[static_cast<size_t>(src) * G + g] = r;
+  }
+}
+
+// d_ctx[s, :] = sum over the target groups g (in order) of dx0[ctx_vrow[s * G + g], :]: the gradient of a context row is the
+// sum of its copies in the G predictor sequences of its instance.  A gather with a fixed summation order -- no atomics, so
+// the bf16 value handed to the student's backward is the same in every run.
+__global__ void __launch_bounds__(256) predictor_ctx_grad_kernel(const float* __restrict__ dx0,
+                                                                 const int* __restrict__ ctx_vrow, long long n4, int D4,
+                                                                 int G, float* __restrict__ out_f32,
+                                                                 bf16* __restrict__ out_bf16) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long s = i / D4;
+    const int c = static_cast<int>(i - s * D4) * 4;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int g = 0; g < G; ++g) {
+      const int r = ctx_vrow[s * G + g];
+      if (r >= 0) {
+        const float4 v = *reinterpret_cast<const float4*>(dx0 + static_cast<size_t>(r) * D4 * 4 + c);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+    }
+    store4(out_f32, out_bf16, static_cast<size_t>(i) * 4, acc);
   }
 }
 
@@ -470,6 +507,19 @@ extern "C" int wj_predictor_assemble_bwd(const float* dx0, const int* vis_src, i
   predictor_assemble_bwd_kernel<<<blocks, 256, 0, WJ_STREAM(stream)>>>(dx0, vis_src, N, D, rows_per_block, d_ctx,
                                                                       d_mask_token);
   return check_launch("predictor_assemble_bwd");
+}
+
+extern "C" int wj_predictor_ctx_grad(const float* dx0, const int* vis_src, const int* cu_v, int n_seqs, int G, int Nc, int D,
+                                     int* ctx_vrow, float* d_ctx_f32, void* d_ctx_bf16, void* stream) {
+  if (Nc <= 0 || n_seqs <= 0) return WJ_OK;
+  if (D % 4 || G <= 0) { set_error("wj_predictor_ctx_grad: D %% 4 != 0 or G <= 0"); return WJ_ERR_ARG; }
+  cudaStream_t st = WJ_STREAM(stream);
+  cudaMemsetAsync(ctx_vrow, 0xFF, static_cast<size_t>(Nc) * G * sizeof(int), st);
+  ctx_vrows_kernel<<<n_seqs, 128, 0, st>>>(vis_src, cu_v, G, ctx_vrow);
+  const long long n4 = static_cast<long long>(Nc) * (D / 4);
+  predictor_ctx_grad_kernel<<<grid_for(n4), 256, 0, st>>>(dx0, ctx_vrow, n4, D / 4, G, d_ctx_f32,
+                                                         reinterpret_cast<bf16*>(d_ctx_bf16));
+  return check_launch("predictor_ctx_grad", 2);
 }
 
 extern "C" int wj_masked_mse(const void* pred_bf16, const float* targets, const int* tgt_rows, int Nt, int D,

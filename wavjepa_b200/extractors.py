@@ -165,7 +165,7 @@ def conv_stack_backward(spec, sv: ConvSaved, dh_last: torch.Tensor, w0, gn_w, gn
         dh = dx
         if on_layer_done is not None:
             on_layer_done(i)
-    red = torch.empty(B, 2 + sv.x16.shape[1] * 10, C, device=dev, dtype=torch.float32)
+    red = torch.empty(B, 2 + sv.x16.shape[1] * 10, C, device=dev, dtype=torch.float64)
     ops.conv0_bwd(sv.x16, w0, gn_w, gn_b, sv.moments, sv.stats, dh, red, g_w0, g_gn_w, g_gn_b, eps=gn_eps)
     if on_layer_done is not None:
         on_layer_done(0)

@@ -582,11 +582,12 @@ class JEPA(_ModuleBase):
         dx0 = self._dec_stack.backward(self._W_dec, G_dec, c.dec_saved, dxp, mi.cu_v, B * mi.G, mi.max_nv,
                                        lambda i: ready(f"decoder.layers.{i}.self_attn.in_proj_weight"))
         # ---- predictor input assembly: context rows and the mask token
-        dctx = torch.zeros(Nc, Dp, device=dev)
-        ops.predictor_assemble_bwd(dx0, mi.vis_src, Nv, Dp, dctx, g("mask_token").view(-1))
+        # (the mask-token gradient by block sums + atomics; the context rows by a fixed-order gather over the target
+        # groups, so the bf16 gradient entering the student's backward is bit-identical from run to run)
+        ops.predictor_assemble_bwd(dx0, mi.vis_src, Nv, Dp, None, g("mask_token").view(-1))
         ready("mask_token")
         dctx16 = torch.empty(Nc, Dp, device=dev, dtype=bf)
-        ops.gather_rows(dctx, None, Nc, None, dctx16)
+        ops.predictor_ctx_grad(dx0, mi.vis_src, mi.cu_v, mi.B * mi.G, mi.G, Nc, Dp, None, dctx16)
         # ---- encoder_to_decoder_mapper
         ops.colsum(dctx16, g("encoder_to_decoder_mapper.bias"))
         ops.gemm_wgrad(ops.plain_operand(dctx16), ops.plain_operand(c.cf16), Nc, 1,

@@ -259,12 +259,12 @@ def mask_indices(ctx_hidden: torch.Tensor, tgt: torch.Tensor, vis_hidden: torch.
 
 # ----------------------------------------------------------------------------------------------------- conv0
 def conv0_workspaces(B: int, Cin: int, C: int, device, backward: bool = False):
-    """(moments fp64 [B, n], stats fp32 [B, C, 2][, red_scratch fp32 [B, 2 + Cin*10, C]]) for conv0_fwd / conv0_bwd."""
+    """(moments fp64 [B, n], stats fp32 [B, C, 2][, red_scratch fp64 [B, 2 + Cin*10, C]]) for conv0_fwd / conv0_bwd."""
     n = int(_lib.load().wj_conv0_moment_count(Cin))
     mom = torch.empty(B, n, device=device, dtype=torch.float64)
     stats = torch.empty(B, C, 2, device=device, dtype=torch.float32)
     if backward:
-        return mom, stats, torch.empty(B, 2 + Cin * 10, C, device=device, dtype=torch.float32)
+        return mom, stats, torch.empty(B, 2 + Cin * 10, C, device=device, dtype=torch.float64)
     return mom, stats
 
 
@@ -288,7 +288,7 @@ def conv0_bwd(x, w, gamma, beta, moments, stats, dy, red_scratch, dw, dgamma, db
               eps: float = 1e-5) -> None:
     """Backward of conv0_fwd from dy (bf16 [B, L_out, C]); GELU' is recomputed from x, nothing else is read."""
     B, Cin, L = x.shape
-    assert red_scratch.dtype == torch.float32 and red_scratch.numel() >= B * (2 + Cin * 10) * w.shape[0]
+    assert red_scratch.dtype == torch.float64 and red_scratch.numel() >= B * (2 + Cin * 10) * w.shape[0]
     assert dy.dtype == torch.bfloat16 and dy.is_contiguous()
     lib = _lib.load()
     p = lambda t: C.c_void_p(_ptr(t))
@@ -467,6 +467,17 @@ def predictor_assemble_bwd(dx0, vis_src, N: int, D: int, d_ctx, d_mask_token):
     lib = _lib.load()
     p = lambda t: C.c_void_p(_ptr(t))
     check(lib.wj_predictor_assemble_bwd(p(dx0), p(vis_src), N, D, p(d_ctx), p(d_mask_token), _stream()))
+
+
+def predictor_ctx_grad(dx0, vis_src, cu_v, n_seqs: int, G: int, Nc: int, D: int, d_ctx_f32=None, d_ctx_bf16=None):
+    """d_ctx[s] = sum over the G target groups (fixed order) of the predictor-input gradient rows that copy context row s
+    (the context part of predictor_assemble_bwd, without atomics).  Either output may be None."""
+    assert dx0.dtype == torch.float32 and dx0.is_contiguous()
+    lib = _lib.load()
+    p = lambda t: C.c_void_p(_ptr(t))
+    ws = torch.empty(Nc * G, device=dx0.device, dtype=torch.int32)
+    check(lib.wj_predictor_ctx_grad(p(dx0), p(vis_src), p(cu_v), n_seqs, G, Nc, D, p(ws), p(d_ctx_f32), p(d_ctx_bf16),
+                                    _stream()))
 
 
 def masked_mse(pred_bf16, targets, tgt_rows, Nt: int, D: int, loss, dpred_bf16=None):
