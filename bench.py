@@ -224,6 +224,9 @@ def run_native(args):
     _lib.require_device()
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    if args.deterministic:
+        from wavjepa_b200 import ops as _ops
+        _ops.set_deterministic(True, (512 if nat else 256) << 20)
     model = build_model(dev, nat=nat)
     model.reserve_workspace((130 if nat else 80) << 30)   # setup: the activation pool of a 512-instance step exists up front
     model.global_step = 1000          # lr(0) == 0 (warm-up from 0): start inside the warm-up so AdamW moves weights
@@ -372,7 +375,7 @@ def run_native(args):
                                       ("configs[1]: WavJEPA-base SSL pre-training step, 64 clips x 8 crops of 2.01 s "
                                        "(512 instances/GPU), random-init weights, AudioSet masker, AdamW+EMA included"),
                           "instances_per_gpu": B, "global_instances": world * B, "tokens_per_instance": T,
-                          "parallelism": f"dp{world}",
+                          "parallelism": f"dp{world}", **({"deterministic": True} if args.deterministic else {}),
                           "l2": "no explicit flush: every step streams > 30 GB of activations (>> 126 MB L2) and "
                                 "rotates 3 different 41 MB clip batches"},
                "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": h2d,
@@ -675,6 +678,8 @@ def main():
     ap.add_argument("--config", default="train", choices=["train", "hear", "nat"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-baseline", action="store_true")
+    ap.add_argument("--deterministic", action="store_true",
+                    help="time the step with bit-reproducible reductions (ops.set_deterministic); not the default bench line")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
     if args.impl == "reference":

@@ -13,6 +13,7 @@
 #ifndef WAVJEPA_B200_H
 #define WAVJEPA_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -92,6 +93,15 @@ int wj_gemm_bf16(const wj_operand_t* A, const void* W, int64_t ldw, int L, int b
 int wj_gemm_dgrad_bf16(const wj_operand_t* A, const void* W, int64_t ldw, int w_rows, int w_cols,
                        const int32_t* seg_col_off, int L, int batch, int N, int K, const wj_epilogue_t* epi,
                        int block_n, void* stream);
+
+/* Deterministic mode.  By default reductions over rows / tokens / blocks end in floating-point atomics (split-token weight
+ * gradients, bias column sums, LayerNorm gamma/beta gradients, the mask-token gradient, the conv-0 reduction, the loss and
+ * gradient-norm scalars), so their low-order bits depend on the order in which blocks finish.  With a workspace
+ * registered here (device memory, >= 256 MB covers the 512-instance training step) every such reduction stores per-block
+ * or per-split partial results in the workspace and a second kernel adds them in a fixed order: two runs on the same inputs
+ * give bit-identical gradients and parameters.  The workspace is used by whichever call runs, so calls must be issued on
+ * ONE stream while the mode is on.  workspace = NULL (or bytes = 0) switches the mode off (the default). */
+int wj_set_deterministic(void* workspace, size_t bytes);
 
 /* Routing switches for A/B measurements and tests: key 1 = weight-gradient GEMMs may use the CTA-pair kernel, key 2 = data
  * gradient GEMMs may (value 1, the default) or stay on single CTAs (value 0). */

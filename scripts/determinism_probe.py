@@ -1,7 +1,8 @@
 """Run-to-run difference of one training step: the SAME model state, clips and masks stepped twice (two identical models),
 then every parameter gradient compared.  What can differ is the order of fp32 / fp64 atomic sums (split-token weight
 gradients, column sums, LayerNorm parameter gradients, conv-0 reduction); the activation gradients themselves take no
-atomics.        python scripts/determinism_probe.py [clips]        (default 16 clips x 8 crops = 128 instances)"""
+atomics.  With --det the library's deterministic mode (workspace + fixed-order reductions) is switched on: expect zeros.
+    python scripts/determinism_probe.py [clips] [--det]        (default 16 clips x 8 crops = 128 instances)"""
 import json
 import os
 import sys
@@ -14,7 +15,12 @@ import wavjepa_b200 as w  # noqa: E402
 from bench import MASKER, build_model  # noqa: E402
 
 dev = torch.device("cuda", 0)
-clips = int(sys.argv[1]) if len(sys.argv) > 1 else 16
+det = "--det" in sys.argv
+argv = [a_ for a_ in sys.argv[1:] if a_ != "--det"]
+clips = int(argv[0]) if argv else 16
+if det:
+    from wavjepa_b200 import ops
+    ops.set_deterministic(True, 256 << 20)
 crops = 8
 a, b = build_model(dev), build_model(dev)
 b.load_state_dict(a.state_dict())
@@ -40,7 +46,7 @@ for n in a._train_names:
     worst = max(worst, d)
     rows.append((d, n))
 rows.sort(reverse=True)
-print(json.dumps({"instances": B, "loss_a": la.item(), "loss_b": lb.item(), "loss_abs_diff": abs(la.item() - lb.item()),
+print(json.dumps({"deterministic_mode": det, "instances": B, "loss_a": la.item(), "loss_b": lb.item(), "loss_abs_diff": abs(la.item() - lb.item()),
                   "parameter_tensors": len(rows), "bit_identical_gradient_tensors": same, "worst_rel_l2_diff": worst,
                   "worst_tensors": [(n, float(f"{d:.3e}")) for d, n in rows[:6]],
                   "params_after_step_max_abs_diff": max((pa.detach() - pb.detach()).abs().max().item()

@@ -411,9 +411,16 @@ extern "C" int wj_attn_varlen_bwd_bias(const void* qkv_bf16, const void* out_bf1
   if (D % H != 0 || (dh != 32 && dh != 64)) { set_error("wj_attn_varlen_bwd: head dim must be 32 or 64"); return WJ_ERR_ARG; }
   {
     // head dim 32, <= 128 tokens: tcgen05 kernel (attention_tc.cu); everything else: the mma.sync kernel below
+    // (deterministic mode: the fused column sums end in shared / global atomics, so the bias gradient is taken from the
+    // stored dqkv by the ordered wj_colsum instead)
+    const bool det = wj::det_on();
     const int rc = wj::attn_bwd_tc_launch(qkv_bf16, out_bf16, dout_bf16, lse2, cu_seqlens, n_seqs, max_len, total_tokens, D, H,
-                                          dqkv_bf16, dbias, WJ_STREAM(stream));
+                                          dqkv_bf16, det ? nullptr : dbias, WJ_STREAM(stream));
     if (rc < 0) return rc;
+    if (rc == 0 && det) {
+      if (dbias != nullptr) return wj_colsum(dqkv_bf16, 1, total_tokens, 3 * D, 3 * D, dbias, stream);
+      return WJ_OK;
+    }
     if (rc == 0) {
       // the tcgen05 kernel added the query third in its epilogue; the value third of the bias gradient is the column sum
       // of dO (softmax rows sum to one), the key third is identically zero (softmax ignores a constant key shift)

@@ -243,7 +243,7 @@ template <int CIN>
 __global__ void __launch_bounds__(256, 2) conv0_bwd_kernel(Conv0Args a, const float* __restrict__ stats,
                                                            const float* __restrict__ gamma,
                                                            const float* __restrict__ beta, const bf16* __restrict__ dy,
-                                                           double* __restrict__ red, int chunks_per_block) {
+                                                           double* __restrict__ red, int chunks_per_block, int nslab) {
   constexpr int NA = CIN * kC0K;
   __shared__ __align__(16) bf16 s_x[CIN * kC0WinB];
   __shared__ float4 s_mr[256];   // (mean0, rstd0, mean1, rstd1) of channel pair i (C = 512), FRAGMENT order [warp][nt][tg]
@@ -330,7 +330,9 @@ __global__ void __launch_bounds__(256, 2) conv0_bwd_kernel(Conv0Args a, const fl
   // Accumulator columns (2 tg, 2 tg + 1) of n-tile nt are channels c_base + tg * 16 + nt * 2 + {0, 1}.
   // (fp64 atomics: the weight gradient is a difference of large sums -- see the finalize kernel -- so fp32 summation-order
   // noise here showed up as ~4e-3 run-to-run differences of dW; in fp64 it is below fp32 resolution)
-  double* r = red + static_cast<size_t>(b) * (2 + NA) * a.C + c_base + tg * 16;
+  // nslab > 1 (deterministic mode): every block of an instance owns a slab, so each element has ONE contributor and the
+  // finalize kernel adds the slabs in order
+  double* r = red + (static_cast<size_t>(b) * nslab + (nslab > 1 ? blockIdx.x : 0)) * (2 + NA) * a.C + c_base + tg * 16;
 #pragma unroll
   for (int nt = 0; nt < 8; ++nt) {
 #pragma unroll
@@ -365,7 +367,8 @@ __global__ void __launch_bounds__(256) conv0_bwd_finalize_kernel(Conv0Args a, co
                                                                  const float* __restrict__ stats,
                                                                  const float* __restrict__ gamma,
                                                                  const double* __restrict__ red, float* __restrict__ dw,
-                                                                 float* __restrict__ dgamma, float* __restrict__ dbeta) {
+                                                                 float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                                 int nslab) {
   constexpr int NA = CIN * kC0K;
   constexpr int NOUT = NA + NA * NA;
   __shared__ float s_m[8][NOUT];
@@ -389,8 +392,13 @@ __global__ void __launch_bounds__(256) conv0_bwd_finalize_kernel(Conv0Args a, co
     __syncthreads();
     if (b < a.B && c_ok) {
       const float mean = stats[(static_cast<size_t>(b) * a.C + c) * 2], rstd = stats[(static_cast<size_t>(b) * a.C + c) * 2 + 1];
-      const double* r = red + static_cast<size_t>(b) * (2 + NA) * a.C + c;
-      const float S1 = static_cast<float>(r[0]), S2 = static_cast<float>(r[a.C]);
+      const double* r0 = red + static_cast<size_t>(b) * nslab * (2 + NA) * a.C + c;
+      auto rd = [&](size_t off) {   // sum over the instance's slabs, in slab order
+        double v = 0.0;
+        for (int sl = 0; sl < nslab; ++sl) v += r0[static_cast<size_t>(sl) * (2 + NA) * a.C + off];
+        return v;
+      };
+      const float S1 = static_cast<float>(rd(0)), S2 = static_cast<float>(rd(a.C));
       const float k1 = S1 * invL, k2 = S2 * invL * rstd, sc = rstd * ga;
 #pragma unroll
       for (int i = 0; i < NA; ++i) {
@@ -398,7 +406,7 @@ __global__ void __launch_bounds__(256) conv0_bwd_finalize_kernel(Conv0Args a, co
 #pragma unroll
         for (int j = 0; j < NA; ++j) rw = fmaf(s_m[by][NA + i * NA + j], w[j], rw);
         const float q = rw - mean * s_m[by][i];            // Q[i] / rstd
-        acc[i] += sc * static_cast<float>(r[static_cast<size_t>(2 + i) * a.C] - static_cast<double>(k1) * s_m[by][i] -
+        acc[i] += sc * static_cast<float>(rd(static_cast<size_t>(2 + i) * a.C) - static_cast<double>(k1) * s_m[by][i] -
                                           static_cast<double>(k2) * q);
       }
       acc[NA] += S2;
@@ -475,19 +483,25 @@ extern "C" int wj_conv0_gn_gelu_bwd(const void* x_bf16, const float* w, const fl
   a.x = reinterpret_cast<const bf16*>(x_bf16); a.w = w; a.B = B; a.Cin = Cin; a.L = L; a.C = C;
   a.L_out = (L - k) / stride + 1;
   const int na = Cin * kC0K;
-  double* red = reinterpret_cast<double*>(red_scratch);
-  cudaMemsetAsync(red, 0, static_cast<size_t>(B) * (2 + na) * C * sizeof(double), st);
   const int chunks = (a.L_out + kC0TT - 1) / kC0TT;
   const int cpb = 13;   // 2 + na accumulators per channel flushed with atomics at the end: few, long blocks
   dim3 grid((chunks + cpb - 1) / cpb, B);
+  double* red = reinterpret_cast<double*>(red_scratch);
+  int nslab = 1;
+  if (det_on()) {   // one slab per block of an instance, from the deterministic-mode workspace
+    nslab = static_cast<int>(grid.x);
+    red = reinterpret_cast<double*>(det_ws(static_cast<size_t>(B) * nslab * (2 + na) * C * sizeof(double), &rc));
+    if (rc) return rc;
+  }
+  cudaMemsetAsync(red, 0, static_cast<size_t>(B) * nslab * (2 + na) * C * sizeof(double), st);
   const bf16* dy = reinterpret_cast<const bf16*>(dy_bf16);
   dim3 fgrid((C + 31) / 32), fblock(32, 8);
   if (Cin == 1) {
-    conv0_bwd_kernel<1><<<grid, C / 2, 0, st>>>(a, stats, gamma, beta, dy, red, cpb);
-    conv0_bwd_finalize_kernel<1><<<fgrid, fblock, 0, st>>>(a, moments, stats, gamma, red, dw, dgamma, dbeta);
+    conv0_bwd_kernel<1><<<grid, C / 2, 0, st>>>(a, stats, gamma, beta, dy, red, cpb, nslab);
+    conv0_bwd_finalize_kernel<1><<<fgrid, fblock, 0, st>>>(a, moments, stats, gamma, red, dw, dgamma, dbeta, nslab);
   } else {
-    conv0_bwd_kernel<2><<<grid, C / 2, 0, st>>>(a, stats, gamma, beta, dy, red, cpb);
-    conv0_bwd_finalize_kernel<2><<<fgrid, fblock, 0, st>>>(a, moments, stats, gamma, red, dw, dgamma, dbeta);
+    conv0_bwd_kernel<2><<<grid, C / 2, 0, st>>>(a, stats, gamma, beta, dy, red, cpb, nslab);
+    conv0_bwd_finalize_kernel<2><<<fgrid, fblock, 0, st>>>(a, moments, stats, gamma, red, dw, dgamma, dbeta, nslab);
   }
   return check_launch("conv0_gn_gelu_bwd", 2);
 }

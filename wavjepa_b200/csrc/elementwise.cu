@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(256) predictor_assemble_kernel(const bf16* __r
 __global__ void __launch_bounds__(256) predictor_assemble_bwd_kernel(const float* __restrict__ dx0,
                                                                      const int* __restrict__ vis_src, int N, int D,
                                                                      int rows_per_block, float* __restrict__ d_ctx,
-                                                                     float* __restrict__ d_mask) {
+                                                                     float* __restrict__ d_mask, float* __restrict__ part) {
   // thread t owns columns t, t+256, ... ; the block walks rows_per_block rows
   const int r0 = blockIdx.x * rows_per_block;
   const int r1 = min(N, r0 + rows_per_block);
@@ -141,7 +141,8 @@ __global__ void __launch_bounds__(256) predictor_assemble_bwd_kernel(const float
         acc += v;
       }
     }
-    atomicAdd(d_mask + c, acc);
+    if (part != nullptr) part[static_cast<size_t>(blockIdx.x) * D + c] = acc;   // deterministic mode: ordered reduce follows
+    else atomicAdd(d_mask + c, acc);
   }
 }
 
@@ -182,7 +183,8 @@ __global__ void __launch_bounds__(256) predictor_ctx_grad_kernel(const float* __
 // loss += sum_i mean_d (pred[i,d] - tgt[trow[i],d])^2 / (Nt + 1e-8);  dpred = 2 (pred - tgt) / (D (Nt + 1e-8))
 __global__ void __launch_bounds__(256) masked_mse_kernel(const bf16* __restrict__ pred, const float* __restrict__ tgt,
                                                          const int* __restrict__ trow, int Nt, int D,
-                                                         float* __restrict__ loss, bf16* __restrict__ dpred) {
+                                                         float* __restrict__ loss, bf16* __restrict__ dpred,
+                                                         float* __restrict__ part) {
   __shared__ float s_part[8];
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float denom = static_cast<float>(Nt) + 1e-8f;
@@ -207,7 +209,8 @@ __global__ void __launch_bounds__(256) masked_mse_kernel(const bf16* __restrict_
   if (threadIdx.x == 0) {
     float t = 0.f;
     for (int w = 0; w < 8; ++w) t += s_part[w];
-    atomicAdd(loss, t * inv);
+    if (part != nullptr) part[blockIdx.x] = t * inv;
+    else atomicAdd(loss, t * inv);
   }
 }
 
@@ -229,7 +232,7 @@ __global__ void __launch_bounds__(256) ema_kernel(float* __restrict__ teacher, c
 }
 
 __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ x, long long n, float scale,
-                                                    double* __restrict__ out) {
+                                                    double* __restrict__ out, double* __restrict__ part) {
   __shared__ double s_part[8];
   double acc = 0.0;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
@@ -244,7 +247,8 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ x,
   if (threadIdx.x == 0) {
     double t = 0.0;
     for (int w = 0; w < 8; ++w) t += s_part[w];
-    atomicAdd(out, t);
+    if (part != nullptr) part[blockIdx.x] = t;
+    else atomicAdd(out, t);
   }
 }
 
@@ -348,7 +352,9 @@ __global__ void __launch_bounds__(256) cast_kernel(const float* __restrict__ x, 
 // Block (32, 8): thread (tx, ty) owns 8 consecutive columns (one 16-byte bf16 vector / two fp32 vectors) and every
 // 8th row of the block's row range, 4 rows in flight; the 8 row-partials meet in smem, one atomic per column per block.
 __global__ void __launch_bounds__(256) colsum8_kernel(const void* __restrict__ x, int is_bf16, long long M, int N,
-                                                      long long ld, int rows_per_block, float* __restrict__ out) {
+                                                      long long ld, int rows_per_block, float* __restrict__ out,
+                                                      float* __restrict__ part) {
+  // part != NULL (deterministic mode): this row block's sums go to part[blockIdx.y][N] instead of atomics on out
   __shared__ float s_acc[8][32][9];
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int c = (blockIdx.x * 32 + tx) * 8;
@@ -402,13 +408,15 @@ __global__ void __launch_bounds__(256) colsum8_kernel(const void* __restrict__ x
     float v = 0.f;
 #pragma unroll
     for (int y = 0; y < 8; ++y) v += s_acc[y][tx][ty];
-    atomicAdd(out + c + ty, v);
+    if (part != nullptr) part[static_cast<size_t>(blockIdx.y) * N + c + ty] = v;
+    else atomicAdd(out + c + ty, v);
   }
 }
 
 // generic fallback (N even)
 __global__ void __launch_bounds__(256) colsum_kernel(const void* __restrict__ x, int is_bf16, long long M, int N,
-                                                     long long ld, int rows_per_block, float* __restrict__ out) {
+                                                     long long ld, int rows_per_block, float* __restrict__ out,
+                                                     float* __restrict__ part) {
   const long long r0 = static_cast<long long>(blockIdx.y) * rows_per_block;
   const long long r1 = min(M, r0 + rows_per_block);
   const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 2;
@@ -427,8 +435,13 @@ __global__ void __launch_bounds__(256) colsum_kernel(const void* __restrict__ x,
       a0 += v.x; a1 += v.y;
     }
   }
-  atomicAdd(out + c, a0);
-  atomicAdd(out + c + 1, a1);
+  if (part != nullptr) {
+    part[static_cast<size_t>(blockIdx.y) * N + c] = a0;
+    part[static_cast<size_t>(blockIdx.y) * N + c + 1] = a1;
+  } else {
+    atomicAdd(out + c, a0);
+    atomicAdd(out + c + 1, a1);
+  }
 }
 
 __global__ void __launch_bounds__(256) scale_kernel(bf16* __restrict__ x, const float* __restrict__ s, long long n) {
@@ -504,9 +517,18 @@ extern "C" int wj_predictor_assemble_bwd(const float* dx0, const int* vis_src, i
   int rows_per_block = (N + sm_count() * 8 - 1) / (sm_count() * 8);
   if (rows_per_block < 1) rows_per_block = 1;
   const int blocks = (N + rows_per_block - 1) / rows_per_block;
+  int rc = WJ_OK;
+  float* part = reinterpret_cast<float*>(det_ws(static_cast<size_t>(blocks) * D * sizeof(float), &rc));
+  if (rc) return rc;
+  if (part != nullptr && d_ctx != nullptr) {
+    set_error("wj_predictor_assemble_bwd: deterministic mode takes d_ctx = NULL (use wj_predictor_ctx_grad)");
+    return WJ_ERR_ARG;
+  }
   predictor_assemble_bwd_kernel<<<blocks, 256, 0, WJ_STREAM(stream)>>>(dx0, vis_src, N, D, rows_per_block, d_ctx,
-                                                                      d_mask_token);
-  return check_launch("predictor_assemble_bwd");
+                                                                      d_mask_token, part);
+  rc = check_launch("predictor_assemble_bwd");
+  if (rc == WJ_OK && part != nullptr) rc = det_reduce_f32(part, blocks, 1, D, d_mask_token, D, WJ_STREAM(stream));
+  return rc;
 }
 
 extern "C" int wj_predictor_ctx_grad(const float* dx0, const int* vis_src, const int* cu_v, int n_seqs, int G, int Nc, int D,
@@ -529,9 +551,14 @@ extern "C" int wj_masked_mse(const void* pred_bf16, const float* targets, const 
   int blocks = (Nt + 7) / 8;
   const int cap = sm_count() * 8;
   if (blocks > cap) blocks = cap;
+  int rc = WJ_OK;
+  float* part = reinterpret_cast<float*>(det_ws(static_cast<size_t>(blocks) * sizeof(float), &rc));
+  if (rc) return rc;
   masked_mse_kernel<<<blocks, 256, 0, WJ_STREAM(stream)>>>(reinterpret_cast<const bf16*>(pred_bf16), targets, tgt_rows,
-                                                          Nt, D, loss, reinterpret_cast<bf16*>(dpred_bf16));
-  return check_launch("masked_mse");
+                                                          Nt, D, loss, reinterpret_cast<bf16*>(dpred_bf16), part);
+  rc = check_launch("masked_mse");
+  if (rc == WJ_OK && part != nullptr) rc = det_reduce_f32(part, blocks, 1, 1, loss, 1, WJ_STREAM(stream));
+  return rc;
 }
 
 extern "C" int wj_ema_update(float* teacher, const float* student, int64_t n, double decay, void* stream) {
@@ -543,8 +570,14 @@ extern "C" int wj_ema_update(float* teacher, const float* student, int64_t n, do
 
 extern "C" int wj_sumsq(const float* x, int64_t n, float scale, double* out, void* stream) {
   if (n <= 0) return WJ_OK;
-  sumsq_kernel<<<grid_for(n, 256, 8), 256, 0, WJ_STREAM(stream)>>>(x, n, scale, out);
-  return check_launch("sumsq");
+  const int blocks = grid_for(n, 256, 8);
+  int rc = WJ_OK;
+  double* part = reinterpret_cast<double*>(det_ws(static_cast<size_t>(blocks) * sizeof(double), &rc));
+  if (rc) return rc;
+  sumsq_kernel<<<blocks, 256, 0, WJ_STREAM(stream)>>>(x, n, scale, out, part);
+  rc = check_launch("sumsq");
+  if (rc == WJ_OK && part != nullptr) rc = det_reduce_f64(part, blocks, 1, out, WJ_STREAM(stream));
+  return rc;
 }
 
 extern "C" int wj_adamw_ema_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
@@ -590,22 +623,32 @@ extern "C" int wj_colsum(const void* x, int x_is_bf16, int64_t M, int N, int64_t
   if (M <= 0) return WJ_OK;
   if (N % 2) { set_error("wj_colsum: N must be even"); return WJ_ERR_ARG; }
   const bool aligned = (reinterpret_cast<uintptr_t>(x) % 16 == 0) && (ld % 8 == 0);
+  float* part = nullptr;
+  int rc = WJ_OK, nb = 0;
   if (N % 8 == 0 && aligned) {
     const int bx = (N / 8 + 31) / 32;
     int by = (8 * sm_count() + bx - 1) / bx;
     if (by > (M + 31) / 32) by = static_cast<int>((M + 31) / 32);
     const int rows_per_block = static_cast<int>((M + by - 1) / by);
     by = static_cast<int>((M + rows_per_block - 1) / rows_per_block);
-    colsum8_kernel<<<dim3(bx, by), dim3(32, 8), 0, WJ_STREAM(stream)>>>(x, x_is_bf16, M, N, ld, rows_per_block, out);
+    part = reinterpret_cast<float*>(det_ws(static_cast<size_t>(by) * N * sizeof(float), &rc));
+    if (rc) return rc;
+    nb = by;
+    colsum8_kernel<<<dim3(bx, by), dim3(32, 8), 0, WJ_STREAM(stream)>>>(x, x_is_bf16, M, N, ld, rows_per_block, out, part);
   } else {
     const int bx = (N / 2 + 255) / 256;
     int by = (2 * sm_count() + bx - 1) / bx;
     if (by > M) by = static_cast<int>(M);
     const int rows_per_block = static_cast<int>((M + by - 1) / by);
     by = static_cast<int>((M + rows_per_block - 1) / rows_per_block);
-    colsum_kernel<<<dim3(bx, by), 256, 0, WJ_STREAM(stream)>>>(x, x_is_bf16, M, N, ld, rows_per_block, out);
+    part = reinterpret_cast<float*>(det_ws(static_cast<size_t>(by) * N * sizeof(float), &rc));
+    if (rc) return rc;
+    nb = by;
+    colsum_kernel<<<dim3(bx, by), 256, 0, WJ_STREAM(stream)>>>(x, x_is_bf16, M, N, ld, rows_per_block, out, part);
   }
-  return check_launch("colsum");
+  rc = check_launch("colsum");
+  if (rc == WJ_OK && part != nullptr) rc = det_reduce_f32(part, nb, 1, N, out, N, WJ_STREAM(stream));   // fixed order
+  return rc;
 }
 
 extern "C" int wj_scale_bf16(void* x_bf16, const float* scale_dev, int64_t n, void* stream) {

@@ -44,6 +44,7 @@ struct GemmParams {
   int total_tiles;
   int splits;        // wgrad: split of the reduction
   int b_single;      // wgrad: the BN columns of a B tile lie in one segment -> one TMA per k-block
+  long long split_stride;   // wgrad, deterministic mode: elements between the output slabs of consecutive token splits
   int kb_per_batch;  // wgrad: ceil(L / 64)
   SegInfo seg;       // normal/dgrad: segments of A's K;  wgrad: segments of B's N
   int segB_col[4];   // dgrad: column offset into W for each reduction segment
@@ -130,7 +131,8 @@ __device__ __forceinline__ void seg_coords(const SegInfo& s, int vc, int& c0, in
 template <int BN, bool WGRAD, typename Arrive>
 __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t t_base, int lane, int lane_grp, int col_q,
                                               int n_blk, int b, int row_in_batch0, long long wgrad_row0, bool have_k,
-                                              Arrive arrive) {
+                                              Arrive arrive, long long out_off = 0) {
+  // out_off: wgrad in deterministic mode writes every token split to its own [M, N] slab (p.split_stride elements apart)
   // work units of 16 TMEM lanes x 32 columns: 2 * BN / 32 per lane group, BN / 64 consecutive ones per warp (the four
   // warps of a lane group split them by col_q); t_base addresses column 0 of the accumulator for this lane group
   constexpr int UNITS = BN / 64;
@@ -276,7 +278,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t t_ba
 #pragma unroll
         for (int c = 0; c < 8; ++c) atomicAdd(op + c * p.ld_out, x[c]);
       } else if (p.out_f32) {
-        float* op = reinterpret_cast<float*>(p.out) + orow * p.ld_out + n0;
+        float* op = reinterpret_cast<float*>(p.out) + out_off + orow * p.ld_out + n0;
         if (p.accumulate) {
           red_add_v4(op, x[0], x[1], x[2], x[3]);
           red_add_v4(op + 4, x[4], x[5], x[6], x[7]);
@@ -782,8 +784,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           continue;
         }
       }
+      long long out_off = 0;
+      if constexpr (WGRAD) out_off = static_cast<long long>(tile / (p.m_blocks * p.n_blocks)) * p.split_stride;
       epilogue_tile<BN, WGRAD>(p, t_acc, lane, lane_grp, col_q, n_blk, b, row_in_batch0,
-                               static_cast<long long>(m_blk) * BM, have_k, [&]() { mbar_arrive(&tempty_bar[acc]); });
+                               static_cast<long long>(m_blk) * BM, have_k, [&]() { mbar_arrive(&tempty_bar[acc]); }, out_off);
     }
     if (p.tma_store && lane == 0) bulk_wait0();   // all TMA stores of this warp are complete before smem goes away
     if (p.dbg && warp == kEpiWarp0 && lane == 0) {
@@ -1037,9 +1041,11 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           continue;
         }
       }
+      long long out_off = 0;
+      if constexpr (WGRAD) out_off = static_cast<long long>(tile / (p.m_blocks * p.n_blocks)) * p.split_stride;
       epilogue_tile<BN, WGRAD>(p, t_base, lane, lane_grp, col_q, n_blk, b, row_in_batch0,
                                static_cast<long long>(m_blk) * BMP + static_cast<long long>(rank) * BM, have_k,
-                               [&]() { mbar_arrive_cluster(te); });
+                               [&]() { mbar_arrive_cluster(te); }, out_off);
     }
     if (p.tma_store && lane == 0) bulk_wait0();   // all TMA stores of this warp are complete before smem goes away
   }
@@ -1304,6 +1310,15 @@ extern "C" int wj_gemm_debug(void* counters) {
 extern "C" int wj_gemm_bf16(const wj_operand_t* A, const void* W, int64_t ldw, int L, int batch, int N, int K,
                             const wj_epilogue_t* epi, int block_n, void* stream) {
   if (L <= 0 || batch <= 0) return WJ_OK;
+  if (epi != nullptr && epi->colsum != nullptr && det_on()) {
+    // deterministic mode: the fused column sums end in atomics; sum the stored output in a fixed order instead
+    if (epi->out_rows != nullptr || epi->accumulate) { set_error("wj_gemm_bf16: deterministic column sums need a plain output"); return WJ_ERR_ARG; }
+    wj_epilogue_t e2 = *epi;
+    e2.colsum = nullptr;
+    const int rc0 = wj_gemm_bf16(A, W, ldw, L, batch, N, K, &e2, block_n, stream);
+    if (rc0) return rc0;
+    return wj_colsum(epi->out, epi->out_f32 ? 0 : 1, static_cast<int64_t>(L) * batch, N, epi->ld_out, epi->colsum, stream);
+  }
   if (K % BK != 0 || N % 8 != 0) { set_error("wj_gemm_bf16: K must be a multiple of 64 and N of 8 (K=%d N=%d)", K, N); return WJ_ERR_ARG; }
   if (A->seg_width > 0 && (A->seg_width % BK != 0 || K > 4 * A->seg_width)) { set_error("wj_gemm_bf16: bad segment width"); return WJ_ERR_ARG; }
   bool pair = block_n < 0;   // -128 / -256: CTA-pair kernel (256-row tiles, tcgen05 cta_group::2)
@@ -1368,11 +1383,12 @@ extern "C" int wj_gemm_wgrad_bf16(const wj_operand_t* dY, const wj_operand_t* X,
   if (L <= 0 || batch <= 0) return WJ_OK;
   if (M % BM != 0 || N % 64 != 0) { set_error("wj_gemm_wgrad_bf16: M must be a multiple of 128 and N of 64 (M=%d N=%d)", M, N); return WJ_ERR_ARG; }
   bool transposed = false;
+  const bool det = det_on();   // deterministic mode: no operand swap (its epilogue scatters with atomics), split slabs below
   // A 128-column B tile makes the main loop shared-memory-bandwidth bound (two 16 KB operand tiles per 128x128x64
   // block of MMAs); when the OTHER dimension allows 256-wide tiles, compute out^T = X^T dY instead and let the
   // (once-per-CTA) epilogue scatter the transposed tile.
   // (A partial last 256-column tile is fine: TMA zero-fills the missing column atoms, the epilogue masks them.)
-  if (N % 256 != 0 && N % 128 == 0 && M > N && dY->seg_width == 0 && X->seg_width == 0) {
+  if (!det && N % 256 != 0 && N % 128 == 0 && M > N && dY->seg_width == 0 && X->seg_width == 0) {
     const wj_operand_t* t = dY; dY = X; X = t;
     const int tm = M; M = N; N = tm;
     transposed = true;
@@ -1425,7 +1441,20 @@ extern "C" int wj_gemm_wgrad_bf16(const wj_operand_t* dY, const wj_operand_t* X,
   p.dbg = g_gemm_dbg;
   p.accumulate = (accumulate || splits > 1 || transposed) ? 1 : 0;
   p.transpose_out = transposed ? 1 : 0;
-  if ((splits > 1 || transposed) && !accumulate) {
+  float* det_slabs = nullptr;
+  if (det && p.accumulate) {
+    // every token split stores its own [M, N] tile set (plain stores); det_reduce_f32 then adds the slabs in split order
+    int rc2 = WJ_OK;
+    det_slabs = reinterpret_cast<float*>(det_ws(static_cast<size_t>(splits) * M * N * sizeof(float), &rc2));
+    if (rc2) return rc2;
+    p.out = det_slabs; p.ld_out = N; p.accumulate = 0;
+    p.split_stride = static_cast<long long>(M) * N;
+    if (!accumulate) {
+      cudaError_t e = cudaMemset2DAsync(out, ld_out * sizeof(float), 0, (size_t)N * sizeof(float), (size_t)M,
+                                        reinterpret_cast<cudaStream_t>(stream));
+      if (e != cudaSuccess) { set_error("memset2d: %s", cudaGetErrorString(e)); return WJ_ERR_RUNTIME; }
+    }
+  } else if ((splits > 1 || transposed) && !accumulate) {
     // caller asked for overwrite semantics but we reduce with atomics: clear the destination first
     // (rows x columns of the caller's matrix: M x N, or N x M when the operands were swapped)
     cudaError_t e = cudaMemset2DAsync(out, ld_out * sizeof(float), 0, (size_t)(transposed ? M : N) * sizeof(float),
@@ -1436,9 +1465,11 @@ extern "C" int wj_gemm_wgrad_bf16(const wj_operand_t* dY, const wj_operand_t* X,
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   OutMaps om;
   memset(&om, 0, sizeof(om));
-  if (pair) return launch_pair<256, 1>(tmA, tmB, om, p, st);
-  if (block_n == 256) return launch<256, 1>(tmA, tmB, tmB1, om, p, grid, st);
-  return launch<128, 1>(tmA, tmB, tmB1, om, p, grid, st);
+  if (pair) rc = launch_pair<256, 1>(tmA, tmB, om, p, st);
+  else if (block_n == 256) rc = launch<256, 1>(tmA, tmB, tmB1, om, p, grid, st);
+  else rc = launch<128, 1>(tmA, tmB, tmB1, om, p, grid, st);
+  if (rc == WJ_OK && det_slabs != nullptr) rc = det_reduce_f32(det_slabs, splits, M, N, out, ld_out, st);
+  return rc;
 }
 
 // out[b*L + t, n] = epilogue( sum_{s, r} A(s*width + r; t, b) * W[r, col_off[s] + n] ),  W bf16 row-major [R, ldw]:
@@ -1447,6 +1478,14 @@ extern "C" int wj_gemm_dgrad_bf16(const wj_operand_t* A, const void* W, int64_t 
                                   const int32_t* seg_col_off, int L, int batch, int N, int K, const wj_epilogue_t* epi,
                                   int block_n, void* stream) {
   if (L <= 0 || batch <= 0) return WJ_OK;
+  if (epi != nullptr && epi->colsum != nullptr && det_on()) {   // (see wj_gemm_bf16)
+    if (epi->out_rows != nullptr || epi->accumulate) { set_error("wj_gemm_dgrad_bf16: deterministic column sums need a plain output"); return WJ_ERR_ARG; }
+    wj_epilogue_t e2 = *epi;
+    e2.colsum = nullptr;
+    const int rc0 = wj_gemm_dgrad_bf16(A, W, ldw, w_rows, w_cols, seg_col_off, L, batch, N, K, &e2, block_n, stream);
+    if (rc0) return rc0;
+    return wj_colsum(epi->out, epi->out_f32 ? 0 : 1, static_cast<int64_t>(L) * batch, N, epi->ld_out, epi->colsum, stream);
+  }
   if (K % BK != 0 || N % 64 != 0) { set_error("wj_gemm_dgrad_bf16: K must be a multiple of 64 and N of 64 (K=%d N=%d)", K, N); return WJ_ERR_ARG; }
   if (A->seg_width > 0 && (A->seg_width % BK != 0 || K > 4 * A->seg_width)) { set_error("wj_gemm_dgrad_bf16: bad segment width"); return WJ_ERR_ARG; }
   const bool auto_bn = block_n == 0;

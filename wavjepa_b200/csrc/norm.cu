@@ -93,7 +93,9 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
                                                             float* __restrict__ dx_f32, bf16* __restrict__ dx_bf16,
                                                             float* __restrict__ dgamma, float* __restrict__ dbeta,
                                                             float* __restrict__ colsum, int rows_per_warp,
-                                                            const bf16* __restrict__ dy_b, const bf16* __restrict__ x_add) {
+                                                            const bf16* __restrict__ dy_b, const bf16* __restrict__ x_add,
+                                                            float* __restrict__ part) {
+  // part != NULL (deterministic mode): block sums go to part[pass][blockIdx.x][D]; an ordered reduction follows
   // dy (fp32, may be NULL) + dy_b (bf16, may be NULL) = gradient w.r.t. the LayerNorm output: the fp32 residual branch
   // plus the bf16 data gradient of the Linear that consumed the output.  x + x_add = the normalised row (see forward).
   constexpr int PER = D / 32;
@@ -215,7 +217,8 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
       float t = 0.f;
 #pragma unroll
       for (int w = 0; w < 8; ++w) t += s_red[w][c];
-      atomicAdd(dst + c, t);
+      if (part != nullptr) part[(static_cast<size_t>(pass) * gridDim.x + blockIdx.x) * D + c] = t;
+      else atomicAdd(dst + c, t);
     }
   }
 }
@@ -392,16 +395,25 @@ static int launch_ln_bwd(const float* dy, const void* xv, const float* stats, co
   if (rows_per_warp < 1) rows_per_warp = 1;
   const int blocks = (M + rows_per_warp * 8 - 1) / (rows_per_warp * 8);
   const TIn* x = reinterpret_cast<const TIn*>(xv);
+  int rc = WJ_OK;
+  float* part = reinterpret_cast<float*>(det_ws(static_cast<size_t>(3) * blocks * D * sizeof(float), &rc));
+  if (rc) return rc;
   switch (D) {
-    case 128: layernorm_bwd_kernel<128, TIn><<<blocks, 256, 0, st>>>(dy, x, stats, gamma, M, dx_f32, db, dgamma, dbeta, colsum, rows_per_warp, dy_b, x_add); break;
-    case 256: layernorm_bwd_kernel<256, TIn><<<blocks, 256, 0, st>>>(dy, x, stats, gamma, M, dx_f32, db, dgamma, dbeta, colsum, rows_per_warp, dy_b, x_add); break;
-    case 384: layernorm_bwd_kernel<384, TIn><<<blocks, 256, 0, st>>>(dy, x, stats, gamma, M, dx_f32, db, dgamma, dbeta, colsum, rows_per_warp, dy_b, x_add); break;
-    case 512: layernorm_bwd_kernel<512, TIn><<<blocks, 256, 0, st>>>(dy, x, stats, gamma, M, dx_f32, db, dgamma, dbeta, colsum, rows_per_warp, dy_b, x_add); break;
-    case 768: layernorm_bwd_kernel<768, TIn><<<blocks, 256, 0, st>>>(dy, x, stats, gamma, M, dx_f32, db, dgamma, dbeta, colsum, rows_per_warp, dy_b, x_add); break;
-    case 1024: layernorm_bwd_kernel<1024, TIn><<<blocks, 256, 0, st>>>(dy, x, stats, gamma, M, dx_f32, db, dgamma, dbeta, colsum, rows_per_warp, dy_b, x_add); break;
+    case 128: layernorm_bwd_kernel<128, TIn><<<blocks, 256, 0, st>>>(dy, x, stats, gamma, M, dx_f32, db, dgamma, dbeta, colsum, rows_per_warp, dy_b, x_add, part); break;
+    case 256: layernorm_bwd_kernel<256, TIn><<<blocks, 256, 0, st>>>(dy, x, stats, gamma, M, dx_f32, db, dgamma, dbeta, colsum, rows_per_warp, dy_b, x_add, part); break;
+    case 384: layernorm_bwd_kernel<384, TIn><<<blocks, 256, 0, st>>>(dy, x, stats, gamma, M, dx_f32, db, dgamma, dbeta, colsum, rows_per_warp, dy_b, x_add, part); break;
+    case 512: layernorm_bwd_kernel<512, TIn><<<blocks, 256, 0, st>>>(dy, x, stats, gamma, M, dx_f32, db, dgamma, dbeta, colsum, rows_per_warp, dy_b, x_add, part); break;
+    case 768: layernorm_bwd_kernel<768, TIn><<<blocks, 256, 0, st>>>(dy, x, stats, gamma, M, dx_f32, db, dgamma, dbeta, colsum, rows_per_warp, dy_b, x_add, part); break;
+    case 1024: layernorm_bwd_kernel<1024, TIn><<<blocks, 256, 0, st>>>(dy, x, stats, gamma, M, dx_f32, db, dgamma, dbeta, colsum, rows_per_warp, dy_b, x_add, part); break;
     default: set_error("layernorm_bwd: unsupported D=%d", D); return WJ_ERR_ARG;
   }
-  return check_launch("layernorm_bwd");
+  rc = check_launch("layernorm_bwd");
+  if (part != nullptr) {   // deterministic mode: add the block sums in block order
+    float* dst[3] = {dgamma, dbeta, colsum};
+    for (int pass = 0; pass < 3 && rc == WJ_OK; ++pass)
+      if (dst[pass] != nullptr) rc = det_reduce_f32(part + static_cast<size_t>(pass) * blocks * D, blocks, 1, D, dst[pass], D, st);
+  }
+  return rc;
 }
 
 extern "C" int wj_layernorm_bwd(const float* dy, const void* x, int x_is_bf16, const float* stats, const float* gamma,

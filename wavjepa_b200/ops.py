@@ -123,6 +123,25 @@ def gemm_wgrad(dy: Operand, x: Operand, L: int, batch: int, out: torch.Tensor, *
                                  C.c_int64(ld), 1 if accumulate else 0, splits, _stream()))
 
 
+_det_ws: Optional[torch.Tensor] = None
+
+
+def set_deterministic(on: bool, workspace_bytes: int = 256 << 20, device=None) -> None:
+    """Bit-reproducible reductions (wj_set_deterministic): per-block / per-split partial results in a workspace plus a
+    fixed-order second pass instead of floating-point atomics.  Costs a few percent of step time; all calls must then be
+    issued on one stream.  The reference has no equivalent switch (torch's own deterministic-algorithms flag is the
+    closest); off by default."""
+    global _det_ws
+    lib = _lib.load()
+    if not on:
+        check(lib.wj_set_deterministic(None, C.c_size_t(0)))
+        _det_ws = None
+        return
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    _det_ws = torch.empty(workspace_bytes, dtype=torch.uint8, device=dev)
+    check(lib.wj_set_deterministic(C.c_void_p(_det_ws.data_ptr()), C.c_size_t(workspace_bytes)))
+
+
 def gemm_option(name: str, value: int) -> None:
     """Routing switch of the GEMM entry points (A/B measurements, tests): 'pair_wgrad' / 'pair_dgrad' = 1 (default) lets
     the weight- / data-gradient GEMMs use the CTA-pair kernel where the shape allows, 0 keeps them on single CTAs."""
