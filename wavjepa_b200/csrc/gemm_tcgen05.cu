@@ -1503,7 +1503,8 @@ extern "C" int wj_gemm_dgrad_bf16(const wj_operand_t* A, const void* W, int64_t 
                        epi->out2 == nullptr && ((epi->act == 0 && epi->colsum == nullptr) || pair_gelu) && epi->ld_out % 8 == 0 &&
                        reinterpret_cast<uintptr_t>(epi->out) % 16 == 0 && N % 256 == 0;
   if (pair && !(pair_ok && block_n == 256)) { set_error("wj_gemm_dgrad_bf16: the CTA-pair kernel takes plain bf16 outputs with N %% 256 == 0"); return WJ_ERR_ARG; }
-  if (auto_bn && g_pair_dgrad && pair_ok && K >= 768 && static_cast<long long>(L) * batch >= 4096) {
+  // (K >= 512 for plain outputs: +4 % on the K = 512 conv data gradient; the GELU-backward form loses there, 645 vs 738)
+  if (auto_bn && g_pair_dgrad && pair_ok && K >= (pair_gelu ? 768 : 512) && static_cast<long long>(L) * batch >= 4096) {
     pair = true;
     block_n = 256;
   }

@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const TIn* __restric
 // dx = rstd * (g*dy - mean(g*dy) - xhat * mean(g*dy*xhat));  dgamma += sum_rows dy*xhat;  dbeta += sum_rows dy
 // Optionally colsum += sum_rows dx (bias gradient of the Linear that produced x's non-residual branch).
 template <int D, typename TIn>
-__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restrict__ dy, const TIn* __restrict__ x,
+__global__ void __launch_bounds__(256, (D == 384 || D == 256) ? 2 : 1) layernorm_bwd_kernel(const float* __restrict__ dy, const TIn* __restrict__ x,
                                                             const float* __restrict__ stats,
                                                             const float* __restrict__ gamma, int M,
                                                             float* __restrict__ dx_f32, bf16* __restrict__ dx_bf16,
@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
   // keeps two rows of HBM requests in flight (only one 8-warp block fits an SM there, and one row per warp in flight
   // left the 19 906-row launches at half the bandwidth of the long ones).  Narrower rows keep two blocks per SM instead
   // (the second row buffer would cost the second block).
-  constexpr bool PIPE = D == 768;   // (D = 1024 would spill)
+  constexpr bool PIPE = D == 768 || D == 384;   // (D = 1024 would spill; D = 384 keeps its two blocks per SM: launch bounds)
   auto load_row = [&](int row, float (&xs)[PER], float (&d)[PER], float& mean, float& rstd) {
     const size_t base = static_cast<size_t>(row) * D;
     mean = stats[2 * row];
