@@ -19,4 +19,9 @@ timeout 400 ncu --set full --clock-control none --import-source on -k regex:conv
     -o $O/conv0_bwd python scripts/profile_step.py --ncu > $O/ncu_conv0_bwd.log 2>&1
 timeout 400 ncu --set full --clock-control none --import-source on -k regex:layernorm_bwd_kernel -c 4 \
     -o $O/ln_bwd python scripts/profile_step.py --ncu > $O/ncu_ln_bwd.log 2>&1
+timeout 300 python scripts/determinism_probe.py > $O/determinism.json 2> $O/determinism.err
+timeout 300 python scripts/determinism_probe.py 16 --det > $O/determinism_det.json 2> $O/determinism_det.err
+timeout 300 python bench.py --deterministic --no-cpu-baseline --no-gpu-baseline > $O/bench_det.json 2> $O/bench_det.err
+timeout 900 compute-sanitizer --tool memcheck python scripts/sanitize_small.py > $O/sanitizer_memcheck.log 2>&1
+tail -3 $O/sanitizer_memcheck.log
 tail -3 $O/pytest_gpu.log; tail -2 $O/smoke.log; cat $O/bench_n1.json | cut -c1-400
