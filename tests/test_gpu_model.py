@@ -172,6 +172,27 @@ def test_train_step_run_to_run_difference_is_summation_order_only():
         assert (ga - gb).norm().item() <= 1e-5 * gb.norm().item() + 1e-12, n_
 
 
+def test_host_known_padding_pattern_equals_the_device_mask_path():
+    """get_audio_representation(host_mask=...) (the HEAR chunk geometry, known on the host, repeating per clip) builds its
+    packed index without a device read-back and must give exactly what the padding_mask path gives."""
+    cfg = jo.Cfg()
+    m = build_model(cfg, jo.make_state_dict(cfg, seed=5))
+    T = m.total_patches
+    P, reps = 5, 3
+    pat = torch.zeros(P, T, dtype=torch.bool)
+    pat[3, 150:] = True                       # a partly padded chunk
+    pat[4, :] = True                          # a chunk that lies entirely in the padding
+    pat[1, 20:40] = True                      # (not prefix-shaped: the index is general)
+    audio = torch.randn(P * reps, 1, m.target_length, device=DEV).bfloat16()
+    a = m.get_audio_representation(audio, pat.repeat(reps, 1).to(DEV))
+    b = m.get_audio_representation(audio, None, host_mask=pat.numpy())
+    assert torch.equal(a, b)
+    b2 = m.get_audio_representation(audio, None, host_mask=pat.numpy())     # cached index
+    assert torch.equal(a, b2)
+    with pytest.raises(ValueError):
+        m.get_audio_representation(audio[:7], None, host_mask=pat.numpy())
+
+
 def test_deterministic_mode_is_bit_reproducible():
     """ops.set_deterministic(True): every reduction that ends in floating-point atomics takes the workspace + fixed-order
     path instead, so two identical models stepped on the same inputs end with bit-identical gradients, parameters, EMA

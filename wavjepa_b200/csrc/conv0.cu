@@ -393,12 +393,16 @@ __global__ void __launch_bounds__(256) conv0_bwd_finalize_kernel(Conv0Args a, co
     if (b < a.B && c_ok) {
       const float mean = stats[(static_cast<size_t>(b) * a.C + c) * 2], rstd = stats[(static_cast<size_t>(b) * a.C + c) * 2 + 1];
       const double* r0 = red + static_cast<size_t>(b) * nslab * (2 + NA) * a.C + c;
-      auto rd = [&](size_t off) {   // sum over the instance's slabs, in slab order
-        double v = 0.0;
-        for (int sl = 0; sl < nslab; ++sl) v += r0[static_cast<size_t>(sl) * (2 + NA) * a.C + off];
-        return v;
-      };
-      const float S1 = static_cast<float>(rd(0)), S2 = static_cast<float>(rd(a.C));
+      // the 2 + NA sums of this (instance, channel): slabs added in slab order, the loads of one slab issued together
+      double rv[2 + NA];
+#pragma unroll
+      for (int i = 0; i < 2 + NA; ++i) rv[i] = 0.0;
+      for (int sl = 0; sl < nslab; ++sl) {
+        const double* rs = r0 + static_cast<size_t>(sl) * (2 + NA) * a.C;
+#pragma unroll
+        for (int i = 0; i < 2 + NA; ++i) rv[i] += rs[static_cast<size_t>(i) * a.C];
+      }
+      const float S1 = static_cast<float>(rv[0]), S2 = static_cast<float>(rv[1]);
       const float k1 = S1 * invL, k2 = S2 * invL * rstd, sc = rstd * ga;
 #pragma unroll
       for (int i = 0; i < NA; ++i) {
@@ -406,8 +410,7 @@ __global__ void __launch_bounds__(256) conv0_bwd_finalize_kernel(Conv0Args a, co
 #pragma unroll
         for (int j = 0; j < NA; ++j) rw = fmaf(s_m[by][NA + i * NA + j], w[j], rw);
         const float q = rw - mean * s_m[by][i];            // Q[i] / rstd
-        acc[i] += sc * static_cast<float>(rd(static_cast<size_t>(2 + i) * a.C) - static_cast<double>(k1) * s_m[by][i] -
-                                          static_cast<double>(k2) * q);
+        acc[i] += sc * (static_cast<float>(rv[2 + i]) - k1 * s_m[by][i] - k2 * q);
       }
       acc[NA] += S2;
       acc[NA + 1] += S1;

@@ -72,16 +72,19 @@ def embed_chunks(model: JEPA, a: torch.Tensor, gain: Optional[torch.Tensor], uni
     starts = (torch.arange(n_chunks, device=dev, dtype=torch.int32) * unit).repeat(B)
     x16 = torch.empty(B * n_chunks, C, unit, device=dev, dtype=torch.bfloat16)
     ops.crop_norm(a, starts, n_chunks, unit, x16, None, gain=gain)
-    mask = torch.zeros(B, max(total_steps, n_chunks * steps), dtype=torch.bool, device=dev)
-    mask[:, cut_off:total_steps] = True
-    mask = mask[:, :n_chunks * steps].reshape(B * n_chunks, steps)
+    # The padding mask depends on the geometry only (the same for every clip), so it is built on the HOST and handed over as
+    # a pattern that repeats every n_chunks sequences: the packed-token index then needs no device read-back, and calls
+    # can be issued back to back without a host synchronisation.
+    mask = torch.zeros(max(total_steps, n_chunks * steps), dtype=torch.bool)
+    mask[cut_off:total_steps] = True
+    mask = mask[:n_chunks * steps].reshape(n_chunks, steps)
     if channel_tokens > 1:
         # WavJEPA-Nat (hear_api/runtime_natjepa.py:142-147): the model emits channel-major tokens [c0 t0.., c1 t0..]; the
         # time mask is repeated "B E -> B (C E)" and the per-channel embeddings are averaged
-        emb = model.get_audio_representation(x16, mask.repeat(1, channel_tokens))   # [B*n_chunks, C*steps, D]
+        emb = model.get_audio_representation(x16, None, host_mask=mask.repeat(1, channel_tokens).numpy())   # [B*n_chunks, C*steps, D]
         emb = emb.view(B * n_chunks, channel_tokens, steps, -1).mean(dim=1)
     else:
-        emb = model.get_audio_representation(x16, mask)          # [B*n_chunks, steps, D] fp32
+        emb = model.get_audio_representation(x16, None, host_mask=mask.numpy())   # [B*n_chunks, steps, D] fp32
     return emb.reshape(B, n_chunks * steps, -1)[:, :cut_off], cut_off
 
 

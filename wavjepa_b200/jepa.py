@@ -856,10 +856,39 @@ class JEPA(_ModuleBase):
 
     # ------------------------------------------------------------------------------------------- inference
     @torch.no_grad()
-    def get_audio_representation(self, audio: torch.Tensor, padding_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+    def _periodic_index(self, host_mask, B: int, T: int):
+        """Packed-row index of a padding mask that is known on the HOST and repeats every P sequences (the HEAR chunk
+        geometry: the same for every clip): (ctx_rows, cu, Nc, max_n) without reading anything back from the device,
+        cached per (pattern, batch)."""
+        import numpy as np
+        hm = np.ascontiguousarray(np.asarray(host_mask, dtype=bool))
+        if hm.ndim != 2 or hm.shape[1] != T or B % hm.shape[0] != 0:
+            raise ValueError(f"host_mask must be [P, {T}] with P dividing the batch ({B}); got {hm.shape}")
+        key = (hm.tobytes(), hm.shape[0], B, str(self.device))
+        cache = self.__dict__.setdefault("_periodic_index_cache", {})
+        if key not in cache:
+            P, reps = hm.shape[0], B // hm.shape[0]
+            vis = ~hm
+            n_per = vis.sum(1)
+            rows_1 = np.flatnonzero(vis.reshape(-1)).astype(np.int64)
+            cu_1 = np.concatenate([[0], np.cumsum(n_per)]).astype(np.int64)
+            dev = self.device
+            rep = torch.arange(reps, device=dev, dtype=torch.int64)[:, None]
+            rows = (torch.from_numpy(rows_1).to(dev)[None, :] + rep * (P * T)).reshape(-1).to(torch.int32)
+            cu = (torch.from_numpy(cu_1[:-1]).to(dev)[None, :] + rep * int(rows_1.size)).reshape(-1)
+            cu = torch.cat([cu, torch.tensor([reps * int(rows_1.size)], device=dev)]).to(torch.int32)
+            if len(cache) >= 16:
+                cache.clear()
+            cache[key] = (rows.contiguous(), cu.contiguous(), reps * int(rows_1.size), int(n_per.max()) if n_per.size else 0)
+        return cache[key]
+
+    def get_audio_representation(self, audio: torch.Tensor, padding_mask: Optional[torch.Tensor] = None,
+                                 host_mask=None) -> torch.Tensor:
         """reference wavjepa/jepa.py:456-467: student encoder (incl. final norm) features [B, T, D] fp32.  Tokens
         hidden by padding_mask (True) are excluded as keys exactly like the reference's key-padding mask; their own
-        output rows (which the callers cut off, hear_api/runtime.py:141-142) are returned as zeros."""
+        output rows (which the callers cut off, hear_api/runtime.py:141-142) are returned as zeros.
+        host_mask (optional, CPU bool [P, T], P | B): the same padding mask given as a pattern known on the host that
+        repeats every P sequences -- the packed index then needs no device read-back (padding_mask is ignored)."""
         self.eval()
         self._ensure_ready()
         self._sync_weights()
@@ -869,7 +898,7 @@ class JEPA(_ModuleBase):
         T, D = self.total_patches, self.encoder_embedding_dim
         local32, _ = self._local_features(x16, save=False)
         p32 = lambda n: self._view(self._flat_p, n)
-        if padding_mask is None:
+        if padding_mask is None and host_mask is None:
             cu = torch.arange(0, (B + 1) * T, T, device=dev, dtype=torch.int32)
             x16r = torch.empty(B * T, D, device=dev, dtype=torch.bfloat16)
             ops.gather_rows(local32, None, B * T, None, x16r)
@@ -878,16 +907,19 @@ class JEPA(_ModuleBase):
             ops.layernorm_fwd(xs32, p32("encoder.norm.weight"), p32("encoder.norm.bias"), self.encoder.norm.eps, out,
                               None, None, None)
             return out.view(B, T, D)
-        pm = padding_mask.to(dev).reshape(B, 1, T).contiguous()
-        mi = ops.mask_indices(pm.view(B, T), torch.zeros_like(pm), pm)
-        Nc = mi.Nc
+        if host_mask is not None:
+            ctx_rows, cu_c, Nc, max_nc = self._periodic_index(host_mask, B, T)
+        else:
+            pm = padding_mask.to(dev).reshape(B, 1, T).contiguous()
+            mi = ops.mask_indices(pm.view(B, T), torch.zeros_like(pm), pm)
+            ctx_rows, cu_c, Nc, max_nc = mi.ctx_rows, mi.cu_c, mi.Nc, mi.max_nc
         xc32 = torch.empty(Nc, D, device=dev)
         xc16 = torch.empty(Nc, D, device=dev, dtype=torch.bfloat16)
-        ops.gather_rows(local32, mi.ctx_rows, Nc, xc32, xc16)
-        xs32, _, _ = self._enc_stack.forward(self._W_enc, xc32, xc16, mi.cu_c, B, mi.max_nc, False)
+        ops.gather_rows(local32, ctx_rows, Nc, xc32, xc16)
+        xs32, _, _ = self._enc_stack.forward(self._W_enc, xc32, xc16, cu_c, B, max_nc, False)
         packed = torch.empty(Nc, D, device=dev)
         ops.layernorm_fwd(xs32, p32("encoder.norm.weight"), p32("encoder.norm.bias"), self.encoder.norm.eps, packed,
                           None, None, None)
         out = torch.zeros(B * T, D, device=dev)
-        ops.scatter_rows(packed, mi.ctx_rows, Nc, out)
+        ops.scatter_rows(packed, ctx_rows, Nc, out)
         return out.view(B, T, D)
