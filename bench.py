@@ -231,7 +231,9 @@ def run_native(args):
     model.reserve_workspace((130 if nat else 80) << 30)   # setup: the activation pool of a 512-instance step exists up front
     model.global_step = 1000          # lr(0) == 0 (warm-up from 0): start inside the warm-up so AdamW moves weights
     if world > 1:
-        model.attach_data_parallel(BucketedAllReduce())
+        # (WJ_BUCKET_MB: measurement override of the gradient bucket size)
+        bucket_mb = int(os.environ.get("WJ_BUCKET_MB", "0"))
+        model.attach_data_parallel(BucketedAllReduce(bucket_bytes=bucket_mb << 20) if bucket_mb else BucketedAllReduce())
     C_in = 2 if nat else 1
     masker = w.TimeInverseBlockMasker(**MASKER, channel_based_masking=nat, seed=1234, row0=rank * (1 << 24), device=dev)
     B = CLIPS * CROPS
@@ -324,6 +326,21 @@ def run_native(args):
         dp_check = {"param_checksum_max_minus_min": float((hi - lo).abs().max().item()),
                     "what": "fp64 sum of student parameters, of EMA-teacher parameters and integer sum of the parameter "
                             "bit patterns after all timed steps: max - min over ranks (0 = replicas bit-identical)"}
+        if dp_check["param_checksum_max_minus_min"] != 0.0:
+            # name what differs: per-tensor bit-pattern sums of parameters, Adam moments and the last all-reduced gradient
+            names = list(model._train_names)
+            per = torch.stack([torch.stack([model._view(buf, n_).view(torch.int32).long().sum() for n_ in names])
+                               for buf in (model._flat_p, model._adam_m, model._adam_v, model._flat_g)])
+            allr = [torch.empty_like(per) for _ in range(world)]
+            dist.all_gather(allr, per)
+            A = torch.stack(allr)                                # [world, 4, n_tensors]
+            diff = (A != A[0]).any(0)
+            dp_check["components_max_minus_min"] = [float(v) for v in (hi - lo).abs().tolist()]
+            for k, lab in enumerate(("params", "adam_m", "adam_v", "last_grads")):
+                idx = torch.nonzero(diff[k]).flatten().tolist()
+                dp_check[f"{lab}_tensors_differ"] = len(idx)
+                dp_check[f"{lab}_first"] = [names[i] for i in idx[:6]]
+            dp_check["ranks_differing_from_rank0"] = [r for r in range(world) if bool((A[r] != A[0]).any())]
 
     # ---------------------------------------------------------------- per-kernel attribution (outside the timed region)
     # every rank runs this extra step (its gradient all-reduce is a collective); only rank 0 brackets its launches

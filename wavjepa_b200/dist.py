@@ -13,8 +13,12 @@ from __future__ import annotations
 
 from typing import List, Optional
 
+import os
+
 import torch
 import torch.distributed as dist
+
+_DRAIN = os.environ.get("WJ_DDP_NO_DRAIN") != "1"   # (opt-out for measurements)
 
 
 class BucketedAllReduce:
@@ -57,6 +61,13 @@ class BucketedAllReduce:
         if lo >= self._hi:
             return
         chunk = self._flat[lo:self._hi]
+        if _DRAIN and chunk.is_cuda:
+            # The bucket is handed to NCCL only after the compute stream has drained up to here.  With the event-based
+            # ordering alone (what all_reduce(async_op=True) sets up between the current stream and NCCL's) two of two
+            # 8-GPU runs ended with one rank's weight gradients of the first bucket differing from the other ranks'
+            # (bench.py dp_check names the tensors); with the drain the replicas stayed bit-identical and the step was
+            # no slower (107.0 vs 107.9-108.2 ms at N = 8: the host is a whole backward ahead of the GPU anyway).
+            torch.cuda.current_stream().synchronize()
         self._handles.append(dist.all_reduce(chunk, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
         self.launched.append((lo, self._hi))
         self._hi = lo
