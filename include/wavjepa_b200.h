@@ -223,7 +223,7 @@ int wj_target_combine(const float* const* xs, const float* const* rowsums, int n
 /* Variable-length multi-head attention over packed tokens: qkv bf16 [tokens, 3*D] (q|k|v), sequences given by
  * cu_seqlens [n_seqs+1], softmax(q k^T / sqrt(D/H)) v, head dim 32 or 64.  out bf16 [tokens, D];
  * lse2 fp32 [tokens, H] = log2-sum-exp2 of the scaled logits (saved for the backward; may be NULL).
- * total_tokens = rows of qkv.  Forward: sequences of <= 256 tokens run on tcgen05 (S = Q K^T and O = P V as UMMAs with
+ * total_tokens = rows of qkv.  Forward: sequences of <= 512 tokens run on tcgen05 (S = Q K^T and O = P V as UMMAs with
  * TMEM accumulators, P handed back through TMEM, softmax one query row per thread); longer ones on the mma.sync kernel.
  * Backward: head dim 32 with <= 128 tokens runs on tcgen05 (S, dP, dV, dK, dQ as UMMAs); everything else on mma.sync.
  * Reference: F.scaled_dot_product_attention with key_padding_mask inside nn.MultiheadAttention. */

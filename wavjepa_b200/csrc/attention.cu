@@ -366,7 +366,7 @@ extern "C" int wj_attn_varlen_fwd(const void* qkv_bf16, const int* cu_seqlens, i
   const int dh = D / H;
   if (D % H != 0 || (dh != 32 && dh != 64)) { set_error("wj_attn_varlen_fwd: head dim must be 32 or 64 (D=%d H=%d)", D, H); return WJ_ERR_ARG; }
   {
-    // sequences of <= 128 tokens: tcgen05 kernel (attention_tc.cu); longer ones: the mma.sync kernel below
+    // sequences of <= 512 tokens: tcgen05 kernels (attention_tc.cu); longer ones: the mma.sync kernel below
     const int rc = wj::attn_fwd_tc_launch(qkv_bf16, cu_seqlens, n_seqs, max_len, total_tokens, D, H, out_bf16, lse2, WJ_STREAM(stream));
     if (rc <= 0) return rc;
   }
