@@ -174,6 +174,28 @@ def test_schedules_and_geometry():
     m.global_step = 0
 
 
+def test_hear_padding_pattern_is_a_function_of_the_geometry_only():
+    """hear.embed_chunks hands the key-padding mask to the model as a HOST pattern that repeats per clip (no device
+    read-back).  It must be the reference's mask (hear_api/runtime.py:19-35,125-131: frames [cut_off, total_steps) hidden,
+    chunked into n_chunks x steps) for every clip length, including exact multiples of the unit and sub-unit clips."""
+    from wavjepa_b200.hear import hear_geometry
+
+    unit, steps, sr = 32159, 200, 16000
+    for n_samples in (160000, 32159, 64318, 5000, 47999, 96477, 100000):
+        pad, n_chunks, cut_off, total_steps = hear_geometry(n_samples, unit, sr, steps)
+        # the reference's construction, per clip
+        ref = torch.zeros(1, total_steps, dtype=torch.bool)
+        ref[:, cut_off:] = True
+        ref = torch.nn.functional.pad(ref, (0, max(0, n_chunks * steps - total_steps)))[:, :n_chunks * steps]
+        ref = ref.reshape(n_chunks, steps)
+        # ours (wavjepa_b200/hear.py: embed_chunks)
+        mask = torch.zeros(max(total_steps, n_chunks * steps), dtype=torch.bool)
+        mask[cut_off:total_steps] = True
+        mask = mask[:n_chunks * steps].reshape(n_chunks, steps)
+        assert torch.equal(mask, ref), n_samples
+        assert 0 < cut_off <= total_steps and n_chunks * unit == n_samples + pad
+
+
 def test_no_cpu_fallback():
     from wavjepa_b200 import _lib
 
